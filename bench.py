@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- Gibbs-generation throughput of the 2-layer scDBM (BASELINE.json
+config "Generation of 1M synthetic cells by Gibbs sampling from the 2-layer
+scDBM"): metric = Gibbs sweeps x chains / sec.
+
+  python bench.py --gpus N --steps K --warmup W            # CUDA path (this repo)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference
+
+One "step" = one `samples(dbm, chains; burnin)` generation pass: particle
+initialisation + `burnin` synchronous Gibbs sweeps of all layers over
+`chains` chains (src/gibbssampling.jl:646-650,153-182).  Chains are sharded
+over GPUs with no collective (weak scaling: `--chains` per GPU).
+
+The reference is Julia and cannot run here; `--impl reference` times the
+NumPy/OpenBLAS restatement (oracle/) on the host cores, one worker process per
+core over disjoint chain shards (the reference's own `batchparallelized`
+pattern, src/misc.jl:38-47).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+UNITS = [2000, 256, 64]
+MODEL_SEED = 3
+SEED = 20261019
+
+
+def make_model(units=UNITS, seed=MODEL_SEED, r=0.5):
+    """Random valid parameters of the C3 model: W1 = -U(5e-4, 2e-3),
+    a = log(m/(m+r)) with 10x-like gene means, upper W ~ N(0, 1/fan_in)."""
+    g = np.random.default_rng(seed)
+    V = units[0]
+    m = np.clip(np.exp(g.normal(-1.5, 1.5, V)), 1e-3, 50.0)
+    rr = np.full(V, r)
+    layers = [dict(weights=-g.uniform(5e-4, 2e-3, (V, units[1])), visbias=np.log(m / (m + rr)),
+                   hidbias=np.zeros(units[1]), inversedispersion=rr)]
+    for i in range(1, len(units) - 1):
+        layers.append(dict(weights=g.normal(0, 1.0 / np.sqrt(units[i]), (units[i], units[i + 1])),
+                           visbias=g.normal(0, 0.1, units[i]), hidbias=g.normal(0, 0.1, units[i + 1])))
+    return layers
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"tflops_burst": p["bf16_tflops"], "tflops_sustained": p["bf16_tflops_sustained"],
+                "hbm_gbs": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[1]) for r in self.rows)
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------ CUDA arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    pkg = entry.load_package()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n, burnin = args.chains, args.burnin
+    layers = make_model()
+    ctx = pkg.Context(local, SEED)
+    host_model = [pkg.NegativeBinomialBernoulliRBM(**layers[0]), pkg.BernoulliRBM(**layers[1])]
+    dm = pkg.DeviceModel.from_host(host_model, ctx)
+    row_offset = rank * n
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def step(p):
+        p.init(False)
+        pkg.gibbssample_(p, dm, burnin)
+
+    p = pkg.DeviceParticles(dm, n, row_offset)
+    for _ in range(args.warmup):
+        step(p)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ctx.launch_count(reset=True)
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step(p)
+    ms = ctx.timer_stop()
+    launches = ctx.launch_count()
+    tc_launches = int(ctx.get("tc_launches"))
+    barrier()
+    sampler.stop_flag = True
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * n * burnin * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel: the fused NB down-sweep (v | h1), timed alone
+    h1, vout = p.layer(1), pkg.Mat(ctx, n, UNITS[0], pkg.MAT_COUNT)
+    lib = pkg.lib()
+    reps = 5
+    for _ in range(2):
+        pkg._lib.check(lib.scdbm_visible(dm.h, 0, h1.h, vout.h, 1.0, pkg.OUT_SAMPLE, 12345, None, 0))
+    ctx.timer_start()
+    for i in range(reps):
+        pkg._lib.check(lib.scdbm_visible(dm.h, 0, h1.h, vout.h, 1.0, pkg.OUT_SAMPLE, 1000 + i, None, 0))
+    k_ms = ctx.timer_stop() / reps
+    pk = peaks()
+    flops = 2.0 * n * UNITS[1] * UNITS[0]
+    achieved = flops / (k_ms * 1e-3) / 1e12
+    roofline = {"kernel": "fused NB down-sweep GEMM (v|h1: tcgen05/SIMT GEMM + NB-mean + Philox NB draw)",
+                "bound": "tensor", "achieved": achieved, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tflops_burst"], "traffic": None, "peak_source": pk["source"] + ", burst (kernel timed alone)",
+                "launch_ms": k_ms, "flops_per_launch": flops, "nb_draws_per_sec": n * UNITS[0] / (k_ms * 1e-3),
+                "note": "sampled sweeps are bound by the draw epilogue (issue/MUFU), not by the tensor pipe; see DESIGN.md"}
+    del vout
+
+    # ---- end to end through the public API: host model in, host uint16 cells out
+    e2e = None
+    if rank == 0 or world > 1:
+        out = torch.empty((n, UNITS[0]), dtype=torch.uint16, pin_memory=True).numpy()
+        h2d = sum(a.nbytes for l in layers for a in l.values())
+        d2h = out.nbytes
+
+        def e2e_step():
+            m = pkg.DeviceModel.from_host(host_model, ctx)          # H2D: parameters
+            q = pkg.sampleparticles(m, n, burnin, row_offset, device=True)
+            q.layer(0).to_host_u16(out)                               # D2H: generated cells
+            q.close()
+            m.close()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        ksteps = max(1, min(args.steps, 3))
+        for _ in range(ksteps):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n * burnin * ksteps / float(dt.item()), "unit": "sweeps*chains/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": ksteps,
+               "cells_per_sec": world * n * ksteps / float(dt.item())}
+
+    line = {
+        "metric": "Gibbs sweeps x chains / sec (synthetic-cell generation, 2-layer scDBM)",
+        "value": value, "unit": "sweeps*chains/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16x2-split operands, fp32 accumulate/epilogue", "data": "synthetic (random valid parameters, seed 3)",
+        "config": {"workload": f"C3: samples(dbm {UNITS[0]}->{UNITS[1]}->{UNITS[2]}, {n} chains per GPU, burnin={burnin}); "
+                               "chains sharded over GPUs, no collective",
+                   "chains_per_gpu": n, "burnin": burnin, "units": UNITS,
+                   "l2": "inputs larger than L2 (particle state %.1f GB per GPU)" % (n * (2048 * 2 * 2 + 256 * 2 + 64 * 2) * 2 / 1e9)},
+        "cells_per_sec": value / burnin,
+        "gpu_launches": launches, "tc_launches": tc_launches,
+        "e2e": e2e, "roofline": roofline, "clocks": sampler.summary(),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(layers, burnin=5, chains=args.cpu_chains, workers=os.cpu_count() or 1)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------- CPU baseline arm
+def _cpu_worker(job):
+    layers, chains, burnin, row_offset = job
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import model as om, philox as px
+    dbm = [om.NegativeBinomialBernoulliRBM(**layers[0]), om.BernoulliRBM(**layers[1])]
+    t0 = time.perf_counter()
+    om.sampleparticles(dbm, chains, px.Rng(SEED), burnin, row_offset=row_offset)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(layers, burnin, chains, workers):
+    """The oracle (NumPy/OpenBLAS restatement of the reference, not Julia) on a
+    bounded sample: `chains` chains x `burnin` sweeps per worker process."""
+    import multiprocessing as mp
+    jobs = [(layers, chains, burnin, w * chains) for w in range(workers)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(workers) as pool:
+        pool.map(_cpu_worker, jobs)
+    dt = time.perf_counter() - t0
+    return {"value": workers * chains * burnin / dt, "unit": "sweeps*chains/s", "cores": workers, "kind": "port",
+            "sample": f"{workers} worker processes x {chains} chains x {burnin} sweeps of the same 2000->256->64 model "
+                      f"(CPU restatement of the reference in NumPy/OpenBLAS, not Julia); wall {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    layers = make_model()
+    workers = os.cpu_count() or 1
+    # warm-up and steps each run a bounded sample; keep the whole run within a few minutes
+    chains, burnin = args.cpu_chains, 5
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(layers, burnin, max(chains // 4, 8), workers)
+    t0 = time.perf_counter()
+    vals = [cpu_baseline(layers, burnin, chains, workers) for _ in range(args.steps)]
+    dt = time.perf_counter() - t0
+    v = float(np.mean([x["value"] for x in vals]))
+    cb = dict(vals[-1])
+    cb["value"] = v
+    line = {"impl": "reference", "metric": "Gibbs sweeps x chains / sec (synthetic-cell generation, 2-layer scDBM)",
+            "value": v, "unit": "sweeps*chains/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic (random valid parameters, seed 3)",
+            "config": {"workload": f"C3 bounded sample: {workers} x {chains} chains x {burnin} sweeps per step, same model",
+                       "units": UNITS},
+            "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": "sweeps*chains/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=1_000_000, help="chains per GPU (C3: 1M cells)")
+    ap.add_argument("--burnin", type=int, default=50)
+    ap.add_argument("--cpu-chains", type=int, default=1500, help="chains per worker in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,208 @@
+/* libscdbm_b200 -- C ABI of the B200-native Gibbs / CD / PCD / mean-field / AIS
+ * hot path of scDBM.jl.
+ *
+ * The reference (pure Julia) has no FFI; its seams are generic functions that
+ * mutate caller-owned Matrix{Float64}.  Each entry point below names the
+ * reference function (file:line under the reference checkout) it replaces.
+ * A Julia `ccall` binding and the Python `ctypes` binding are shown in
+ * INTEGRATION.md; the Python mirror lives in scdbm.jl_b200/.
+ *
+ * Conventions
+ *  - every function returns int32 status: 0 ok, <0 error class (below);
+ *    scdbm_last_error() returns a thread-local message.
+ *  - opaque handles are library-owned and released by *_destroy.
+ *  - host matrices are COLUMN-MAJOR Float64 with explicit leading dimension
+ *    (a Julia Matrix{Float64} or a NumPy order='F' array passes its pointer
+ *    unchanged); host buffers are never retained after return.
+ *  - logical shapes follow the reference: states (nsamples x nunits), weights
+ *    (nvisible x nhidden) (src/bmtypes.jl:17-21,85-92, src/gibbssampling.jl:1-9).
+ *  - work is asynchronous on the context's stream; downloads and scdbm_sync
+ *    synchronise.  One host thread per context.
+ *  - randomness is counter-based Philox4x32-10 keyed by (seed; stream = layer |
+ *    purpose; clock tick; global row; column), hence independent of launch
+ *    geometry and of how chains are sharded over GPUs.
+ */
+#ifndef SCDBM_B200_H
+#define SCDBM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCDBM_OK 0
+#define SCDBM_EINVAL (-1)   /* bad argument / shape mismatch (Julia: error(...)/DimensionMismatch) */
+#define SCDBM_ECUDA (-2)    /* CUDA runtime failure */
+#define SCDBM_ENOMEM (-3)   /* device allocation failed */
+#define SCDBM_EUNSUP (-4)   /* shape/engine combination not supported */
+
+/* visible unit family of the first RBM (src/bmtypes.jl:17,85) */
+#define SCDBM_VIS_BERNOULLI 0
+#define SCDBM_VIS_NEGBIN 1
+
+/* matrix kinds (device storage, see DESIGN.md "data layout") */
+#define SCDBM_MAT_BINARY 0
+#define SCDBM_MAT_COUNT 1
+#define SCDBM_MAT_REAL 2
+
+/* what a conditional operator returns */
+#define SCDBM_OUT_INPUT 0      /* hiddeninput! / visibleinput!                */
+#define SCDBM_OUT_POTENTIAL 1  /* hiddenpotential! / visiblepotential!        */
+#define SCDBM_OUT_SAMPLE 2     /* samplehidden! / samplevisible!              */
+
+/* engines (ctx option "engine") */
+#define SCDBM_ENGINE_AUTO 0
+#define SCDBM_ENGINE_SIMT 1    /* CUDA-core FFMA kernel (tiny / unaligned shapes) */
+#define SCDBM_ENGINE_TC 2      /* tcgen05 + TMA + TMEM kernel                     */
+
+typedef struct scdbm_ctx scdbm_ctx;
+typedef struct scdbm_model scdbm_model;
+typedef struct scdbm_mat scdbm_mat;
+typedef struct scdbm_particles scdbm_particles;
+typedef struct scdbm_opt scdbm_opt;
+typedef struct scdbm_trainer scdbm_trainer;
+
+const char* scdbm_last_error(void);
+int32_t scdbm_version(void);
+
+/* ---- context ------------------------------------------------------------ */
+/* stream == NULL: the library creates its own stream.  Otherwise a
+ * cudaStream_t owned by the caller (e.g. torch's current stream). */
+int32_t scdbm_ctx_create(int32_t device, uint64_t seed, void* stream, scdbm_ctx** out);
+int32_t scdbm_ctx_destroy(scdbm_ctx* ctx);
+int32_t scdbm_sync(scdbm_ctx* ctx);
+/* options: "engine" (0/1/2), "mu_inv_max" (NB inversion / gamma-Poisson switch),
+ * "nb_pshift" (0 or 1e-6, quirk B5), "seed" */
+int32_t scdbm_ctx_set_option(scdbm_ctx* ctx, const char* name, double value);
+int32_t scdbm_ctx_get_option(scdbm_ctx* ctx, const char* name, double* value);
+/* CUDA-event timer on the context's stream, and a count of the library's own
+ * kernel launches since the last reset (bench.py "gpu_launches"). */
+int32_t scdbm_timer_start(scdbm_ctx* ctx);
+int32_t scdbm_timer_stop(scdbm_ctx* ctx, float* elapsed_ms);
+int32_t scdbm_launch_count(scdbm_ctx* ctx, int64_t* count, int32_t reset);
+
+/* ---- model: RBM (nrbms == 1) or DBM = Vector{<:AbstractRBM} --------------
+ * replaces the parameter structs BernoulliRBM / NegativeBinomialBernoulliRBM
+ * (src/bmtypes.jl:17-21,85-92) and MultimodalDBM (:139).
+ * units[0..nrbms] = layer sizes (visible, h1, ...). */
+int32_t scdbm_model_create(scdbm_ctx* ctx, int32_t nrbms, const int32_t* units, int32_t visible_kind,
+                           scdbm_model** out);
+int32_t scdbm_model_destroy(scdbm_model* m);
+/* W: (units[l] x units[l+1]) column-major, ldw >= units[l]; visbias, hidbias;
+ * inversedispersion only for an NB layer 0 (else NULL). */
+int32_t scdbm_model_set_layer(scdbm_model* m, int32_t l, const double* W, int64_t ldw, const double* visbias,
+                              const double* hidbias, const double* inversedispersion);
+int32_t scdbm_model_get_layer(scdbm_model* m, int32_t l, double* W, int64_t ldw, double* visbias, double* hidbias,
+                              double* inversedispersion);
+int32_t scdbm_model_copy_layer(scdbm_model* dst, int32_t dst_l, scdbm_model* src, int32_t src_l);
+/* initrbm (src/rbmtraining.jl:332-374): NB: W = -U(0.0005,0.002), a = log(mean/(mean+r)), b = 0;
+ * Bernoulli: W = randn/sqrt(V), a = logit(mean).  x supplies the column means. */
+int32_t scdbm_model_init_layer(scdbm_model* m, int32_t l, const scdbm_mat* x, const double* inversedispersion,
+                               uint64_t seed);
+
+/* ---- state matrices (data, particles' layers, potentials) ---------------- */
+int32_t scdbm_mat_create(scdbm_ctx* ctx, int64_t rows, int64_t cols, int32_t kind, scdbm_mat** out);
+int32_t scdbm_mat_destroy(scdbm_mat* m);
+int32_t scdbm_mat_shape(const scdbm_mat* m, int64_t* rows, int64_t* cols, int32_t* kind);
+int32_t scdbm_mat_upload(scdbm_mat* m, const double* x, int64_t ld);        /* column-major fp64 in   */
+int32_t scdbm_mat_download(const scdbm_mat* m, double* x, int64_t ld);      /* column-major fp64 out  */
+int32_t scdbm_mat_download_u16(const scdbm_mat* m, uint16_t* x_rowmajor);   /* compact counts, row = sample */
+int32_t scdbm_mat_copy(scdbm_mat* dst, const scdbm_mat* src);
+/* per-column mean, variance (n-1 denominator, as Julia `var`) and zero fraction
+ * (src/NegativeBinomialRBMPlots.jl:148-182,428-462,500-515) */
+int32_t scdbm_mat_column_stats(const scdbm_mat* m, double* mean, double* var, double* zerofrac);
+
+/* ---- single conditional operators (parity gates G1/G2) ------------------
+ * `what` = SCDBM_OUT_*.  `uniforms`: optional host column-major fp64 matrix
+ * with the shape of `out` that replaces the Philox uniforms of the primary
+ * draw (gate "same uniforms"); `tick` is the Philox clock tick otherwise.
+ *   hidden : hiddeninput!/hiddenpotential!/samplehidden!
+ *            (src/gibbssampling.jl:207-212,271-276,327-335,594-610)
+ *   visible: visibleinput!/visiblepotential!/samplevisible!
+ *            (src/gibbssampling.jl:752-756,765-770,810-820,884-890,949-957,1013-1020)
+ *   dbm_layer: intermediate DBM layer from both neighbours
+ *            (src/gibbssampling.jl:165-170; src/dbmtraining.jl:197-207) */
+int32_t scdbm_hidden(scdbm_model* m, int32_t l, const scdbm_mat* v, scdbm_mat* h_out, double factor, int32_t what,
+                     uint32_t tick, const double* uniforms, int64_t ldu);
+int32_t scdbm_visible(scdbm_model* m, int32_t l, const scdbm_mat* h, scdbm_mat* v_out, double factor, int32_t what,
+                      uint32_t tick, const double* uniforms, int64_t ldu);
+int32_t scdbm_dbm_layer(scdbm_model* m, int32_t layer, const scdbm_mat* below, const scdbm_mat* above, scdbm_mat* out,
+                        int32_t what, uint32_t tick, const double* uniforms, int64_t ldu);
+
+/* ---- particles and chains ------------------------------------------------
+ * Particles (src/gibbssampling.jl:9); initparticles (:386-419, NB visible init
+ * :512-531, hidden :421-453); row_offset = global index of particle 0 (chain
+ * sharding over GPUs; results do not depend on the sharding). */
+/* real_valued != 0: hidden layers hold probabilities (mean-field `mu`), not samples. */
+int32_t scdbm_particles_create(scdbm_model* m, int64_t nparticles, uint64_t row_offset, int32_t real_valued,
+                               scdbm_particles** out);
+int32_t scdbm_particles_destroy(scdbm_particles* p);
+int32_t scdbm_particles_init(scdbm_particles* p, int32_t biased);
+int32_t scdbm_particles_layer(scdbm_particles* p, int32_t layer, scdbm_mat** borrowed);
+int32_t scdbm_particles_clock(scdbm_particles* p, int64_t* clock, int64_t set_to /* <0: keep */);
+/* gibbssample!(particles, dbm, nsteps) (src/gibbssampling.jl:153-182): synchronous
+ * update of all layers; temperature scales all weight matrices (copyannealed!,
+ * src/evaluating.jl:320-326,348-355).  For a 1-RBM model this is
+ * gibbssample!(particles, rbm, nsteps, up, down) (src/gibbssampling.jl:62-70). */
+int32_t scdbm_gibbs(scdbm_model* m, scdbm_particles* p, int32_t nsteps, double temperature, double upfactor,
+                    double downfactor);
+/* gibbssamplenegativebinomial!(x, particles, rbm, ...) (src/gibbssampling.jl:82-110):
+ * p - 1e-6 form, hidden sampled from the OLD visible state. */
+int32_t scdbm_gibbs_negbin_rbm(scdbm_model* m, scdbm_particles* p, int32_t nsteps, double upfactor, double downfactor);
+/* last step of samples(...; samplelast=false): visible potential into `out`
+ * (src/gibbssampling.jl:677-689) */
+int32_t scdbm_particles_visible_potential(scdbm_model* m, scdbm_particles* p, scdbm_mat* out);
+
+/* ---- mean-field (src/dbmtraining.jl:175-228) ------------------------------
+ * mu: particles with nparticles == rows(x); layer 0 is set to x.  Runs until
+ * the global max-abs change <= eps or maxiter iterations (maxiter <= 0: no cap).
+ * x.W1 is hoisted out of the loop. */
+int32_t scdbm_meanfield(scdbm_model* m, const scdbm_mat* x, double eps, int32_t maxiter, scdbm_particles* mu,
+                        int32_t* niter, double* delta);
+
+/* ---- learning --------------------------------------------------------------
+ * scdbm_opt = LoglikelihoodOptimizer / StackedOptimizer gradient holder
+ * (src/optimizers.jl:34-39,57-70,103). */
+int32_t scdbm_opt_create(scdbm_model* m, scdbm_opt** out);
+int32_t scdbm_opt_destroy(scdbm_opt* o);
+/* computegradient!(opt, v, vmodel, h, hmodel, rbm) (src/optimizers.jl:207-214,263-310).
+ * npos/nneg <= 0: use the row counts.  normalize == 0 leaves the un-normalised
+ * partial sums (data-parallel mode: allreduce, then scdbm_opt_scale). */
+int32_t scdbm_compute_gradient(scdbm_opt* o, scdbm_model* m, int32_t l, const scdbm_mat* v, const scdbm_mat* vmodel,
+                               const scdbm_mat* h, const scdbm_mat* hmodel, int64_t nrows_used);
+/* computegradient!(StackedOptimizer, mu, particles, dbm) (src/optimizers.jl:431-442) */
+int32_t scdbm_compute_gradient_dbm(scdbm_opt* o, scdbm_model* m, scdbm_particles* mu, scdbm_particles* particles,
+                                   double pos_scale, double neg_scale);
+/* updateparameters!(bm, opt) (src/optimizers.jl:450-454,478-485,505-520); l < 0: all layers */
+int32_t scdbm_update_parameters(scdbm_model* m, scdbm_opt* o, int32_t l, double learningrate);
+int32_t scdbm_opt_get_gradient(scdbm_opt* o, int32_t l, double* W, int64_t ldw, double* visbias, double* hidbias);
+/* the gradient block {dW_l, da_l, db_l for all l} as one contiguous device
+ * fp32 buffer -- the payload of the data-parallel allreduce */
+int32_t scdbm_opt_buffer(scdbm_opt* o, void** device_ptr, int64_t* nfloats);
+
+/* trainrbm! state held by fitrbm across epochs (src/rbmtraining.jl:137-151): the
+ * PCD chain state (`rand(batchsize, nhidden)`) and the draw clock. */
+int32_t scdbm_trainer_create(scdbm_model* m, int32_t l, int32_t batchsize, int32_t pcd, scdbm_trainer** out);
+int32_t scdbm_trainer_destroy(scdbm_trainer* t);
+int32_t scdbm_trainer_clock(scdbm_trainer* t, int64_t* clock, int64_t set_to);
+int32_t scdbm_trainer_chainstate(scdbm_trainer* t, scdbm_mat** borrowed);
+/* trainrbm!(rbm, x; ...) one epoch of minibatch CD-k / PCD
+ * (src/rbmtraining.jl:498-591).  perm: the epoch's sample order (randombatchmasks,
+ * :416-429), 0-based, length rows(x). */
+int32_t scdbm_rbm_train_epoch(scdbm_trainer* t, const scdbm_mat* x, const int32_t* perm, double learningrate,
+                              int32_t cdsteps, double upfactor, double downfactor);
+/* traindbm!(dbm, x, particles, opt) one PCD step (src/dbmtraining.jl:287-297):
+ * gibbssample!(particles, dbm, nsteps); meanfield; gradient; update. */
+int32_t scdbm_dbm_pcd_step(scdbm_model* m, const scdbm_mat* x, scdbm_particles* particles, scdbm_particles* mu,
+                           scdbm_opt* o, double learningrate, int32_t nsteps, double eps, int32_t* mf_iters);
+
+/* ---- AIS (src/evaluating.jl:18-46,164-206,265-355,1314-1364,1596-1648) -----
+ * Returns nparticles log importance weights.  temperatures[0..ntemps-1]
+ * ascending from 0 to 1. */
+int32_t scdbm_ais_run(scdbm_model* m, const double* temperatures, int32_t ntemps, int64_t nparticles, int32_t burnin,
+                      uint64_t row_offset, double* logimpweights);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCDBM_B200_H */

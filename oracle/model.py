@@ -448,7 +448,7 @@ def stackrbms(x, rng, nhiddens=None, epochs=10, predbm=False, learningrate=0.005
                     upfactor = 1.0
             else:
                 upfactor = downfactor = 1.0
-        lrng = px.Rng(rng.seed + 0x9E3779B97F4A7C15 * (i + 1))
+        lrng = px.Rng((rng.seed + 1000003 * (i + 1)) % (1 << 52))
         dbm.append(fitrbm(hiddenval, lrng, nhidden=tl.nhidden,
                           epochs=tl.epochs if tl.epochs >= 0 else epochs,
                           upfactor=upfactor, downfactor=downfactor,

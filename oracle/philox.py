@@ -8,7 +8,8 @@ reproduced, so oracle and GPU agree on this stateless generator instead.
 
 Addressing of the uniform used for element (row i, column j) of a state
 matrix:  counter = (j >> 2, i, tick, stream), key = (seed_lo, seed_hi),
-word = output[j & 3],  u = ((word >> 8) + 0.5) * 2**-24   (exact in fp32).
+word = output[j & 3],  u = ((word >> 9) + 0.5) * 2**-23   (23 random bits;
+24 significant bits, hence exact in fp32; 2**-24 <= u <= 1 - 2**-24).
 """
 import numpy as np
 
@@ -56,9 +57,10 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def u24(word):
-    """uint32 word -> uniform in (0,1) with 24 random bits; exactly
-    representable in fp32, so GPU and oracle compare the *same* number."""
-    return ((np.asarray(word, dtype=np.uint32) >> np.uint32(8)).astype(np.float64) + 0.5) * (2.0 ** -24)
+    """uint32 word -> uniform in (0,1): 23 random bits plus a half, i.e. 24
+    significant bits, exactly representable in fp32, so GPU and oracle
+    compare the *same* number."""
+    return ((np.asarray(word, dtype=np.uint32) >> np.uint32(9)).astype(np.float64) + 0.5) * (2.0 ** -23)
 
 
 class Rng:

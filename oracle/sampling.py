@@ -31,6 +31,8 @@ from . import philox as px
 KMAX = 65535          # counts saturate here (device count planes hold 16 bits)
 MAX_ATTEMPTS = 64     # rejection-loop cap (probability of hitting it < 1e-30)
 MU_INV_MAX = 8.0      # default switch between inversion and gamma-Poisson
+PMIN = 2.0 ** -26     # inversion stops once the pmf term falls below this (the
+                      # uniforms carry 23 bits; guards fp32 round-off run-away)
 
 
 def sigm(x):
@@ -55,13 +57,13 @@ def _invert_pmf(u, p0, ratio_fn, kmax=KMAX):
     u = u.copy()
     P = p0.copy()
     k = np.zeros(u.shape, dtype=np.int64)
-    active = u >= P
+    active = (u >= P) & (P > PMIN)
     while active.any():
         idx = np.nonzero(active)
         u[idx] -= P[idx]
         P[idx] *= ratio_fn(k[idx], idx)
         k[idx] += 1
-        active[idx] = (u[idx] >= P[idx]) & (k[idx] < kmax)
+        active[idx] = (u[idx] >= P[idx]) & (k[idx] < kmax) & (P[idx] > PMIN)
     return k
 
 

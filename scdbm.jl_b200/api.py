@@ -1,0 +1,822 @@
+"""Host-side mirror of the reference's Julia API for the hot path
+(export list src/scDBM.jl:17-64), written in Python because Julia is not
+available in this image; `julia/scDBM.jl` is the same facade over `ccall`.
+
+Naming: Julia's `f!` is `f_` here.  Matrices are NumPy Float64, logical shapes
+as in the reference (samples x units, weights nvisible x nhidden).  Functions
+take either host objects (NumPy arrays / RBM dataclasses: uploaded, processed
+on the GPU, downloaded) or device handles (`DeviceModel`, `Mat`,
+`DeviceParticles`: stay resident in HBM).
+"""
+import ctypes as C
+import copy
+from dataclasses import dataclass, field
+import numpy as np
+
+from . import _lib as L
+from ._lib import lib, check
+
+_D = L.D
+
+
+def _f64(a, order="F"):
+    return np.asarray(a, dtype=np.float64, order=order)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_D) if a is not None else None
+
+
+# ------------------------------------------------------------------ context
+class Context:
+    """One GPU + stream + Philox seed (`Random.seed!` stands behind `seed`)."""
+
+    def __init__(self, device=0, seed=0, stream=None):
+        self.h = C.c_void_p()
+        check(lib().scdbm_ctx_create(device, C.c_uint64(seed), stream, C.byref(self.h)))
+        self.device = device
+
+    def set(self, name, value):
+        check(lib().scdbm_ctx_set_option(self.h, name.encode(), float(value)))
+
+    def get(self, name):
+        v = C.c_double()
+        check(lib().scdbm_ctx_get_option(self.h, name.encode(), C.byref(v)))
+        return v.value
+
+    def sync(self):
+        check(lib().scdbm_sync(self.h))
+
+    def timer_start(self):
+        check(lib().scdbm_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(lib().scdbm_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self, reset=False):
+        n = C.c_int64()
+        check(lib().scdbm_launch_count(self.h, C.byref(n), int(reset)))
+        return n.value
+
+    def close(self):
+        if self.h:
+            lib().scdbm_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = None
+
+
+def default_context(seed=None):
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0, 0 if seed is None else seed)
+    elif seed is not None:
+        _default_ctx.set("seed", seed)
+    return _default_ctx
+
+
+def seed_(seed):
+    """`Random.seed!(seed)`"""
+    return default_context(seed)
+
+
+# -------------------------------------------------------------- host models
+@dataclass
+class BernoulliRBM:
+    """src/bmtypes.jl:17-21"""
+    weights: np.ndarray
+    visbias: np.ndarray
+    hidbias: np.ndarray
+    kind = L.VIS_BERNOULLI
+
+
+@dataclass
+class NegativeBinomialBernoulliRBM:
+    """src/bmtypes.jl:85-92"""
+    weights: np.ndarray
+    visbias: np.ndarray
+    hidbias: np.ndarray
+    inversedispersion: np.ndarray
+    dropoutmid: np.ndarray = field(default_factory=lambda: np.array([0.5]))
+    dropoutshape: np.ndarray = field(default_factory=lambda: np.array([1.0]))
+    kind = L.VIS_NEGBIN
+
+
+def _rbms(bm):
+    return list(bm) if isinstance(bm, (list, tuple)) else [bm]
+
+
+# ------------------------------------------------------------ device model
+class DeviceModel:
+    """RBM / DBM parameters resident on the GPU (fp32 master + bf16 operand
+    planes)."""
+
+    def __init__(self, ctx, units, visible_kind):
+        self.ctx = ctx
+        self.units = [int(u) for u in units]
+        self.visible_kind = visible_kind
+        self.h = C.c_void_p()
+        arr = (C.c_int32 * len(self.units))(*self.units)
+        check(lib().scdbm_model_create(ctx.h, len(self.units) - 1, arr, visible_kind, C.byref(self.h)))
+
+    @property
+    def nrbms(self):
+        return len(self.units) - 1
+
+    @classmethod
+    def from_host(cls, bm, ctx=None):
+        ctx = ctx or default_context()
+        rbms = _rbms(bm)
+        units = [rbms[0].weights.shape[0]] + [r.weights.shape[1] for r in rbms]
+        for i in range(1, len(rbms)):
+            if rbms[i].weights.shape[0] != units[i]:
+                raise ValueError("DBM layer sizes are inconsistent")
+            if rbms[i].kind != L.VIS_BERNOULLI:
+                raise ValueError("only the first layer may have NB visible units")
+        m = cls(ctx, units, rbms[0].kind)
+        for l, r in enumerate(rbms):
+            m.set_layer(l, r)
+        return m
+
+    def set_layer(self, l, rbm):
+        W = _f64(rbm.weights)
+        if W.shape != (self.units[l], self.units[l + 1]):
+            raise ValueError("weights have the wrong shape")
+        a, b = _f64(rbm.visbias), _f64(rbm.hidbias)
+        if a.shape != (self.units[l],) or b.shape != (self.units[l + 1],):
+            raise ValueError("bias vectors have the wrong length")
+        r = _f64(rbm.inversedispersion) if rbm.kind == L.VIS_NEGBIN else None
+        if r is not None and r.shape != (self.units[l],):
+            raise ValueError("inversedispersion has the wrong length")
+        check(lib().scdbm_model_set_layer(self.h, l, _ptr(W), W.shape[0], _ptr(a), _ptr(b), _ptr(r)))
+
+    def get_layer(self, l):
+        V, H = self.units[l], self.units[l + 1]
+        W = np.zeros((V, H), order="F")
+        a, b, r = np.zeros(V), np.zeros(H), np.zeros(V)
+        check(lib().scdbm_model_get_layer(self.h, l, _ptr(W), V, _ptr(a), _ptr(b), _ptr(r)))
+        if l == 0 and self.visible_kind == L.VIS_NEGBIN:
+            return NegativeBinomialBernoulliRBM(W, a, b, r)
+        return BernoulliRBM(W, a, b)
+
+    def to_host(self):
+        rbms = [self.get_layer(l) for l in range(self.nrbms)]
+        return rbms if self.nrbms > 1 else rbms[0]
+
+    def copy_layer_from(self, l, src, src_l):
+        check(lib().scdbm_model_copy_layer(self.h, l, src.h, src_l))
+
+    def init_layer(self, l, x, inversedispersion=None, seed=0):
+        r = _f64(inversedispersion) if inversedispersion is not None else None
+        check(lib().scdbm_model_init_layer(self.h, l, x.h, _ptr(r), C.c_uint64(seed)))
+
+    def close(self):
+        if self.h:
+            lib().scdbm_model_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _model(bm, ctx=None):
+    return bm if isinstance(bm, DeviceModel) else DeviceModel.from_host(bm, ctx)
+
+
+# ------------------------------------------------------------------- Mat
+class Mat:
+    """Device state matrix (samples x units)."""
+
+    def __init__(self, ctx, rows, cols, kind, handle=None, owns=True):
+        self.ctx, self.rows, self.cols, self.kind, self.owns = ctx, int(rows), int(cols), kind, owns
+        if handle is None:
+            self.h = C.c_void_p()
+            check(lib().scdbm_mat_create(ctx.h, self.rows, self.cols, kind, C.byref(self.h)))
+        else:
+            self.h = handle
+
+    @classmethod
+    def borrowed(cls, ctx, handle):
+        r, c, k = C.c_int64(), C.c_int64(), C.c_int32()
+        check(lib().scdbm_mat_shape(handle, C.byref(r), C.byref(c), C.byref(k)))
+        return cls(ctx, r.value, c.value, k.value, handle, owns=False)
+
+    @classmethod
+    def from_host(cls, ctx, x, kind):
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim != 2:
+            raise ValueError("expected a matrix (samples x units)")
+        m = cls(ctx, x.shape[0], x.shape[1], kind)
+        m.upload(x)
+        return m
+
+    def upload(self, x):
+        x = _f64(x)
+        if x.shape != (self.rows, self.cols):
+            raise ValueError(f"shape {x.shape} does not match ({self.rows}, {self.cols})")
+        check(lib().scdbm_mat_upload(self.h, _ptr(x), max(self.rows, 1)))
+
+    def to_host(self):
+        out = np.zeros((self.rows, self.cols), order="F")
+        check(lib().scdbm_mat_download(self.h, _ptr(out), max(self.rows, 1)))
+        return out
+
+    def to_host_u16(self, out=None):
+        if out is None:
+            out = np.zeros((self.rows, self.cols), dtype=np.uint16)
+        check(lib().scdbm_mat_download_u16(self.h, out.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return out
+
+    def column_stats(self):
+        mean, var, zf = np.zeros(self.cols), np.zeros(self.cols), np.zeros(self.cols)
+        check(lib().scdbm_mat_column_stats(self.h, _ptr(mean), _ptr(var), _ptr(zf)))
+        return mean, var, zf
+
+    def close(self):
+        if self.owns and self.h:
+            lib().scdbm_mat_destroy(self.h)
+        self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _data_kind(model, layer=0):
+    if layer == 0:
+        return L.MAT_COUNT if model.visible_kind == L.VIS_NEGBIN else L.MAT_BINARY
+    return L.MAT_BINARY
+
+
+def _as_mat(ctx, x, kind):
+    return x if isinstance(x, Mat) else Mat.from_host(ctx, x, kind)
+
+
+def _state_kind(x, default):
+    """binary data may be passed for a REAL slot; pick the cheapest exact kind"""
+    if isinstance(x, Mat):
+        return x.kind
+    x = np.asarray(x)
+    if default == L.MAT_COUNT:
+        return L.MAT_COUNT
+    return L.MAT_BINARY if np.isin(x, (0.0, 1.0)).all() else L.MAT_REAL
+
+
+# ---------------------------------------------- conditional operators (L1)
+def _conditional(fn, bm, l, src, out_cols, what, factor, tick, u, src_kind, out_kind, ctx):
+    m = _model(bm, ctx)
+    s = _as_mat(m.ctx, src, src_kind)
+    out = Mat(m.ctx, s.rows, out_cols, out_kind)
+    uu = _f64(u) if u is not None else None
+    if uu is not None and uu.shape != (s.rows, out_cols):
+        raise ValueError("uniforms must have the shape of the output")
+    check(fn(m.h, l, s.h, out.h, float(factor), what, int(tick) & 0xFFFFFFFF, _ptr(uu), max(s.rows, 1)))
+    return out
+
+
+def _hidden(bm, v, what, factor=1.0, layer=0, tick=0, u=None, device=False, ctx=None):
+    m = _model(bm, ctx)
+    kind = _state_kind(v, _data_kind(m, layer))
+    okind = L.MAT_BINARY if what == L.OUT_SAMPLE else L.MAT_REAL
+    out = _conditional(lib().scdbm_hidden, m, layer, v, m.units[layer + 1], what, factor, tick, u, kind, okind, ctx)
+    return out if device else out.to_host()
+
+
+def _visible(bm, h, what, factor=1.0, layer=0, tick=0, u=None, device=False, ctx=None):
+    m = _model(bm, ctx)
+    kind = _state_kind(h, L.MAT_BINARY)
+    nb = layer == 0 and m.visible_kind == L.VIS_NEGBIN
+    okind = (L.MAT_COUNT if nb else L.MAT_BINARY) if what == L.OUT_SAMPLE else L.MAT_REAL
+    out = _conditional(lib().scdbm_visible, m, layer, h, m.units[layer], what, factor, tick, u, kind, okind, ctx)
+    return out if device else out.to_host()
+
+
+def hiddeninput(rbm, v, **kw):
+    """src/gibbssampling.jl:189-276"""
+    return _hidden(rbm, v, L.OUT_INPUT, **kw)
+
+
+def hiddenpotential(rbm, v, factor=1.0, **kw):
+    """src/gibbssampling.jl:314-335"""
+    return _hidden(rbm, v, L.OUT_POTENTIAL, factor, **kw)
+
+
+def samplehidden(rbm, v, factor=1.0, **kw):
+    """src/gibbssampling.jl:575-610"""
+    return _hidden(rbm, v, L.OUT_SAMPLE, factor, **kw)
+
+
+def visibleinput(rbm, h, **kw):
+    """src/gibbssampling.jl:860-890"""
+    return _visible(rbm, h, L.OUT_INPUT, **kw)
+
+
+def visiblepotential(rbm, h, factor=1.0, **kw):
+    """src/gibbssampling.jl:930-1020"""
+    return _visible(rbm, h, L.OUT_POTENTIAL, factor, **kw)
+
+
+def samplevisible(rbm, h, factor=1.0, **kw):
+    """src/gibbssampling.jl:733-756"""
+    return _visible(rbm, h, L.OUT_SAMPLE, factor, **kw)
+
+
+def dbmlayer(dbm, layer, below, above, what=L.OUT_POTENTIAL, tick=0, u=None, device=False, ctx=None):
+    """Intermediate DBM layer from both neighbours (src/gibbssampling.jl:165-170)."""
+    m = _model(dbm, ctx)
+    lo = _as_mat(m.ctx, below, _state_kind(below, _data_kind(m, layer - 1)))
+    hi = _as_mat(m.ctx, above, _state_kind(above, L.MAT_BINARY))
+    out = Mat(m.ctx, lo.rows, m.units[layer], L.MAT_BINARY if what == L.OUT_SAMPLE else L.MAT_REAL)
+    uu = _f64(u) if u is not None else None
+    check(lib().scdbm_dbm_layer(m.h, layer, lo.h, hi.h, out.h, what, int(tick) & 0xFFFFFFFF, _ptr(uu), max(lo.rows, 1)))
+    return out if device else out.to_host()
+
+
+# ------------------------------------------------------------- particles
+class DeviceParticles:
+    """`Particles` (src/gibbssampling.jl:9) resident on the GPU."""
+
+    def __init__(self, model, nparticles, row_offset=0, real_valued=False):
+        self.model, self.n = model, int(nparticles)
+        self.h = C.c_void_p()
+        check(lib().scdbm_particles_create(model.h, self.n, C.c_uint64(row_offset), int(real_valued), C.byref(self.h)))
+
+    def init(self, biased=False):
+        check(lib().scdbm_particles_init(self.h, int(biased)))
+        return self
+
+    def layer(self, i):
+        h = C.c_void_p()
+        check(lib().scdbm_particles_layer(self.h, i, C.byref(h)))
+        return Mat.borrowed(self.model.ctx, h)
+
+    @property
+    def clock(self):
+        c = C.c_int64()
+        check(lib().scdbm_particles_clock(self.h, C.byref(c), -1))
+        return c.value
+
+    @clock.setter
+    def clock(self, v):
+        check(lib().scdbm_particles_clock(self.h, None, int(v)))
+
+    def to_host(self):
+        return [self.layer(i).to_host() for i in range(len(self.model.units))]
+
+    def upload(self, mats):
+        for i, x in enumerate(mats):
+            self.layer(i).upload(x)
+        return self
+
+    def close(self):
+        if self.h:
+            lib().scdbm_particles_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def initparticles(bm, nparticles, biased=False, row_offset=0, device=False, ctx=None):
+    """src/gibbssampling.jl:386-419"""
+    m = _model(bm, ctx)
+    p = DeviceParticles(m, nparticles, row_offset).init(biased)
+    return p if device else p.to_host()
+
+
+def gibbssample_(particles, bm, nsteps=5, upfactor=1.0, downfactor=1.0, temperature=1.0, ctx=None):
+    """`gibbssample!` (src/gibbssampling.jl:62-70 RBM, :153-182 DBM).  Host
+    particles (list of arrays) are updated in place."""
+    m = _model(bm, ctx)
+    if isinstance(particles, DeviceParticles):
+        check(lib().scdbm_gibbs(m.h, particles.h, nsteps, temperature, upfactor, downfactor))
+        return particles
+    p = DeviceParticles(m, particles[0].shape[0]).upload(particles)
+    p.clock = getattr(particles, "clock", 1)
+    check(lib().scdbm_gibbs(m.h, p.h, nsteps, temperature, upfactor, downfactor))
+    for i, x in enumerate(p.to_host()):
+        particles[i] = x
+    if hasattr(particles, "clock"):
+        particles.clock = p.clock
+    return particles
+
+
+def gibbssamplenegativebinomial_(particles, rbm, nsteps=5, upfactor=1.0, downfactor=1.0, ctx=None):
+    """`gibbssamplenegativebinomial!` RBM form (src/gibbssampling.jl:82-110);
+    the DBM form (:112-151) equals `gibbssample_` for a DBM."""
+    m = _model(rbm, ctx)
+    if m.nrbms > 1:
+        return gibbssample_(particles, m, nsteps)
+    if isinstance(particles, DeviceParticles):
+        check(lib().scdbm_gibbs_negbin_rbm(m.h, particles.h, nsteps, upfactor, downfactor))
+        return particles
+    p = DeviceParticles(m, particles[0].shape[0]).upload(particles)
+    p.clock = getattr(particles, "clock", 1)
+    check(lib().scdbm_gibbs_negbin_rbm(m.h, p.h, nsteps, upfactor, downfactor))
+    for i, x in enumerate(p.to_host()):
+        particles[i] = x
+    if hasattr(particles, "clock"):
+        particles.clock = p.clock
+    return particles
+
+
+def sampleparticles(bm, nparticles, burnin=10, row_offset=0, device=False, ctx=None):
+    """src/gibbssampling.jl:646-650"""
+    m = _model(bm, ctx)
+    p = DeviceParticles(m, nparticles, row_offset).init(False)
+    check(lib().scdbm_gibbs(m.h, p.h, burnin, 1.0, 1.0, 1.0))
+    return p if device else p.to_host()
+
+
+def samples(bm, nsamples, burnin=50, samplelast=True, row_offset=0, device=False, dtype=np.float64, ctx=None):
+    """src/gibbssampling.jl:663-689.  `dtype=np.uint16` returns the compact
+    row-major count matrix instead of Float64."""
+    m = _model(bm, ctx)
+    if samplelast:
+        p = sampleparticles(m, nsamples, burnin, row_offset, device=True)
+        out = p.layer(0)
+        out._keepalive = p
+    else:
+        p = sampleparticles(m, nsamples, burnin - 1, row_offset, device=True)
+        out = Mat(m.ctx, nsamples, m.units[0], L.MAT_REAL)
+        check(lib().scdbm_particles_visible_potential(m.h, p.h, out.h))
+    if device:
+        return out
+    return out.to_host_u16() if dtype == np.uint16 else out.to_host()
+
+
+# ------------------------------------------------------------- mean-field
+def meanfield(dbm, x, eps=0.001, maxiter=0, device=False, return_info=False, ctx=None):
+    """src/dbmtraining.jl:175-228"""
+    m = _model(dbm, ctx)
+    xm = _as_mat(m.ctx, x, _data_kind(m))
+    mu = DeviceParticles(m, xm.rows, real_valued=True)
+    it, delta = C.c_int32(), C.c_double()
+    check(lib().scdbm_meanfield(m.h, xm.h, eps, maxiter, mu.h, C.byref(it), C.byref(delta)))
+    mu._x = xm
+    res = mu if device else mu.to_host()
+    return (res, it.value, delta.value) if return_info else res
+
+
+# ----------------------------------------------------------- optimizers
+class LoglikelihoodOptimizer:
+    """`LoglikelihoodOptimizer` / `StackedOptimizer` (src/optimizers.jl:34-39,
+    57-70,103): holds the gradient on the device; implements the documented
+    plug-in protocol `initialized`, `computegradient_`, `updateparameters_`
+    (src/optimizers.jl:1-18)."""
+
+    def __init__(self, learningrate=0.005, sdlearningrate=0.0):
+        self.learningrate = learningrate
+        self.sdlearningrate = sdlearningrate
+        self.model = None
+        self.h = C.c_void_p()
+
+    def initialized(self, bm):
+        o = LoglikelihoodOptimizer(self.learningrate, self.sdlearningrate)
+        o.model = bm
+        check(lib().scdbm_opt_create(bm.h, C.byref(o.h)))
+        return o
+
+    def computegradient_(self, v, vmodel, h, hmodel, rbm, layer=0, nrows_used=0):
+        check(lib().scdbm_compute_gradient(self.h, rbm.h, layer, v.h, vmodel.h, h.h, hmodel.h, nrows_used))
+
+    def computegradient_dbm_(self, mu, particles, dbm, pos_scale=0.0, neg_scale=0.0):
+        check(lib().scdbm_compute_gradient_dbm(self.h, dbm.h, mu.h, particles.h, pos_scale, neg_scale))
+
+    def updateparameters_(self, bm, layer=-1):
+        check(lib().scdbm_update_parameters(bm.h, self.h, layer, self.learningrate))
+
+    def gradient(self, layer=0):
+        V, H = self.model.units[layer], self.model.units[layer + 1]
+        W = np.zeros((V, H), order="F")
+        a, b = np.zeros(V), np.zeros(H)
+        check(lib().scdbm_opt_get_gradient(self.h, layer, _ptr(W), V, _ptr(a), _ptr(b)))
+        return W, a, b
+
+    def buffer(self):
+        """(device pointer, number of floats) of the contiguous gradient block
+        -- the data-parallel allreduce payload."""
+        p, n = C.c_void_p(), C.c_int64()
+        check(lib().scdbm_opt_buffer(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def close(self):
+        if self.h:
+            lib().scdbm_opt_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def loglikelihoodoptimizer(bm=None, learningrate=0.0, sdlearningrate=0.0):
+    """src/optimizers.jl:57-70"""
+    o = LoglikelihoodOptimizer(learningrate, sdlearningrate)
+    return o.initialized(bm) if bm is not None else o
+
+
+def computegradient_(optimizer, v, vmodel, h, hmodel, rbm):
+    """src/optimizers.jl:207-214 with host matrices."""
+    m = _model(rbm)
+    if optimizer.model is not m:
+        raise ValueError("optimizer was initialised for a different model")
+    vk = _data_kind(m)
+    mats = [_as_mat(m.ctx, v, _state_kind(v, vk)), _as_mat(m.ctx, vmodel, L.MAT_REAL if vk != L.MAT_COUNT else _state_kind(vmodel, L.MAT_REAL)),
+            _as_mat(m.ctx, h, L.MAT_REAL), _as_mat(m.ctx, hmodel, L.MAT_REAL)]
+    optimizer.computegradient_(*mats, m)
+
+
+def updateparameters_(bm, optimizer):
+    """src/optimizers.jl:450-454,478-485,505-510"""
+    optimizer.updateparameters_(bm)
+
+
+# ----------------------------------------------------------- samplers
+@dataclass
+class NoSampler:
+    """src/samplers.jl:22-35"""
+
+
+@dataclass
+class GibbsSampler:
+    """src/samplers.jl:4-6,47-62"""
+    nsteps: int = 1
+
+
+# ----------------------------------------------------------- RBM training
+class RBMTrainer:
+    """State `fitrbm` keeps across epochs (src/rbmtraining.jl:137-151)."""
+
+    def __init__(self, model, batchsize, pcd=True, layer=0):
+        self.model, self.batchsize, self.pcd, self.layer = model, batchsize, pcd, layer
+        self.h = C.c_void_p()
+        check(lib().scdbm_trainer_create(model.h, layer, batchsize, int(pcd), C.byref(self.h)))
+
+    @property
+    def clock(self):
+        c = C.c_int64()
+        check(lib().scdbm_trainer_clock(self.h, C.byref(c), -1))
+        return c.value
+
+    @clock.setter
+    def clock(self, v):
+        check(lib().scdbm_trainer_clock(self.h, None, int(v)))
+
+    def chainstate(self):
+        h = C.c_void_p()
+        check(lib().scdbm_trainer_chainstate(self.h, C.byref(h)))
+        return Mat.borrowed(self.model.ctx, h)
+
+    def close(self):
+        if self.h:
+            lib().scdbm_trainer_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def philox_permutation(n, seed, tick):
+    """`randperm(n)` stand-in shared with oracle.philox.Rng.permutation
+    (host-side integer work; the library receives the permutation)."""
+    from . import hostrng
+    return hostrng.permutation(n, seed, tick)
+
+
+def trainrbm_(model, x, trainer, learningrate=0.005, cdsteps=1, upfactor=1.0, downfactor=1.0, perm=None,
+              sampler=None):
+    """`trainrbm!` one epoch (src/rbmtraining.jl:498-591)."""
+    if sampler is not None:
+        cdsteps = 1 if isinstance(sampler, NoSampler) else sampler.nsteps + 1
+    n = x.rows
+    if trainer.batchsize > n:
+        raise ValueError(f"Batchsize ({trainer.batchsize}) exceeds number of samples ({n}).")
+    if perm is None:
+        perm = philox_permutation(n, int(model.ctx.get("seed")), trainer.clock)
+        trainer.clock = trainer.clock + 1
+    perm = np.ascontiguousarray(perm, dtype=np.int32)
+    check(lib().scdbm_rbm_train_epoch(trainer.h, x.h, perm.ctypes.data_as(C.POINTER(C.c_int32)), learningrate, cdsteps,
+                                      upfactor, downfactor))
+    return model
+
+
+def fitrbm(x, nhidden=None, epochs=10, upfactor=1.0, downfactor=1.0, learningrate=0.005, learningrates=None,
+           pcd=True, cdsteps=1, batchsize=1, rbmtype=BernoulliRBM, inversedispersion=None, startrbm=None,
+           monitoring=None, fisherscoring=0, zeroinflation=False, sampler=None, seed=None, device=False, ctx=None):
+    """`fitrbm` (src/rbmtraining.jl:89-223).  Dispersion re-estimation
+    (`fisherscoring`) and zero-inflation are "next" rows: any non-default value
+    raises rather than being silently ignored."""
+    if fisherscoring != 0 or zeroinflation:
+        raise NotImplementedError("fisherscoring / zeroinflation are outside the accelerated hot path (DESIGN.md)")
+    ctx = ctx or default_context()
+    if seed is not None:
+        ctx.set("seed", seed)
+    nb = rbmtype is NegativeBinomialBernoulliRBM or rbmtype == "nb"
+    xm = x if isinstance(x, Mat) else Mat.from_host(ctx, x, L.MAT_COUNT if nb else L.MAT_REAL)
+    nhidden = xm.cols if nhidden is None else nhidden
+    if learningrates is None:
+        learningrates = [learningrate] * epochs
+    if len(learningrates) < epochs:
+        raise ValueError("Not enough `learningrates` (vector of length %d) for training epochs (%d)" % (len(learningrates), epochs))
+    if batchsize > xm.rows:
+        raise ValueError(f"Batchsize ({batchsize}) exceeds number of samples ({xm.rows}).")
+    if startrbm is not None:
+        m = startrbm if isinstance(startrbm, DeviceModel) else DeviceModel.from_host(startrbm, ctx)
+    else:
+        m = DeviceModel(ctx, [xm.cols, nhidden], L.VIS_NEGBIN if nb else L.VIS_BERNOULLI)
+        m.init_layer(0, xm, inversedispersion, seed=int(ctx.get("seed")))
+    trainer = RBMTrainer(m, batchsize, pcd)
+    for epoch in range(epochs):
+        trainrbm_(m, xm, trainer, learningrates[epoch], cdsteps, upfactor, downfactor, sampler=sampler)
+        if monitoring is not None:
+            monitoring(m.to_host(), epoch + 1)
+    trainer.close()
+    return m if device else m.to_host()
+
+
+@dataclass
+class TrainLayer:
+    """The hot-path subset of `TrainLayer` (src/rbmstacking.jl:9-94)."""
+    nhidden: int = -1
+    rbmtype: type = BernoulliRBM
+    epochs: int = -1
+    learningrate: float = -np.inf
+    batchsize: int = -1
+    pcd: bool = True
+    cdsteps: int = 1
+    inversedispersion: np.ndarray = None
+    startrbm: object = None
+
+
+def stackrbms(x, nhiddens=None, epochs=10, predbm=False, learningrate=0.005, batchsize=1, trainlayers=None,
+              seed=None, device=False, ctx=None):
+    """`stackrbms` (src/rbmstacking.jl:228-284; factors :247-275)."""
+    ctx = ctx or default_context()
+    if seed is not None:
+        ctx.set("seed", seed)
+    base_seed = int(ctx.get("seed"))
+    if not trainlayers:
+        nb0 = False
+        if nhiddens is None or len(nhiddens) == 0:
+            ncol = x.cols if isinstance(x, Mat) else np.asarray(x).shape[1]
+            nhiddens = [ncol] * 2
+        trainlayers = [TrainLayer(nhidden=n) for n in nhiddens]
+    nb0 = trainlayers[0].rbmtype is NegativeBinomialBernoulliRBM
+    xm = x if isinstance(x, Mat) else Mat.from_host(ctx, x, L.MAT_COUNT if nb0 else L.MAT_REAL)
+    layers = []
+    upfactor, downfactor = (2.0 if predbm else 1.0), 1.0
+    hiddenval = xm
+    for i, tl in enumerate(trainlayers):
+        if i > 0:
+            hiddenval = _conditional(lib().scdbm_hidden, layers[i - 1], 0, hiddenval, layers[i - 1].units[1],
+                                     L.OUT_POTENTIAL, upfactor, 0, None, None, L.MAT_REAL, ctx)
+            if predbm:
+                upfactor = downfactor = 2.0
+                if i == len(trainlayers) - 1:
+                    upfactor = 1.0
+            else:
+                upfactor = downfactor = 1.0
+        ctx.set("seed", (base_seed + 1000003 * (i + 1)) % (1 << 52))
+        layers.append(fitrbm(hiddenval, nhidden=tl.nhidden, epochs=tl.epochs if tl.epochs >= 0 else epochs,
+                             upfactor=upfactor, downfactor=downfactor,
+                             learningrate=tl.learningrate if tl.learningrate >= 0 else learningrate,
+                             pcd=tl.pcd, cdsteps=tl.cdsteps, batchsize=tl.batchsize if tl.batchsize > 0 else batchsize,
+                             rbmtype=tl.rbmtype, inversedispersion=tl.inversedispersion, startrbm=tl.startrbm,
+                             device=True, ctx=ctx))
+    ctx.set("seed", base_seed)
+    units = [layers[0].units[0]] + [m.units[1] for m in layers]
+    dbm = DeviceModel(ctx, units, layers[0].visible_kind)
+    for i, m in enumerate(layers):
+        dbm.copy_layer_from(i, m, 0)
+    return dbm if device else dbm.to_host()
+
+
+def defaultfinetuninglearningrates(learningrate, epochs):
+    """src/dbmtraining.jl:59-61"""
+    return learningrate * 11.0 / (10.0 + np.arange(1, epochs + 1))
+
+
+def traindbm_(dbm, x, epochs=10, nparticles=100, learningrate=0.005, learningrates=None, monitoring=None,
+              particles=None, nsteps=5, eps=0.001, allreduce=None, device=False, ctx=None):
+    """`traindbm!` (src/dbmtraining.jl:250-297).  `allreduce(ptr, nfloats)`:
+    optional hook that sums the gradient block over data-parallel ranks."""
+    m = _model(dbm, ctx)
+    xm = _as_mat(m.ctx, x, _data_kind(m))
+    if learningrates is None:
+        learningrates = defaultfinetuninglearningrates(learningrate, epochs)
+    if len(learningrates) < epochs:
+        raise ValueError("Not enough `learningrates` for training epochs")
+    p = particles if particles is not None else DeviceParticles(m, nparticles).init(False)
+    mu = DeviceParticles(m, xm.rows, real_valued=True)
+    opt = LoglikelihoodOptimizer().initialized(m)
+    for epoch in range(epochs):
+        if allreduce is None:
+            check(lib().scdbm_dbm_pcd_step(m.h, xm.h, p.h, mu.h, opt.h, float(learningrates[epoch]), nsteps, eps, None))
+        else:
+            check(lib().scdbm_gibbs(m.h, p.h, nsteps, 1.0, 1.0, 1.0))
+            check(lib().scdbm_meanfield(m.h, xm.h, eps, 0, mu.h, None, None))
+            npos, nneg = allreduce.global_counts(xm.rows, p.n)
+            opt.computegradient_dbm_(mu, p, m, 1.0 / npos, 1.0 / nneg)
+            ptr, nfl = opt.buffer()
+            m.ctx.sync()
+            allreduce(ptr, nfl)
+            opt.learningrate = float(learningrates[epoch])
+            opt.updateparameters_(m)
+        if monitoring is not None:
+            monitoring(m.to_host(), epoch + 1)
+    opt.close()
+    mu.close()
+    return m if device else m.to_host()
+
+
+def fitdbm(x, nhiddens=None, epochs=10, nparticles=100, learningrate=0.005, learningrates=None,
+           learningratepretraining=None, epochspretraining=None, batchsizepretraining=1, pretraining=None,
+           monitoring=None, seed=None, device=False, ctx=None):
+    """`fitdbm` (src/dbmtraining.jl:108-149)."""
+    ctx = ctx or default_context()
+    if seed is not None:
+        ctx.set("seed", seed)
+    nb0 = bool(pretraining) and pretraining[0].rbmtype is NegativeBinomialBernoulliRBM
+    xm = x if isinstance(x, Mat) else Mat.from_host(ctx, x, L.MAT_COUNT if nb0 else L.MAT_REAL)
+    if not pretraining and not nhiddens:
+        nhiddens = [xm.cols] * 2
+    dbm = stackrbms(xm, nhiddens=nhiddens, epochs=epochs if epochspretraining is None else epochspretraining,
+                    predbm=True, batchsize=batchsizepretraining,
+                    learningrate=learningrate if learningratepretraining is None else learningratepretraining,
+                    trainlayers=pretraining, device=True, ctx=ctx)
+    xd = xm
+    if not nb0 and xm.kind == L.MAT_REAL:
+        xd = xm  # Bernoulli-visible DBMs train on the same matrix
+    return traindbm_(dbm, xd, epochs=epochs, nparticles=nparticles, learningrate=learningrate,
+                     learningrates=learningrates, monitoring=monitoring, device=device, ctx=ctx)
+
+
+# ------------------------------------------------------------------ AIS
+def aislogimpweights(bm, ntemperatures=100, temperatures=None, nparticles=100, burnin=5, row_offset=0, ctx=None):
+    """src/evaluating.jl:18-46 (RBM), :164-206 (MultimodalDBM)."""
+    m = _model(bm, ctx)
+    if temperatures is None:
+        temperatures = np.arange(ntemperatures + 1) / ntemperatures
+    t = np.ascontiguousarray(temperatures, dtype=np.float64)
+    out = np.zeros(nparticles)
+    check(lib().scdbm_ais_run(m.h, _ptr(t), len(t), nparticles, burnin, C.c_uint64(row_offset), _ptr(out)))
+    return out
+
+
+def logmeanexp(v):
+    """src/evaluating.jl:935-943"""
+    v = np.asarray(v, float)
+    vmax = v.max()
+    return vmax + np.log(np.sum(np.exp(v - vmax))) - np.log(len(v))
+
+
+def logpartitionfunctionzeroweights(bm):
+    """src/evaluating.jl:1001-1031,1055-1065 (host: O(units) scalar work)."""
+    rbms = _rbms(bm.to_host() if isinstance(bm, DeviceModel) else bm)
+    first = rbms[0]
+    if first.kind == L.VIS_NEGBIN:
+        vis = np.sum(-first.inversedispersion * np.log(1.0 - np.exp(first.visbias)))
+    else:
+        vis = np.sum(np.logaddexp(0.0, first.visbias))
+    if len(rbms) == 1:
+        return vis + np.sum(np.logaddexp(0.0, first.hidbias))
+    tot = vis
+    for i in range(1, len(rbms)):
+        tot += np.sum(np.logaddexp(0.0, rbms[i].visbias + rbms[i - 1].hidbias))
+    return tot + np.sum(np.logaddexp(0.0, rbms[-1].hidbias))
+
+
+def logpartitionfunction(bm, logr=None, **kw):
+    """src/evaluating.jl:967-992"""
+    if logr is None:
+        logr = logmeanexp(aislogimpweights(bm, **kw))
+    return logr + logpartitionfunctionzeroweights(bm)
+
+
+def mostevenbatches(ntasks, nbatches):
+    """src/misc.jl:157-169 -- the model for sharding chains over GPUs."""
+    minparticles, nbigger = divmod(ntasks, nbatches)
+    return [minparticles + 1] * nbigger + [minparticles] * (nbatches - nbigger)

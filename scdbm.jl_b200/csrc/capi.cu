@@ -1,0 +1,1394 @@
+// libscdbm_b200: C ABI + host orchestration (handles, chain drivers, mean-field,
+// CD/PCD epoch, DBM PCD step, AIS).  Kernels live in the included headers.
+#include "../../include/scdbm_b200.h"
+#include "elementwise.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+
+using namespace scdbm;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+struct Err : std::runtime_error {
+    int code;
+    Err(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            throw Err(e__ == cudaErrorMemoryAllocation ? SCDBM_ENOMEM : SCDBM_ECUDA,                     \
+                      std::string(#call) + ": " + cudaGetErrorString(e__));                             \
+    } while (0)
+#define REQUIRE(cond, msg)                          \
+    do {                                            \
+        if (!(cond)) throw Err(SCDBM_EINVAL, msg);  \
+    } while (0)
+#define API_BEGIN try {
+#define API_END                          \
+    return SCDBM_OK;                     \
+    }                                    \
+    catch (const Err& e) {               \
+        g_err = e.what();                \
+        return e.code;                   \
+    }                                    \
+    catch (const std::exception& e) {    \
+        g_err = e.what();                \
+        return SCDBM_EINVAL;             \
+    }
+
+// ------------------------------------------------------------------ handles
+struct scdbm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t seed = 0;
+    float mu_inv_max = 8.0f;
+    float nb_pshift = 0.0f;
+    int engine = SCDBM_ENGINE_AUTO;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned int* d_delta = nullptr;
+    int64_t launches = 0;
+    int64_t tc_launches = 0;
+    int num_sms = 148;
+    TcContext tc;
+};
+
+struct Layer {
+    int V = 0, H = 0, kind = SCDBM_VIS_BERNOULLI;
+    float *W = nullptr, *a = nullptr, *b = nullptr, *r = nullptr;
+    __nv_bfloat16 *w0 = nullptr, *w1 = nullptr, *t0 = nullptr, *t1 = nullptr;  // W[V x ldh], Wt[H x ldv] hi/lo
+    int64_t ldh = 0, ldv = 0;
+};
+
+struct scdbm_model {
+    scdbm_ctx* ctx;
+    std::vector<Layer> L;
+    int units(int layer) const { return layer == 0 ? L[0].V : L[layer - 1].H; }
+    int nlayers() const { return (int)L.size() + 1; }
+};
+
+struct scdbm_mat {
+    scdbm_ctx* ctx;
+    MatView v;
+    bool owns;
+};
+
+struct scdbm_particles {
+    scdbm_model* model;
+    int64_t n;
+    uint64_t row_offset;
+    int64_t clock;
+    bool real_valued;
+    std::vector<scdbm_mat*> cur, nxt;
+    scdbm_mat* alias0 = nullptr;  // mean-field: layer 0 aliases the data matrix
+    float* hoist = nullptr;       // mean-field: x * W1 (fp32 [n x H1])
+};
+
+struct scdbm_opt {
+    scdbm_model* model;
+    float* buf = nullptr;
+    int64_t n = 0;
+    std::vector<int64_t> offW, offA, offB;
+};
+
+struct scdbm_trainer {
+    scdbm_model* model;
+    int l, B, pcd;
+    int64_t clock;
+    scdbm_mat *chain = nullptr, *v = nullptr, *h = nullptr, *hm = nullptr, *hs = nullptr, *vm = nullptr, *vs = nullptr;
+    scdbm_opt* opt = nullptr;
+    int32_t* d_perm = nullptr;
+    int64_t perm_cap = 0;
+};
+
+// ------------------------------------------------------------------ helpers
+static inline int grid1d(int64_t n, int block = 256) { return (int)std::min<int64_t>((n + block - 1) / block, 148 * 16); }
+
+static scdbm_mat* mat_new(scdbm_ctx* ctx, int64_t rows, int64_t cols, int kind) {
+    REQUIRE(rows >= 0 && cols >= 0, "matrix dimensions must be non-negative");
+    REQUIRE(kind >= 0 && kind <= 2, "unknown matrix kind");
+    auto* m = new scdbm_mat{ctx, {}, true};
+    m->v.rows = rows;
+    m->v.cols = cols;
+    m->v.ld = round_up(std::max<int64_t>(cols, 1), 64);
+    m->v.kind = kind;
+    const size_t bytes = (size_t)std::max<int64_t>(rows, 1) * m->v.ld * sizeof(__nv_bfloat16);
+    CK(cudaMalloc(&m->v.p0, bytes));
+    CK(cudaMemsetAsync(m->v.p0, 0, bytes, ctx->stream));
+    if (kind != MAT_BINARY) {
+        CK(cudaMalloc(&m->v.p1, bytes));
+        CK(cudaMemsetAsync(m->v.p1, 0, bytes, ctx->stream));
+    }
+    return m;
+}
+static void mat_free(scdbm_mat* m) {
+    if (!m) return;
+    if (m->owns) {
+        cudaFree(m->v.p0);
+        cudaFree(m->v.p1);
+    }
+    delete m;
+}
+static MatView rows_view(const MatView& v, int64_t rows) {
+    MatView r = v;
+    r.rows = std::min(rows, v.rows);
+    return r;
+}
+
+static EpiParams epi_base(scdbm_ctx* ctx) {
+    EpiParams e;
+    memset(&e, 0, sizeof(e));
+    e.factor = 1.0f;
+    e.wscale = 1.0f;
+    e.pshift = ctx->nb_pshift;
+    e.mu_inv_max = ctx->mu_inv_max;
+    e.k0 = (uint32_t)(ctx->seed & 0xFFFFFFFFu);
+    e.k1 = (uint32_t)(ctx->seed >> 32);
+    return e;
+}
+
+// One contraction source of a sweep: state matrix x one RBM's weights.
+struct SweepSrc {
+    const MatView* a;
+    const Layer* layer;
+    bool up;  // up: out units = hidden of `layer` (K = V); down: out units = visible (K = H)
+};
+
+static void run_gemm(scdbm_ctx* ctx, GemmArgs& g, const SweepSrc* srcs, int nsrc) {
+    bool use_tc = false;
+    if (ctx->engine != SCDBM_ENGINE_SIMT && srcs) use_tc = tc_supported(g, nsrc);
+    if (ctx->engine == SCDBM_ENGINE_TC && !use_tc && srcs)
+        throw Err(SCDBM_EUNSUP, "engine=tc requested but the shape is not tiled by the tcgen05 kernel");
+    if (use_tc) {
+        TcOperandPlanes ops[2];
+        for (int s = 0; s < nsrc; ++s) {
+            const Layer& L = *srcs[s].layer;
+            ops[s].a = *srcs[s].a;
+            ops[s].b0 = srcs[s].up ? L.t0 : L.w0;
+            ops[s].b1 = srcs[s].up ? L.t1 : L.w1;
+            ops[s].ldb = srcs[s].up ? L.ldv : L.ldh;
+            ops[s].N = srcs[s].up ? L.H : L.V;
+            ops[s].K = srcs[s].up ? L.V : L.H;
+        }
+        CK(launch_gemm_tc(ctx->tc, ops, nsrc, g, ctx->num_sms, ctx->stream));
+        ctx->tc_launches++;
+    } else {
+        CK(launch_gemm_simt(g, ctx->stream));
+    }
+    ctx->launches++;
+}
+
+static void run_sweep(scdbm_ctx* ctx, const SweepSrc* srcs, int nsrc, int64_t M, int64_t N, EpiParams& epi) {
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.nsrc = nsrc;
+    g.M = M;
+    g.N = N;
+    for (int s = 0; s < nsrc; ++s) {
+        const MatView& a = *srcs[s].a;
+        const Layer& L = *srcs[s].layer;
+        const int64_t K = srcs[s].up ? L.V : L.H;
+        REQUIRE(a.cols == K, "state width does not match the weight matrix");
+        REQUIRE(a.rows >= M, "state has fewer rows than requested");
+        REQUIRE((srcs[s].up ? L.H : L.V) == N, "output width does not match the weight matrix");
+        g.src[s].a = Operand{a.p0, a.p1, nullptr, a.ld, 1};
+        g.src[s].b = srcs[s].up ? Operand{nullptr, nullptr, L.W, 1, (int64_t)L.H} : Operand{nullptr, nullptr, L.W, (int64_t)L.H, 1};
+        g.src[s].K = K;
+        g.src[s].scale = 1.0f;
+    }
+    g.epi = epi;
+    if (M == 0 || N == 0) return;
+    run_gemm(ctx, g, srcs, nsrc);
+}
+
+// uniforms override: host column-major fp64 -> device row-major fp32
+struct DevUniforms {
+    float* d = nullptr;
+    int64_t ld = 0;
+    ~DevUniforms() { cudaFree(d); }
+};
+static void upload_uniforms(scdbm_ctx* ctx, const double* u, int64_t ldu, int64_t rows, int64_t cols, DevUniforms& out) {
+    if (!u) return;
+    REQUIRE(ldu >= rows, "uniforms: leading dimension smaller than the row count");
+    double* stage = nullptr;
+    const size_t nb = (size_t)ldu * cols * sizeof(double);
+    CK(cudaMalloc(&stage, std::max<size_t>(nb, 8)));
+    CK(cudaMemcpyAsync(stage, u, nb, cudaMemcpyHostToDevice, ctx->stream));
+    out.ld = cols;
+    CK(cudaMalloc(&out.d, std::max<size_t>((size_t)rows * cols * sizeof(float), 8)));
+    k_upload_uniforms<<<grid1d(rows * cols), 256, 0, ctx->stream>>>(stage, ldu, out.d, rows, cols, out.ld);
+    ctx->launches++;
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(stage);
+}
+
+static void refresh_operands(scdbm_ctx* ctx, Layer& L) {
+    dim3 grid((L.V + 31) / 32, (L.H + 31) / 32), block(32, 8);
+    k_refresh_operands<<<grid, block, 0, ctx->stream>>>(L.W, L.V, L.H, L.w0, L.w1, L.ldh, L.t0, L.t1, L.ldv);
+    CK(cudaGetLastError());
+    ctx->launches++;
+}
+
+// ---- the three conditional operators, with explicit Philox stream/tick
+static int epi_mode_for(int what, bool nb_visible) {
+    if (what == SCDBM_OUT_INPUT) return EPI_INPUT;
+    if (what == SCDBM_OUT_POTENTIAL) return nb_visible ? EPI_NBMEAN : EPI_SIGM;
+    if (what == SCDBM_OUT_SAMPLE) return nb_visible ? EPI_NB_DRAW : EPI_SIGM_BERN;
+    throw Err(SCDBM_EINVAL, "`what` must be SCDBM_OUT_INPUT/POTENTIAL/SAMPLE");
+}
+
+struct DrawCfg {
+    uint32_t stream = 0, tick = 0, row_offset = 0;
+    const float* uniforms = nullptr;
+    int64_t ldu = 0;
+    float wscale = 1.0f;
+    float pshift = -1.0f;  // <0: context default
+};
+
+static void op_hidden(scdbm_model* m, int l, const MatView& v, const MatView& out, float factor, int what, const DrawCfg& d,
+                      int64_t rows = -1) {
+    Layer& L = m->L[l];
+    EpiParams e = epi_base(m->ctx);
+    e.mode = epi_mode_for(what, false);
+    e.bias0 = L.b;
+    e.factor = factor;
+    e.wscale = d.wscale;
+    e.stream = d.stream; e.tick = d.tick; e.row_offset = d.row_offset;
+    e.uniforms = d.uniforms; e.ldu = d.ldu;
+    e.out = out;
+    SweepSrc s{&v, &L, true};
+    const int64_t M = rows < 0 ? v.rows : rows;
+    REQUIRE(out.rows >= M && out.cols == L.H, "hidden output has the wrong shape");
+    run_sweep(m->ctx, &s, 1, M, L.H, e);
+}
+
+static void op_visible(scdbm_model* m, int l, const MatView& h, const MatView& out, float factor, int what, const DrawCfg& d,
+                       int64_t rows = -1) {
+    Layer& L = m->L[l];
+    const bool nb = L.kind == SCDBM_VIS_NEGBIN;
+    EpiParams e = epi_base(m->ctx);
+    e.mode = epi_mode_for(what, nb);
+    e.bias0 = L.a;
+    e.factor = (nb && what != SCDBM_OUT_INPUT) ? 1.0f : factor;  // NB visiblepotential! ignores `factor` (quirk B1)
+    if (what == SCDBM_OUT_INPUT) e.factor = 1.0f;
+    e.wscale = d.wscale;
+    e.r = L.r;
+    if (d.pshift >= 0.0f) e.pshift = d.pshift;
+    e.stream = d.stream; e.tick = d.tick; e.row_offset = d.row_offset;
+    e.uniforms = d.uniforms; e.ldu = d.ldu;
+    e.out = out;
+    SweepSrc s{&h, &L, false};
+    const int64_t M = rows < 0 ? h.rows : rows;
+    REQUIRE(out.rows >= M && out.cols == L.V, "visible output has the wrong shape");
+    run_sweep(m->ctx, &s, 1, M, L.V, e);
+}
+
+// intermediate DBM layer `layer` (1 <= layer <= nrbms-1) from both neighbours
+static void op_dbm_layer(scdbm_model* m, int layer, const MatView* below, const float* below_hoist, int64_t ld_hoist,
+                         const MatView& above, const MatView& out, int what, const DrawCfg& d, const MatView* prev,
+                         unsigned int* delta_bits) {
+    Layer& Lb = m->L[layer - 1];
+    Layer& La = m->L[layer];
+    EpiParams e = epi_base(m->ctx);
+    e.mode = epi_mode_for(what, false);
+    e.bias0 = Lb.b;
+    e.bias1 = La.a;
+    e.wscale = d.wscale;
+    e.stream = d.stream; e.tick = d.tick; e.row_offset = d.row_offset;
+    e.uniforms = d.uniforms; e.ldu = d.ldu;
+    e.out = out;
+    if (prev) { e.prev = *prev; e.delta_bits = delta_bits; }
+    SweepSrc s[2];
+    int ns = 0;
+    if (below_hoist) { e.addend = below_hoist; e.ld_add = ld_hoist; }
+    else s[ns++] = SweepSrc{below, &Lb, true};
+    s[ns++] = SweepSrc{&above, &La, false};
+    REQUIRE(out.cols == Lb.H && La.V == Lb.H, "DBM layer widths are inconsistent");
+    run_sweep(m->ctx, s, ns, above.rows, Lb.H, e);
+}
+
+// ================================================================== C ABI
+extern "C" {
+
+const char* scdbm_last_error(void) { return g_err.c_str(); }
+int32_t scdbm_version(void) { return 100; }
+
+int32_t scdbm_ctx_create(int32_t device, uint64_t seed, void* stream, scdbm_ctx** out) {
+    API_BEGIN
+    REQUIRE(out, "out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw Err(SCDBM_ECUDA, std::string("no CUDA device available (libscdbm_b200 has no CPU fallback): ") +
+                                   cudaGetErrorString(e));
+    REQUIRE(device >= 0 && device < count, "device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        throw Err(SCDBM_EUNSUP, std::string("libscdbm_b200 is built for sm_100a only; device is ") + prop.name);
+    auto* c = new scdbm_ctx();
+    c->device = device;
+    c->seed = seed;
+    c->num_sms = prop.multiProcessorCount;
+    if (stream) c->stream = (cudaStream_t)stream;
+    else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    CK(cudaMalloc(&c->d_delta, sizeof(unsigned int)));
+    tc_context_init(c->tc);
+    *out = c;
+    API_END
+}
+
+int32_t scdbm_ctx_destroy(scdbm_ctx* c) {
+    API_BEGIN
+    if (!c) return SCDBM_OK;
+    cudaStreamSynchronize(c->stream);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaFree(c->d_delta);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    API_END
+}
+
+int32_t scdbm_sync(scdbm_ctx* c) {
+    API_BEGIN
+    REQUIRE(c, "ctx is NULL");
+    CK(cudaStreamSynchronize(c->stream));
+    API_END
+}
+
+int32_t scdbm_ctx_set_option(scdbm_ctx* c, const char* name, double value) {
+    API_BEGIN
+    REQUIRE(c && name, "NULL argument");
+    const std::string n(name);
+    if (n == "engine") { REQUIRE(value >= 0 && value <= 2, "engine must be 0, 1 or 2"); c->engine = (int)value; }
+    else if (n == "mu_inv_max") c->mu_inv_max = (float)value;
+    else if (n == "nb_pshift") c->nb_pshift = (float)value;
+    else if (n == "seed") c->seed = (uint64_t)value;
+    else throw Err(SCDBM_EINVAL, "unknown option: " + n);
+    API_END
+}
+
+int32_t scdbm_ctx_get_option(scdbm_ctx* c, const char* name, double* value) {
+    API_BEGIN
+    REQUIRE(c && name && value, "NULL argument");
+    const std::string n(name);
+    if (n == "engine") *value = c->engine;
+    else if (n == "mu_inv_max") *value = c->mu_inv_max;
+    else if (n == "nb_pshift") *value = c->nb_pshift;
+    else if (n == "seed") *value = (double)c->seed;
+    else if (n == "num_sms") *value = c->num_sms;
+    else if (n == "tc_launches") *value = (double)c->tc_launches;
+    else throw Err(SCDBM_EINVAL, "unknown option: " + n);
+    API_END
+}
+
+int32_t scdbm_timer_start(scdbm_ctx* c) {
+    API_BEGIN
+    REQUIRE(c, "ctx is NULL");
+    CK(cudaEventRecord(c->ev0, c->stream));
+    API_END
+}
+int32_t scdbm_timer_stop(scdbm_ctx* c, float* ms) {
+    API_BEGIN
+    REQUIRE(c && ms, "NULL argument");
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    API_END
+}
+int32_t scdbm_launch_count(scdbm_ctx* c, int64_t* count, int32_t reset) {
+    API_BEGIN
+    REQUIRE(c, "ctx is NULL");
+    if (count) *count = c->launches;
+    if (reset) { c->launches = 0; c->tc_launches = 0; }
+    API_END
+}
+
+// ------------------------------------------------------------------- model
+int32_t scdbm_model_create(scdbm_ctx* c, int32_t nrbms, const int32_t* units, int32_t visible_kind, scdbm_model** out) {
+    API_BEGIN
+    REQUIRE(c && units && out, "NULL argument");
+    REQUIRE(nrbms >= 1 && nrbms <= 16, "nrbms must be in 1..16");
+    REQUIRE(visible_kind == SCDBM_VIS_BERNOULLI || visible_kind == SCDBM_VIS_NEGBIN, "unknown visible kind");
+    for (int i = 0; i <= nrbms; ++i) REQUIRE(units[i] > 0, "layer sizes must be positive");
+    auto* m = new scdbm_model{c, {}};
+    m->L.resize(nrbms);
+    for (int l = 0; l < nrbms; ++l) {
+        Layer& L = m->L[l];
+        L.V = units[l];
+        L.H = units[l + 1];
+        L.kind = (l == 0) ? visible_kind : SCDBM_VIS_BERNOULLI;
+        L.ldh = round_up(L.H, 64);
+        L.ldv = round_up(L.V, 64);
+        CK(cudaMalloc(&L.W, (size_t)L.V * L.H * sizeof(float)));
+        CK(cudaMalloc(&L.a, (size_t)L.V * sizeof(float)));
+        CK(cudaMalloc(&L.b, (size_t)L.H * sizeof(float)));
+        CK(cudaMalloc(&L.r, (size_t)L.V * sizeof(float)));
+        CK(cudaMemsetAsync(L.W, 0, (size_t)L.V * L.H * sizeof(float), c->stream));
+        CK(cudaMemsetAsync(L.a, 0, (size_t)L.V * sizeof(float), c->stream));
+        CK(cudaMemsetAsync(L.b, 0, (size_t)L.H * sizeof(float), c->stream));
+        k_fill_f32<<<grid1d(L.V), 256, 0, c->stream>>>(L.r, L.V, 1.0f);
+        const size_t wb = (size_t)L.V * L.ldh * sizeof(__nv_bfloat16), tb = (size_t)L.H * L.ldv * sizeof(__nv_bfloat16);
+        CK(cudaMalloc(&L.w0, wb)); CK(cudaMalloc(&L.w1, wb));
+        CK(cudaMalloc(&L.t0, tb)); CK(cudaMalloc(&L.t1, tb));
+        CK(cudaMemsetAsync(L.w0, 0, wb, c->stream)); CK(cudaMemsetAsync(L.w1, 0, wb, c->stream));
+        CK(cudaMemsetAsync(L.t0, 0, tb, c->stream)); CK(cudaMemsetAsync(L.t1, 0, tb, c->stream));
+    }
+    *out = m;
+    API_END
+}
+
+int32_t scdbm_model_destroy(scdbm_model* m) {
+    API_BEGIN
+    if (!m) return SCDBM_OK;
+    cudaStreamSynchronize(m->ctx->stream);
+    for (auto& L : m->L) {
+        cudaFree(L.W); cudaFree(L.a); cudaFree(L.b); cudaFree(L.r);
+        cudaFree(L.w0); cudaFree(L.w1); cudaFree(L.t0); cudaFree(L.t1);
+    }
+    delete m;
+    API_END
+}
+
+int32_t scdbm_model_set_layer(scdbm_model* m, int32_t l, const double* W, int64_t ldw, const double* a, const double* b,
+                              const double* r) {
+    API_BEGIN
+    REQUIRE(m, "model is NULL");
+    REQUIRE(l >= 0 && l < (int)m->L.size(), "layer index out of range");
+    Layer& L = m->L[l];
+    cudaStream_t st = m->ctx->stream;
+    if (W) {
+        REQUIRE(ldw >= L.V, "ldw smaller than the number of visible units");
+        std::vector<float> w((size_t)L.V * L.H);
+        for (int h = 0; h < L.H; ++h)
+            for (int v = 0; v < L.V; ++v) {
+                const double x = W[(size_t)h * ldw + v];
+                REQUIRE(std::isfinite(x), "weights contain NaN/Inf");
+                w[(size_t)v * L.H + h] = (float)x;
+            }
+        CK(cudaMemcpyAsync(L.W, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        refresh_operands(m->ctx, L);
+    }
+    auto up = [&](float* dst, const double* src, int n, const char* what, bool need_pos, bool need_neg) {
+        if (!src) return;
+        std::vector<float> t(n);
+        for (int i = 0; i < n; ++i) {
+            REQUIRE(std::isfinite(src[i]), std::string(what) + " contains NaN/Inf");
+            if (need_pos) REQUIRE(src[i] > 0.0, std::string(what) + " must be positive");
+            if (need_neg) REQUIRE(src[i] < 0.0, std::string(what) + " must be negative for an NB visible layer");
+            t[i] = (float)src[i];
+        }
+        CK(cudaMemcpyAsync(dst, t.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    };
+    up(L.a, a, L.V, "visbias", false, L.kind == SCDBM_VIS_NEGBIN);
+    up(L.b, b, L.H, "hidbias", false, false);
+    if (r) {
+        REQUIRE(L.kind == SCDBM_VIS_NEGBIN, "inversedispersion given for a non-NB layer");
+        up(L.r, r, L.V, "inversedispersion", true, false);
+    }
+    API_END
+}
+
+int32_t scdbm_model_get_layer(scdbm_model* m, int32_t l, double* W, int64_t ldw, double* a, double* b, double* r) {
+    API_BEGIN
+    REQUIRE(m, "model is NULL");
+    REQUIRE(l >= 0 && l < (int)m->L.size(), "layer index out of range");
+    Layer& L = m->L[l];
+    cudaStream_t st = m->ctx->stream;
+    CK(cudaStreamSynchronize(st));
+    if (W) {
+        REQUIRE(ldw >= L.V, "ldw smaller than the number of visible units");
+        std::vector<float> w((size_t)L.V * L.H);
+        CK(cudaMemcpy(w.data(), L.W, w.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        for (int h = 0; h < L.H; ++h)
+            for (int v = 0; v < L.V; ++v) W[(size_t)h * ldw + v] = (double)w[(size_t)v * L.H + h];
+    }
+    auto down = [&](double* dst, const float* src, int n) {
+        if (!dst) return;
+        std::vector<float> t(n);
+        CK(cudaMemcpy(t.data(), src, n * sizeof(float), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; ++i) dst[i] = (double)t[i];
+    };
+    down(a, L.a, L.V);
+    down(b, L.b, L.H);
+    down(r, L.r, L.V);
+    API_END
+}
+
+int32_t scdbm_model_copy_layer(scdbm_model* dst, int32_t dl, scdbm_model* src, int32_t sl) {
+    API_BEGIN
+    REQUIRE(dst && src, "NULL argument");
+    REQUIRE(dl >= 0 && dl < (int)dst->L.size() && sl >= 0 && sl < (int)src->L.size(), "layer index out of range");
+    Layer& D = dst->L[dl];
+    Layer& S = src->L[sl];
+    REQUIRE(D.V == S.V && D.H == S.H, "layer shapes differ");
+    cudaStream_t st = dst->ctx->stream;
+    CK(cudaStreamSynchronize(src->ctx->stream));
+    CK(cudaMemcpyAsync(D.W, S.W, (size_t)D.V * D.H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(D.a, S.a, (size_t)D.V * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(D.b, S.b, (size_t)D.H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(D.r, S.r, (size_t)D.V * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    refresh_operands(dst->ctx, D);
+    API_END
+}
+
+__global__ void k_init_weights(float* W, int V, int H, int nb, uint32_t k0, uint32_t k1) {
+    const int64_t groups = (H + 3) / 4;
+    const int64_t n = (int64_t)V * groups;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = i / groups, g = i % groups;
+        const uint4 w = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)v, 0xFFFF0000u, stream_id(0, P_INIT)), k0, k1);
+        const uint4 w2 = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)v, 0xFFFF0000u, stream_id(0, P_INIT2)), k0, k1);
+        const uint32_t a[4] = {w.x, w.y, w.z, w.w}, b[4] = {w2.x, w2.y, w2.z, w2.w};
+        for (int j = 0; j < 4 && g * 4 + j < H; ++j) {
+            float x;
+            if (nb) x = -(0.0005f + (0.002f - 0.0005f) * u23(a[j]));
+            else x = sqrtf(-2.0f * logf(u23(a[j]))) * cospif(2.0f * u23(b[j])) * rsqrtf((float)V);
+            W[v * H + g * 4 + j] = x;
+        }
+    }
+}
+
+int32_t scdbm_model_init_layer(scdbm_model* m, int32_t l, const scdbm_mat* x, const double* r, uint64_t seed) {
+    API_BEGIN
+    REQUIRE(m && x, "NULL argument");
+    REQUIRE(l >= 0 && l < (int)m->L.size(), "layer index out of range");
+    Layer& L = m->L[l];
+    REQUIRE(x->v.cols == L.V, "data width does not match the visible layer");
+    REQUIRE(x->v.rows > 0, "data has no rows");
+    scdbm_ctx* c = m->ctx;
+    const bool nb = L.kind == SCDBM_VIS_NEGBIN;
+    k_init_weights<<<grid1d((int64_t)L.V * ((L.H + 3) / 4)), 256, 0, c->stream>>>(L.W, L.V, L.H, nb ? 1 : 0,
+                                                                                  (uint32_t)seed, (uint32_t)(seed >> 32));
+    CK(cudaGetLastError());
+    c->launches++;
+    refresh_operands(c, L);
+    // column means -> visible bias on the host (V numbers)
+    float* d_sum = nullptr;
+    CK(cudaMalloc(&d_sum, L.V * sizeof(float)));
+    CK(cudaMemsetAsync(d_sum, 0, L.V * sizeof(float), c->stream));
+    dim3 grid((L.V + 31) / 32, (unsigned)std::min<int64_t>((x->v.rows + 7) / 8, 64)), block(32, 8);
+    k_colsum<<<grid, block, 0, c->stream>>>(x->v, 1.0f, d_sum, 1);
+    c->launches++;
+    std::vector<float> s(L.V);
+    CK(cudaMemcpyAsync(s.data(), d_sum, L.V * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_sum);
+    std::vector<double> a(L.V), rr(L.V, 0.5), b(L.H, 0.0);
+    if (r) for (int i = 0; i < L.V; ++i) rr[i] = r[i];
+    for (int i = 0; i < L.V; ++i) {
+        const double mean = (double)s[i] / (double)x->v.rows;
+        if (nb) {
+            // log(mean/(mean+r)); a zero-mean gene gives -Inf in the reference, kept finite here
+            a[i] = std::log(std::max(mean, 1e-30) / (std::max(mean, 1e-30) + rr[i]));
+            a[i] = std::min(a[i], -1e-10);
+        } else a[i] = mean > 0.0 ? std::log(mean / (1.0 - mean)) : 0.0;
+    }
+    return scdbm_model_set_layer(m, l, nullptr, 0, a.data(), b.data(), nb ? rr.data() : nullptr);
+    API_END
+}
+
+// --------------------------------------------------------------------- mat
+int32_t scdbm_mat_create(scdbm_ctx* c, int64_t rows, int64_t cols, int32_t kind, scdbm_mat** out) {
+    API_BEGIN
+    REQUIRE(c && out, "NULL argument");
+    *out = mat_new(c, rows, cols, kind);
+    API_END
+}
+int32_t scdbm_mat_destroy(scdbm_mat* m) {
+    API_BEGIN
+    if (m) { cudaStreamSynchronize(m->ctx->stream); mat_free(m); }
+    API_END
+}
+int32_t scdbm_mat_shape(const scdbm_mat* m, int64_t* rows, int64_t* cols, int32_t* kind) {
+    API_BEGIN
+    REQUIRE(m, "mat is NULL");
+    if (rows) *rows = m->v.rows;
+    if (cols) *cols = m->v.cols;
+    if (kind) *kind = m->v.kind;
+    API_END
+}
+
+int32_t scdbm_mat_upload(scdbm_mat* m, const double* x, int64_t ld) {
+    API_BEGIN
+    REQUIRE(m && x, "NULL argument");
+    REQUIRE(ld >= m->v.rows, "leading dimension smaller than the row count");
+    if (m->v.rows == 0 || m->v.cols == 0) return SCDBM_OK;
+    scdbm_ctx* c = m->ctx;
+    // validate on the host: NaN never enters; counts / binary states must be valid
+    for (int64_t j = 0; j < m->v.cols; ++j)
+        for (int64_t i = 0; i < m->v.rows; ++i) {
+            const double v = x[j * ld + i];
+            if (!std::isfinite(v)) throw Err(SCDBM_EINVAL, "matrix contains NaN/Inf");
+            if (m->v.kind == MAT_COUNT && (v < 0.0 || v > 65535.0 || v != std::floor(v)))
+                throw Err(SCDBM_EINVAL, "count matrix entries must be integers in [0, 65535]");
+            if (m->v.kind == MAT_BINARY && v != 0.0 && v != 1.0)
+                throw Err(SCDBM_EINVAL, "binary matrix entries must be 0 or 1");
+        }
+    // column-block staging keeps the fp64 staging buffer small
+    const int64_t colblk = std::max<int64_t>(32, std::min<int64_t>(m->v.cols, (int64_t)(256ll << 20) / (8 * std::max<int64_t>(ld, 1)) / 32 * 32));
+    double* stage = nullptr;
+    CK(cudaMalloc(&stage, (size_t)ld * colblk * sizeof(double)));
+    for (int64_t c0 = 0; c0 < m->v.cols; c0 += colblk) {
+        const int64_t nc = std::min(colblk, m->v.cols - c0);
+        CK(cudaMemcpyAsync(stage, x + c0 * ld, (size_t)ld * nc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        MatView sub = m->v;
+        sub.p0 += c0;
+        if (sub.p1) sub.p1 += c0;
+        sub.cols = nc;
+        dim3 grid((unsigned)((m->v.rows + 31) / 32), (unsigned)((nc + 31) / 32)), block(32, 8);
+        k_upload_f64<<<grid, block, 0, c->stream>>>(stage, ld, sub);
+        CK(cudaGetLastError());
+        c->launches++;
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    cudaFree(stage);
+    API_END
+}
+
+int32_t scdbm_mat_download(const scdbm_mat* m, double* x, int64_t ld) {
+    API_BEGIN
+    REQUIRE(m && x, "NULL argument");
+    REQUIRE(ld >= m->v.rows, "leading dimension smaller than the row count");
+    if (m->v.rows == 0 || m->v.cols == 0) return SCDBM_OK;
+    scdbm_ctx* c = m->ctx;
+    const int64_t colblk = std::max<int64_t>(32, std::min<int64_t>(m->v.cols, (int64_t)(256ll << 20) / (8 * std::max<int64_t>(ld, 1)) / 32 * 32));
+    double* stage = nullptr;
+    CK(cudaMalloc(&stage, (size_t)ld * colblk * sizeof(double)));
+    CK(cudaMemsetAsync(stage, 0, (size_t)ld * colblk * sizeof(double), c->stream));
+    for (int64_t c0 = 0; c0 < m->v.cols; c0 += colblk) {
+        const int64_t nc = std::min(colblk, m->v.cols - c0);
+        MatView sub = m->v;
+        sub.p0 += c0;
+        if (sub.p1) sub.p1 += c0;
+        sub.cols = nc;
+        dim3 grid((unsigned)((m->v.rows + 31) / 32), (unsigned)((nc + 31) / 32)), block(32, 8);
+        k_download_f64<<<grid, block, 0, c->stream>>>(sub, stage, ld);
+        CK(cudaGetLastError());
+        c->launches++;
+        if (ld == m->v.rows) {
+            CK(cudaMemcpyAsync(x + c0 * ld, stage, (size_t)ld * nc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            CK(cudaMemcpy2DAsync(x + c0 * ld, ld * sizeof(double), stage, ld * sizeof(double), m->v.rows * sizeof(double), nc,
+                                 cudaMemcpyDeviceToHost, c->stream));
+        }
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    cudaFree(stage);
+    API_END
+}
+
+int32_t scdbm_mat_download_u16(const scdbm_mat* m, uint16_t* x) {
+    API_BEGIN
+    REQUIRE(m && x, "NULL argument");
+    const int64_t n = m->v.rows * m->v.cols;
+    if (n == 0) return SCDBM_OK;
+    scdbm_ctx* c = m->ctx;
+    uint16_t* d = nullptr;
+    CK(cudaMalloc(&d, (size_t)n * sizeof(uint16_t)));
+    k_download_u16<<<grid1d(n), 256, 0, c->stream>>>(m->v, d);
+    c->launches++;
+    CK(cudaMemcpyAsync(x, d, (size_t)n * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    API_END
+}
+
+int32_t scdbm_mat_copy(scdbm_mat* dst, const scdbm_mat* src) {
+    API_BEGIN
+    REQUIRE(dst && src, "NULL argument");
+    REQUIRE(dst->v.rows == src->v.rows && dst->v.cols == src->v.cols, "shapes differ");
+    REQUIRE(dst->v.kind == src->v.kind, "kinds differ");
+    if (dst->v.rows == 0) return SCDBM_OK;
+    k_copy_rows<<<(unsigned)dst->v.rows, 128, 0, dst->ctx->stream>>>(src->v, dst->v, dst->v.rows);
+    CK(cudaGetLastError());
+    dst->ctx->launches++;
+    API_END
+}
+
+int32_t scdbm_mat_column_stats(const scdbm_mat* m, double* mean, double* var, double* zerofrac) {
+    API_BEGIN
+    REQUIRE(m, "mat is NULL");
+    const int64_t C = m->v.cols, R = m->v.rows;
+    REQUIRE(R > 0 && C > 0, "matrix is empty");
+    scdbm_ctx* c = m->ctx;
+    double* d = nullptr;
+    CK(cudaMalloc(&d, 3 * C * sizeof(double)));
+    CK(cudaMemsetAsync(d, 0, 3 * C * sizeof(double), c->stream));
+    dim3 grid((unsigned)((C + 31) / 32), (unsigned)std::min<int64_t>((R + 7) / 8, 256)), block(32, 8);
+    k_colstats<<<grid, block, 0, c->stream>>>(m->v, d, d + C, d + 2 * C);
+    c->launches++;
+    std::vector<double> h(3 * C);
+    CK(cudaMemcpyAsync(h.data(), d, 3 * C * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    for (int64_t j = 0; j < C; ++j) {
+        const double mu = h[j] / R;
+        if (mean) mean[j] = mu;
+        if (var) var[j] = R > 1 ? (h[C + j] - R * mu * mu) / (R - 1) : 0.0;
+        if (zerofrac) zerofrac[j] = h[2 * C + j] / R;
+    }
+    API_END
+}
+
+// ------------------------------------------------- single conditional ops
+int32_t scdbm_hidden(scdbm_model* m, int32_t l, const scdbm_mat* v, scdbm_mat* out, double factor, int32_t what,
+                     uint32_t tick, const double* uniforms, int64_t ldu) {
+    API_BEGIN
+    REQUIRE(m && v && out, "NULL argument");
+    REQUIRE(l >= 0 && l < (int)m->L.size(), "layer index out of range");
+    REQUIRE(out->v.rows == v->v.rows, "row counts differ");
+    DevUniforms du;
+    upload_uniforms(m->ctx, uniforms, ldu, out->v.rows, out->v.cols, du);
+    DrawCfg d;
+    d.stream = stream_id(l + 1); d.tick = tick; d.uniforms = du.d; d.ldu = du.ld;
+    op_hidden(m, l, v->v, out->v, (float)factor, what, d);
+    if (du.d) CK(cudaStreamSynchronize(m->ctx->stream));
+    API_END
+}
+
+int32_t scdbm_visible(scdbm_model* m, int32_t l, const scdbm_mat* h, scdbm_mat* out, double factor, int32_t what,
+                      uint32_t tick, const double* uniforms, int64_t ldu) {
+    API_BEGIN
+    REQUIRE(m && h && out, "NULL argument");
+    REQUIRE(l >= 0 && l < (int)m->L.size(), "layer index out of range");
+    REQUIRE(out->v.rows == h->v.rows, "row counts differ");
+    DevUniforms du;
+    upload_uniforms(m->ctx, uniforms, ldu, out->v.rows, out->v.cols, du);
+    DrawCfg d;
+    d.stream = stream_id(l); d.tick = tick; d.uniforms = du.d; d.ldu = du.ld;
+    op_visible(m, l, h->v, out->v, (float)factor, what, d);
+    if (du.d) CK(cudaStreamSynchronize(m->ctx->stream));
+    API_END
+}
+
+int32_t scdbm_dbm_layer(scdbm_model* m, int32_t layer, const scdbm_mat* below, const scdbm_mat* above, scdbm_mat* out,
+                        int32_t what, uint32_t tick, const double* uniforms, int64_t ldu) {
+    API_BEGIN
+    REQUIRE(m && below && above && out, "NULL argument");
+    REQUIRE(layer >= 1 && layer <= (int)m->L.size() - 1, "not an intermediate layer");
+    REQUIRE(below->v.rows == above->v.rows && out->v.rows == above->v.rows, "row counts differ");
+    DevUniforms du;
+    upload_uniforms(m->ctx, uniforms, ldu, out->v.rows, out->v.cols, du);
+    DrawCfg d;
+    d.stream = stream_id(layer); d.tick = tick; d.uniforms = du.d; d.ldu = du.ld;
+    op_dbm_layer(m, layer, &below->v, nullptr, 0, above->v, out->v, what, d, nullptr, nullptr);
+    if (du.d) CK(cudaStreamSynchronize(m->ctx->stream));
+    API_END
+}
+
+// --------------------------------------------------------------- particles
+int32_t scdbm_particles_create(scdbm_model* m, int64_t n, uint64_t row_offset, int32_t real_valued, scdbm_particles** out) {
+    API_BEGIN
+    REQUIRE(m && out, "NULL argument");
+    REQUIRE(n >= 0, "nparticles must be non-negative");
+    REQUIRE(row_offset + (uint64_t)n <= 0xFFFFFFFFull, "global particle index exceeds 2^32");
+    auto* p = new scdbm_particles{m, n, row_offset, 1, real_valued != 0, {}, {}};
+    const int nl = m->nlayers();
+    for (int i = 0; i < nl; ++i) {
+        int kind = i == 0 ? (m->L[0].kind == SCDBM_VIS_NEGBIN ? MAT_COUNT : MAT_BINARY) : MAT_BINARY;
+        if (real_valued && i > 0) kind = MAT_REAL;
+        if (real_valued && i == 0) { p->cur.push_back(nullptr); p->nxt.push_back(nullptr); continue; }
+        p->cur.push_back(mat_new(m->ctx, n, m->units(i), kind));
+        p->nxt.push_back(real_valued ? nullptr : mat_new(m->ctx, n, m->units(i), kind));
+    }
+    *out = p;
+    API_END
+}
+
+int32_t scdbm_particles_destroy(scdbm_particles* p) {
+    API_BEGIN
+    if (!p) return SCDBM_OK;
+    cudaStreamSynchronize(p->model->ctx->stream);
+    for (auto* x : p->cur) mat_free(x);
+    for (auto* x : p->nxt) mat_free(x);
+    if (p->alias0) delete p->alias0;
+    cudaFree(p->hoist);
+    delete p;
+    API_END
+}
+
+int32_t scdbm_particles_init(scdbm_particles* p, int32_t biased) {
+    API_BEGIN
+    REQUIRE(p, "particles is NULL");
+    REQUIRE(!p->real_valued, "mean-field particles are initialised by scdbm_meanfield");
+    scdbm_model* m = p->model;
+    scdbm_ctx* c = m->ctx;
+    const uint32_t k0 = (uint32_t)c->seed, k1 = (uint32_t)(c->seed >> 32);
+    for (int i = 0; i < m->nlayers(); ++i) {
+        MatView& v = p->cur[i]->v;
+        if (v.rows == 0) continue;
+        int mode;
+        const float* bias = nullptr;
+        const float* r = nullptr;
+        if (i == 0) {
+            if (m->L[0].kind == SCDBM_VIS_NEGBIN) { mode = 3; r = m->L[0].r; }
+            else { mode = biased ? 1 : 0; bias = m->L[0].a; }
+        } else { mode = biased ? 1 : 0; bias = m->L[i - 1].b; }
+        k_init<<<grid1d(v.rows * ((v.cols + 3) / 4)), 256, 0, c->stream>>>(v, mode, bias, r, k0, k1, (uint32_t)i,
+                                                                            (uint32_t)p->row_offset);
+        CK(cudaGetLastError());
+        c->launches++;
+    }
+    p->clock = 1;
+    API_END
+}
+
+int32_t scdbm_particles_layer(scdbm_particles* p, int32_t layer, scdbm_mat** borrowed) {
+    API_BEGIN
+    REQUIRE(p && borrowed, "NULL argument");
+    REQUIRE(layer >= 0 && layer < (int)p->cur.size(), "layer index out of range");
+    scdbm_mat* x = (layer == 0 && p->real_valued) ? p->alias0 : p->cur[layer];
+    REQUIRE(x, "layer 0 of mean-field particles is set by scdbm_meanfield");
+    *borrowed = x;
+    API_END
+}
+
+int32_t scdbm_particles_clock(scdbm_particles* p, int64_t* clock, int64_t set_to) {
+    API_BEGIN
+    REQUIRE(p, "particles is NULL");
+    if (set_to >= 0) p->clock = set_to;
+    if (clock) *clock = p->clock;
+    API_END
+}
+
+static void gibbs_dbm_steps(scdbm_model* m, scdbm_particles* p, int nsteps, float temperature) {
+    const int nl = m->nlayers();
+    for (int step = 0; step < nsteps; ++step) {
+        DrawCfg d;
+        d.tick = (uint32_t)p->clock;
+        d.row_offset = (uint32_t)p->row_offset;
+        d.wscale = temperature;
+        d.stream = stream_id(0);
+        op_visible(m, 0, p->cur[1]->v, p->nxt[0]->v, 1.0f, SCDBM_OUT_SAMPLE, d);
+        for (int i = 1; i < nl - 1; ++i) {
+            d.stream = stream_id(i);
+            op_dbm_layer(m, i, &p->cur[i - 1]->v, nullptr, 0, p->cur[i + 1]->v, p->nxt[i]->v, SCDBM_OUT_SAMPLE, d, nullptr, nullptr);
+        }
+        d.stream = stream_id(nl - 1);
+        op_hidden(m, nl - 2, p->cur[nl - 2]->v, p->nxt[nl - 1]->v, 1.0f, SCDBM_OUT_SAMPLE, d);
+        std::swap(p->cur, p->nxt);
+        p->clock++;
+    }
+}
+
+int32_t scdbm_gibbs(scdbm_model* m, scdbm_particles* p, int32_t nsteps, double temperature, double upfactor,
+                    double downfactor) {
+    API_BEGIN
+    REQUIRE(m && p, "NULL argument");
+    REQUIRE(p->model == m, "particles belong to a different model");
+    REQUIRE(!p->real_valued, "cannot Gibbs-sample mean-field particles");
+    REQUIRE(nsteps >= 0, "nsteps must be non-negative");
+    if (p->n == 0) return SCDBM_OK;
+    if (m->L.size() == 1) {
+        // gibbssample!(particles, rbm, nsteps, up, down): v | h, then h | new v
+        for (int s = 0; s < nsteps; ++s) {
+            DrawCfg d;
+            d.row_offset = (uint32_t)p->row_offset;
+            d.wscale = (float)temperature;
+            d.tick = (uint32_t)p->clock; d.stream = stream_id(0);
+            op_visible(m, 0, p->cur[1]->v, p->cur[0]->v, (float)downfactor, SCDBM_OUT_SAMPLE, d);
+            p->clock++;
+            d.tick = (uint32_t)p->clock; d.stream = stream_id(1);
+            op_hidden(m, 0, p->cur[0]->v, p->cur[1]->v, (float)upfactor, SCDBM_OUT_SAMPLE, d);
+            p->clock++;
+        }
+    } else {
+        gibbs_dbm_steps(m, p, nsteps, (float)temperature);
+    }
+    API_END
+}
+
+int32_t scdbm_gibbs_negbin_rbm(scdbm_model* m, scdbm_particles* p, int32_t nsteps, double upfactor, double downfactor) {
+    API_BEGIN
+    REQUIRE(m && p, "NULL argument");
+    REQUIRE(p->model == m && m->L.size() == 1, "needs particles of a single-RBM model");
+    REQUIRE(m->L[0].kind == SCDBM_VIS_NEGBIN, "model is not an NB-Bernoulli RBM");
+    if (p->n == 0) return SCDBM_OK;
+    for (int s = 0; s < nsteps; ++s) {
+        DrawCfg d;
+        d.row_offset = (uint32_t)p->row_offset;
+        d.tick = (uint32_t)p->clock;
+        d.stream = stream_id(0);
+        d.pshift = 1e-6f;
+        op_visible(m, 0, p->cur[1]->v, p->nxt[0]->v, (float)downfactor, SCDBM_OUT_SAMPLE, d);
+        d.stream = stream_id(1);
+        d.pshift = -1.0f;
+        op_hidden(m, 0, p->cur[0]->v, p->nxt[1]->v, (float)upfactor, SCDBM_OUT_SAMPLE, d);
+        std::swap(p->cur, p->nxt);
+        p->clock++;
+    }
+    API_END
+}
+
+int32_t scdbm_particles_visible_potential(scdbm_model* m, scdbm_particles* p, scdbm_mat* out) {
+    API_BEGIN
+    REQUIRE(m && p && out, "NULL argument");
+    DrawCfg d;
+    op_visible(m, 0, p->cur[1]->v, out->v, 1.0f, SCDBM_OUT_POTENTIAL, d);
+    API_END
+}
+
+// -------------------------------------------------------------- mean-field
+static float read_delta(scdbm_ctx* c) {
+    unsigned int bits = 0;
+    CK(cudaMemcpyAsync(&bits, c->d_delta, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float f;
+    memcpy(&f, &bits, sizeof(f));
+    return f;
+}
+
+static void meanfield_impl(scdbm_model* m, const scdbm_mat* x, double eps, int maxiter, scdbm_particles* mu, int* niter,
+                           double* delta_out) {
+    scdbm_ctx* c = m->ctx;
+    const int nl = m->nlayers();
+    const int64_t n = x->v.rows;
+    REQUIRE(mu->real_valued, "mu must be created with real_valued = 1");
+    REQUIRE(mu->n == n, "mu must have as many particles as x has rows");
+    REQUIRE(x->v.cols == m->L[0].V, "data width does not match the visible layer");
+    if (!mu->alias0) mu->alias0 = new scdbm_mat{c, x->v, false};
+    mu->alias0->v = x->v;
+    if (n == 0) { if (niter) *niter = 0; if (delta_out) *delta_out = 0; return; }
+    // hoist x*W1 (loop invariant; the reference recomputes it, quirk B10)
+    Layer& L0 = m->L[0];
+    if (!mu->hoist) CK(cudaMalloc(&mu->hoist, (size_t)n * L0.H * sizeof(float)));
+    {
+        EpiParams e = epi_base(c);
+        e.mode = EPI_RAW_F32;
+        e.out_f32 = mu->hoist;
+        e.ldo = L0.H;
+        SweepSrc s{&x->v, &L0, true};
+        run_sweep(c, &s, 1, n, L0.H, e);
+    }
+    auto from_hoist = [&](const MatView& out, float factor, const MatView* prev) {
+        // sigm(factor * (x W1 + b1)) with no contraction
+        EpiParams e = epi_base(c);
+        e.mode = EPI_SIGM;
+        e.bias0 = L0.b;
+        e.addend = mu->hoist; e.ld_add = L0.H;
+        e.factor = factor;
+        e.out = out;
+        if (prev) { e.prev = *prev; e.delta_bits = c->d_delta; }
+        run_sweep(c, nullptr, 0, n, L0.H, e);
+    };
+    // bottom-up initialisation with doubled weights except for the top layer (dbmtraining.jl:182-186)
+    DrawCfg d;
+    for (int i = 1; i < nl; ++i) {
+        const float factor = (i < nl - 1) ? 2.0f : 1.0f;
+        if (i == 1) from_hoist(mu->cur[1]->v, factor, nullptr);
+        else op_hidden(m, i - 1, mu->cur[i - 1]->v, mu->cur[i]->v, factor, SCDBM_OUT_POTENTIAL, d);
+    }
+    double delta = 1.0;
+    int it = 0;
+    while (delta > eps && (maxiter <= 0 || it < maxiter)) {
+        CK(cudaMemsetAsync(c->d_delta, 0, sizeof(unsigned int), c->stream));
+        for (int i = 1; i < nl - 1; ++i) {
+            const MatView& cur = mu->cur[i]->v;
+            op_dbm_layer(m, i, i == 1 ? nullptr : &mu->cur[i - 1]->v, i == 1 ? mu->hoist : nullptr, L0.H, mu->cur[i + 1]->v, cur,
+                         SCDBM_OUT_POTENTIAL, d, &cur, c->d_delta);
+        }
+        // last layer from the NEW layer below (Gauss-Seidel, dbmtraining.jl:218-224)
+        {
+            const MatView& cur = mu->cur[nl - 1]->v;
+            if (nl == 2) from_hoist(cur, 1.0f, &cur);
+            else {
+                Layer& L = m->L[nl - 2];
+                EpiParams e = epi_base(c);
+                e.mode = EPI_SIGM;
+                e.bias0 = L.b;
+                e.out = cur;
+                e.prev = cur;
+                e.delta_bits = c->d_delta;
+                SweepSrc s{&mu->cur[nl - 2]->v, &L, true};
+                run_sweep(c, &s, 1, n, L.H, e);
+            }
+        }
+        delta = read_delta(c);
+        ++it;
+    }
+    if (niter) *niter = it;
+    if (delta_out) *delta_out = delta;
+}
+
+int32_t scdbm_meanfield(scdbm_model* m, const scdbm_mat* x, double eps, int32_t maxiter, scdbm_particles* mu,
+                        int32_t* niter, double* delta) {
+    API_BEGIN
+    REQUIRE(m && x && mu, "NULL argument");
+    REQUIRE(mu->model == m, "mu belongs to a different model");
+    int it = 0;
+    meanfield_impl(m, x, eps, maxiter, mu, &it, delta);
+    if (niter) *niter = it;
+    API_END
+}
+
+// ---------------------------------------------------------------- learning
+int32_t scdbm_opt_create(scdbm_model* m, scdbm_opt** out) {
+    API_BEGIN
+    REQUIRE(m && out, "NULL argument");
+    auto* o = new scdbm_opt{m};
+    int64_t off = 0;
+    for (auto& L : m->L) {
+        o->offW.push_back(off); off += (int64_t)L.V * L.H;
+        o->offA.push_back(off); off += L.V;
+        o->offB.push_back(off); off += L.H;
+    }
+    o->n = off;
+    CK(cudaMalloc(&o->buf, off * sizeof(float)));
+    CK(cudaMemsetAsync(o->buf, 0, off * sizeof(float), m->ctx->stream));
+    *out = o;
+    API_END
+}
+int32_t scdbm_opt_destroy(scdbm_opt* o) {
+    API_BEGIN
+    if (o) { cudaStreamSynchronize(o->model->ctx->stream); cudaFree(o->buf); delete o; }
+    API_END
+}
+
+// dW = pos_scale * v'h - neg_scale * vm'hm ; da, db likewise from column sums
+static void gradient_layer(scdbm_opt* o, int l, const MatView& v, const MatView& vm, const MatView& h, const MatView& hm,
+                           float pos_scale, float neg_scale) {
+    scdbm_model* m = o->model;
+    scdbm_ctx* c = m->ctx;
+    Layer& L = m->L[l];
+    REQUIRE(v.cols == L.V && vm.cols == L.V && h.cols == L.H && hm.cols == L.H, "gradient: widths do not match the RBM");
+    REQUIRE(v.rows == h.rows && vm.rows == hm.rows, "gradient: row counts of v/h (or vmodel/hmodel) differ");
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.nsrc = 2;
+    g.M = L.V;
+    g.N = L.H;
+    g.src[0].a = Operand{v.p0, v.p1, nullptr, 1, v.ld};
+    g.src[0].b = Operand{h.p0, h.p1, nullptr, 1, h.ld};
+    g.src[0].K = v.rows;
+    g.src[0].scale = pos_scale;
+    g.src[1].a = Operand{vm.p0, vm.p1, nullptr, 1, vm.ld};
+    g.src[1].b = Operand{hm.p0, hm.p1, nullptr, 1, hm.ld};
+    g.src[1].K = vm.rows;
+    g.src[1].scale = -neg_scale;
+    g.epi = epi_base(c);
+    g.epi.mode = EPI_RAW_F32;
+    g.epi.out_f32 = o->buf + o->offW[l];
+    g.epi.ldo = L.H;
+    bool done = false;
+    if (c->engine != SCDBM_ENGINE_SIMT) {
+        TcGradArgs ga{v, h, vm, hm, pos_scale, -neg_scale, g.epi.out_f32, L.V, L.H};
+        if (tc_grad_supported(ga)) {
+            CK(launch_grad_tc(c->tc, ga, c->num_sms, c->stream));
+            c->tc_launches++;
+            done = true;
+        }
+    }
+    if (!done) CK(launch_gemm_simt(g, c->stream));
+    c->launches++;
+    float* ga = o->buf + o->offA[l];
+    float* gb = o->buf + o->offB[l];
+    CK(cudaMemsetAsync(ga, 0, (size_t)(L.V + L.H) * sizeof(float), c->stream));  // offA and offB are adjacent
+    auto colsum = [&](const MatView& s, float scale, float* out) {
+        if (s.rows == 0) return;
+        dim3 grid((unsigned)((s.cols + 31) / 32), (unsigned)std::min<int64_t>((s.rows + 7) / 8, 128)), block(32, 8);
+        k_colsum<<<grid, block, 0, c->stream>>>(s, scale, out, 1);
+        c->launches++;
+    };
+    colsum(v, pos_scale, ga);
+    colsum(vm, -neg_scale, ga);
+    colsum(h, pos_scale, gb);
+    colsum(hm, -neg_scale, gb);
+    CK(cudaGetLastError());
+}
+
+int32_t scdbm_compute_gradient(scdbm_opt* o, scdbm_model* m, int32_t l, const scdbm_mat* v, const scdbm_mat* vmodel,
+                               const scdbm_mat* h, const scdbm_mat* hmodel, int64_t nrows_used) {
+    API_BEGIN
+    REQUIRE(o && m && v && vmodel && h && hmodel, "NULL argument");
+    REQUIRE(o->model == m, "optimizer belongs to a different model");
+    REQUIRE(l >= 0 && l < (int)m->L.size(), "layer index out of range");
+    const int64_t npos = v->v.rows;
+    const int64_t nneg = nrows_used > 0 ? std::min<int64_t>(nrows_used, vmodel->v.rows) : vmodel->v.rows;
+    REQUIRE(npos > 0 && nneg > 0, "gradient needs at least one positive and one negative sample");
+    // the reference skips the division when the count is 1 (src/optimizers.jl:272-279)
+    gradient_layer(o, l, v->v, rows_view(vmodel->v, nneg), h->v, rows_view(hmodel->v, nneg), 1.0f / (float)npos, 1.0f / (float)nneg);
+    API_END
+}
+
+int32_t scdbm_compute_gradient_dbm(scdbm_opt* o, scdbm_model* m, scdbm_particles* mu, scdbm_particles* p, double pos_scale,
+                                   double neg_scale) {
+    API_BEGIN
+    REQUIRE(o && m && mu && p, "NULL argument");
+    REQUIRE(o->model == m && mu->model == m && p->model == m, "objects belong to different models");
+    REQUIRE(mu->alias0, "mu has not been filled by scdbm_meanfield");
+    const float ps = pos_scale > 0 ? (float)pos_scale : 1.0f / (float)std::max<int64_t>(mu->n, 1);
+    const float ns = neg_scale > 0 ? (float)neg_scale : 1.0f / (float)std::max<int64_t>(p->n, 1);
+    for (int l = 0; l < (int)m->L.size(); ++l) {
+        const MatView& v = l == 0 ? mu->alias0->v : mu->cur[l]->v;
+        gradient_layer(o, l, v, p->cur[l]->v, mu->cur[l + 1]->v, p->cur[l + 1]->v, ps, ns);
+    }
+    API_END
+}
+
+static void update_layer(scdbm_model* m, scdbm_opt* o, int l, float lr) {
+    scdbm_ctx* c = m->ctx;
+    Layer& L = m->L[l];
+    const bool nb = L.kind == SCDBM_VIS_NEGBIN;
+    const int64_t nW = (int64_t)L.V * L.H;
+    k_update<<<grid1d(nW), 256, 0, c->stream>>>(L.W, o->buf + o->offW[l], nW, lr, 0.0f, nb ? 1 : 0);
+    k_update<<<grid1d(L.V), 256, 0, c->stream>>>(L.a, o->buf + o->offA[l], L.V, lr, -1e-10f, nb ? 1 : 0);
+    k_update<<<grid1d(L.H), 256, 0, c->stream>>>(L.b, o->buf + o->offB[l], L.H, lr, 0.0f, 0);
+    CK(cudaGetLastError());
+    c->launches += 3;
+    refresh_operands(c, L);
+}
+
+int32_t scdbm_update_parameters(scdbm_model* m, scdbm_opt* o, int32_t l, double lr) {
+    API_BEGIN
+    REQUIRE(m && o, "NULL argument");
+    REQUIRE(o->model == m, "optimizer belongs to a different model");
+    REQUIRE(l < (int)m->L.size(), "layer index out of range");
+    if (l >= 0) update_layer(m, o, l, (float)lr);
+    else for (int i = 0; i < (int)m->L.size(); ++i) update_layer(m, o, i, (float)lr);
+    API_END
+}
+
+int32_t scdbm_opt_get_gradient(scdbm_opt* o, int32_t l, double* W, int64_t ldw, double* a, double* b) {
+    API_BEGIN
+    REQUIRE(o, "optimizer is NULL");
+    scdbm_model* m = o->model;
+    REQUIRE(l >= 0 && l < (int)m->L.size(), "layer index out of range");
+    Layer& L = m->L[l];
+    CK(cudaStreamSynchronize(m->ctx->stream));
+    std::vector<float> t((size_t)L.V * L.H + L.V + L.H);
+    CK(cudaMemcpy(t.data(), o->buf + o->offW[l], t.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    if (W) {
+        REQUIRE(ldw >= L.V, "ldw smaller than the number of visible units");
+        for (int h = 0; h < L.H; ++h)
+            for (int v = 0; v < L.V; ++v) W[(size_t)h * ldw + v] = t[(size_t)v * L.H + h];
+    }
+    const size_t oa = (size_t)L.V * L.H, ob = oa + L.V;
+    if (a) for (int i = 0; i < L.V; ++i) a[i] = t[oa + i];
+    if (b) for (int i = 0; i < L.H; ++i) b[i] = t[ob + i];
+    API_END
+}
+
+int32_t scdbm_opt_buffer(scdbm_opt* o, void** ptr, int64_t* nfloats) {
+    API_BEGIN
+    REQUIRE(o, "optimizer is NULL");
+    if (ptr) *ptr = o->buf;
+    if (nfloats) *nfloats = o->n;
+    API_END
+}
+
+// ------------------------------------------------------------- RBM trainer
+int32_t scdbm_trainer_create(scdbm_model* m, int32_t l, int32_t B, int32_t pcd, scdbm_trainer** out) {
+    API_BEGIN
+    REQUIRE(m && out, "NULL argument");
+    REQUIRE(l >= 0 && l < (int)m->L.size(), "layer index out of range");
+    REQUIRE(B >= 1, "batchsize must be positive");
+    scdbm_ctx* c = m->ctx;
+    Layer& L = m->L[l];
+    auto* t = new scdbm_trainer{m, l, B, pcd, 1};
+    const int vkind = L.kind == SCDBM_VIS_NEGBIN ? MAT_COUNT : MAT_REAL;  // upper layers train on potentials
+    t->v = mat_new(c, B, L.V, vkind);
+    t->h = mat_new(c, B, L.H, MAT_REAL);
+    t->hm = mat_new(c, B, L.H, MAT_REAL);
+    t->hs = mat_new(c, B, L.H, MAT_BINARY);
+    t->vm = mat_new(c, B, L.V, MAT_REAL);
+    t->vs = mat_new(c, B, L.V, L.kind == SCDBM_VIS_NEGBIN ? MAT_COUNT : MAT_BINARY);
+    CK(scdbm_opt_create(m, &t->opt) == SCDBM_OK ? cudaSuccess : cudaErrorUnknown);
+    if (pcd) {
+        // chainstate = rand(batchsize, nhidden): uniforms used as probabilities (quirk B9)
+        t->chain = mat_new(c, B, L.H, MAT_REAL);
+        k_init<<<grid1d((int64_t)B * ((L.H + 3) / 4)), 256, 0, c->stream>>>(t->chain->v, 2, nullptr, nullptr, (uint32_t)c->seed,
+                                                                             (uint32_t)(c->seed >> 32), 1u, 0u);
+        CK(cudaGetLastError());
+        c->launches++;
+    }
+    *out = t;
+    API_END
+}
+
+int32_t scdbm_trainer_destroy(scdbm_trainer* t) {
+    API_BEGIN
+    if (!t) return SCDBM_OK;
+    cudaStreamSynchronize(t->model->ctx->stream);
+    mat_free(t->chain); mat_free(t->v); mat_free(t->h); mat_free(t->hm); mat_free(t->hs); mat_free(t->vm); mat_free(t->vs);
+    scdbm_opt_destroy(t->opt);
+    cudaFree(t->d_perm);
+    delete t;
+    API_END
+}
+
+int32_t scdbm_trainer_clock(scdbm_trainer* t, int64_t* clock, int64_t set_to) {
+    API_BEGIN
+    REQUIRE(t, "trainer is NULL");
+    if (set_to >= 0) t->clock = set_to;
+    if (clock) *clock = t->clock;
+    API_END
+}
+
+int32_t scdbm_trainer_chainstate(scdbm_trainer* t, scdbm_mat** borrowed) {
+    API_BEGIN
+    REQUIRE(t && borrowed, "NULL argument");
+    REQUIRE(t->chain, "trainer was created without PCD");
+    *borrowed = t->chain;
+    API_END
+}
+
+int32_t scdbm_rbm_train_epoch(scdbm_trainer* t, const scdbm_mat* x, const int32_t* perm, double lr, int32_t cdsteps,
+                              double upfactor, double downfactor) {
+    API_BEGIN
+    REQUIRE(t && x && perm, "NULL argument");
+    REQUIRE(cdsteps >= 1, "cdsteps must be >= 1");
+    scdbm_model* m = t->model;
+    scdbm_ctx* c = m->ctx;
+    Layer& L = m->L[t->l];
+    const int64_t n = x->v.rows;
+    const int B = t->B;
+    REQUIRE(x->v.cols == L.V, "data width does not match the visible layer");
+    REQUIRE(x->v.kind == t->v->v.kind, "data kind does not match the trainer (COUNT for NB, REAL otherwise)");
+    if (B > n) throw Err(SCDBM_EINVAL, "Batchsize (" + std::to_string(B) + ") exceeds number of samples (" + std::to_string(n) + ").");
+    for (int64_t i = 0; i < n; ++i) REQUIRE(perm[i] >= 0 && perm[i] < n, "perm entry out of range");
+    if (t->perm_cap < n) {
+        cudaFree(t->d_perm);
+        CK(cudaMalloc(&t->d_perm, n * sizeof(int32_t)));
+        t->perm_cap = n;
+    }
+    CK(cudaMemcpyAsync(t->d_perm, perm, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    const float up = (float)upfactor, down = (float)downfactor;
+    for (int64_t s = 0; s < n; s += B) {
+        const int64_t thisb = std::min<int64_t>(B, n - s);
+        const int64_t mrows = t->pcd ? B : thisb;  // PCD keeps the full chain (rbmtraining.jl:548-553)
+        MatView v = rows_view(t->v->v, thisb), h = rows_view(t->h->v, thisb);
+        k_gather_rows<<<(unsigned)thisb, 128, 0, c->stream>>>(x->v, t->d_perm + s, v);
+        c->launches++;
+        DrawCfg d;
+        op_hidden(m, t->l, v, h, up, SCDBM_OUT_POTENTIAL, d);                         // :556
+        MatView prob = t->pcd ? t->chain->v : h;                                       // :561-565
+        MatView hs = rows_view(t->hs->v, mrows);
+        DrawAddr da{(uint32_t)c->seed, (uint32_t)(c->seed >> 32), (uint32_t)t->clock, stream_id(1), 0u, nullptr, 0};
+        k_bernoulli<<<grid1d(mrows * ((L.H + 3) / 4)), 256, 0, c->stream>>>(rows_view(prob, mrows), hs, da);  // :567
+        c->launches++;
+        t->clock++;
+        MatView vs = rows_view(t->vs->v, mrows);
+        for (int k = 0; k < cdsteps - 1; ++k) {                                        // :570, samplers.jl:47-56
+            d.tick = (uint32_t)t->clock; d.stream = stream_id(0);
+            op_visible(m, t->l, hs, vs, down, SCDBM_OUT_SAMPLE, d);
+            t->clock++;
+            d.tick = (uint32_t)t->clock; d.stream = stream_id(1);
+            op_hidden(m, t->l, vs, hs, up, SCDBM_OUT_SAMPLE, d);
+            t->clock++;
+        }
+        MatView vm = rows_view(t->vm->v, mrows);
+        op_visible(m, t->l, hs, vm, down, SCDBM_OUT_POTENTIAL, d);                     // :573
+        MatView hm = t->pcd ? t->chain->v : rows_view(t->hm->v, mrows);
+        op_hidden(m, t->l, vm, hm, up, SCDBM_OUT_POTENTIAL, d);                        // :578
+        gradient_layer(t->opt, t->l, v, rows_view(vm, thisb), h, rows_view(hm, thisb), 1.0f / (float)thisb, 1.0f / (float)thisb);
+        update_layer(m, t->opt, t->l, (float)lr);                                      // :586-587
+    }
+    CK(cudaGetLastError());
+    API_END
+}
+
+int32_t scdbm_dbm_pcd_step(scdbm_model* m, const scdbm_mat* x, scdbm_particles* p, scdbm_particles* mu, scdbm_opt* o,
+                           double lr, int32_t nsteps, double eps, int32_t* mf_iters) {
+    API_BEGIN
+    REQUIRE(m && x && p && mu && o, "NULL argument");
+    REQUIRE(p->model == m && mu->model == m && o->model == m, "objects belong to different models");
+    REQUIRE(m->L.size() >= 2, "traindbm! needs at least two RBM layers");
+    gibbs_dbm_steps(m, p, nsteps, 1.0f);                       // dbmtraining.jl:290
+    int it = 0;
+    meanfield_impl(m, x, eps, 0, mu, &it, nullptr);            // :291
+    if (mf_iters) *mf_iters = it;
+    const float ps = 1.0f / (float)std::max<int64_t>(mu->n, 1), ns = 1.0f / (float)std::max<int64_t>(p->n, 1);
+    for (int l = 0; l < (int)m->L.size(); ++l) {               // :293
+        const MatView& v = l == 0 ? mu->alias0->v : mu->cur[l]->v;
+        gradient_layer(o, l, v, p->cur[l]->v, mu->cur[l + 1]->v, p->cur[l + 1]->v, ps, ns);
+    }
+    for (int l = 0; l < (int)m->L.size(); ++l) update_layer(m, o, l, (float)lr);  // :294
+    API_END
+}
+
+// --------------------------------------------------------------------- AIS
+static void ais_ratio(scdbm_model* m, const SweepSrc* s, int ns, int64_t n, int64_t N, const float* bias0, const float* bias1,
+                      float t1, float t2, double* logw) {
+    EpiParams e = epi_base(m->ctx);
+    e.mode = EPI_AIS_RATIO;
+    e.bias0 = bias0;
+    e.bias1 = bias1;
+    e.t1 = t1;
+    e.t2 = t2;
+    e.logw = logw;
+    run_sweep(m->ctx, s, ns, n, N, e);
+}
+
+int32_t scdbm_ais_run(scdbm_model* m, const double* temps, int32_t ntemps, int64_t n, int32_t burnin, uint64_t row_offset,
+                      double* out) {
+    API_BEGIN
+    REQUIRE(m && temps && out, "NULL argument");
+    REQUIRE(ntemps >= 2, "need at least two temperatures");
+    REQUIRE(n > 0 && burnin >= 0, "nparticles must be positive, burnin non-negative");
+    scdbm_ctx* c = m->ctx;
+    double* d_logw = nullptr;
+    CK(cudaMalloc(&d_logw, n * sizeof(double)));
+    CK(cudaMemsetAsync(d_logw, 0, n * sizeof(double), c->stream));
+    scdbm_particles* p = nullptr;
+    if (scdbm_particles_create(m, n, row_offset, 0, &p) != SCDBM_OK) throw Err(SCDBM_ENOMEM, g_err);
+    const int nl = m->nlayers();
+    try {
+        if (m->L.size() == 1) {
+            // aislogimpweights(rbm) (evaluating.jl:18-46): h ~ Bernoulli(sigm(hidbias))
+            Layer& L = m->L[0];
+            k_init<<<grid1d(n * ((L.H + 3) / 4)), 256, 0, c->stream>>>(p->cur[1]->v, 1, L.b, nullptr, (uint32_t)c->seed,
+                                                                        (uint32_t)(c->seed >> 32), 1u, (uint32_t)row_offset);
+            c->launches++;
+            p->clock = 1;
+            for (int k = 1; k < ntemps; ++k) {
+                SweepSrc s{&p->cur[1]->v, &L, false};
+                ais_ratio(m, &s, 1, n, L.V, L.a, nullptr, (float)temps[k], (float)temps[k - 1], d_logw);
+                if (scdbm_gibbs(m, p, burnin, temps[k], 1.0, 1.0) != SCDBM_OK) throw Err(SCDBM_ECUDA, g_err);
+            }
+        } else {
+            if (scdbm_particles_init(p, 1) != SCDBM_OK) throw Err(SCDBM_ECUDA, g_err);
+            for (int k = 1; k < ntemps; ++k) {
+                const float t1 = (float)temps[k], t2 = (float)temps[k - 1];
+                {   // visible layer summed out from h1 (evaluating.jl:195, :1356-1364)
+                    SweepSrc s{&p->cur[1]->v, &m->L[0], false};
+                    ais_ratio(m, &s, 1, n, m->L[0].V, m->L[0].a, nullptr, t1, t2, d_logw);
+                }
+                // even layers of the hidden DBM: absolute layers 2, 4, ... (evaluating.jl:265-290)
+                for (int j = 2; j < nl; j += 2) {
+                    SweepSrc s[2];
+                    int ns = 0;
+                    s[ns++] = SweepSrc{&p->cur[j - 1]->v, &m->L[j - 1], true};
+                    const float* bias1 = nullptr;
+                    if (j + 1 < nl) { s[ns++] = SweepSrc{&p->cur[j + 1]->v, &m->L[j], false}; bias1 = m->L[j].a; }
+                    ais_ratio(m, s, ns, n, m->units(j), m->L[j - 1].b, bias1, t1, t2, d_logw);
+                }
+                gibbs_dbm_steps(m, p, burnin, t1);  // copyannealed! folded into the epilogue scale
+            }
+        }
+        CK(cudaMemcpyAsync(out, d_logw, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    } catch (...) {
+        scdbm_particles_destroy(p);
+        cudaFree(d_logw);
+        throw;
+    }
+    scdbm_particles_destroy(p);
+    cudaFree(d_logw);
+    API_END
+}
+
+}  // extern "C"

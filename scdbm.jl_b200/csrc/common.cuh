@@ -1,0 +1,85 @@
+// Shared definitions for libscdbm_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+namespace scdbm {
+
+// ---- device state matrix: [rows x cols], row = chain/cell, unit-contiguous.
+// Stored as one or two bf16 "planes" whose SUM is the value, so that every
+// state is directly a tcgen05 kind::f16 operand without conversion:
+//   BINARY : p0 in {0,1}                                   (exact)
+//   COUNT  : p0 = v mod 256, p1 = v - p0  (multiple of 256) (exact to 65535)
+//   REAL   : p0 = bf16(v),   p1 = bf16(v - p0)             (16 significant bits)
+enum MatKind : int32_t { MAT_BINARY = 0, MAT_COUNT = 1, MAT_REAL = 2 };
+
+struct MatView {
+    __nv_bfloat16* p0;
+    __nv_bfloat16* p1;     // nullptr for BINARY
+    int64_t rows, cols, ld; // ld (elements) is a multiple of 64
+    int32_t kind;
+};
+
+__host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// epilogue modes of the fused sweep GEMM
+enum EpiMode : int32_t {
+    EPI_INPUT = 0,      // x                         (hiddeninput!/visibleinput!)
+    EPI_SIGM = 1,       // sigm(x)                   (hiddenpotential!, Bernoulli visiblepotential!, mean-field)
+    EPI_SIGM_BERN = 2,  // u < sigm(x)               (samplehidden!, sigm_bernoulli!)
+    EPI_NBMEAN = 3,     // r e^x/(1-e^x) + 1e-6      (NB visiblepotential!)
+    EPI_NB_DRAW = 4,    // NB(r, r/(mu+r)) draw      (NB samplevisiblepotential!)
+    EPI_AIS_RATIO = 5,  // row-sum of log((1+e^{t1 I+a})/(1+e^{t2 I+a}))
+    EPI_RAW_F32 = 6     // acc -> fp32 matrix (gradient GEMM)
+};
+
+struct EpiParams {
+    int32_t mode;
+    const float* bias0;     // per-column bias (nullable)
+    const float* bias1;     // second per-column bias (DBM intermediate layers; nullable)
+    const float* addend;    // optional fp32 [rows x ld_add] added to the pre-activation
+    int64_t ld_add;         //   (mean-field: the hoisted x*W1)
+    float factor;           // multiplies (wscale*acc + biases): up/down factor
+    float wscale;           // multiplies acc only: AIS temperature (weights-only annealing)
+    const float* r;         // NB inverse dispersion per column
+    float pshift;           // 1e-6 for the gamma-Poisson form of the reference, else 0
+    float mu_inv_max;       // inversion / gamma-Poisson switch
+    uint32_t k0, k1;        // Philox key (seed)
+    uint32_t tick, stream;  // Philox counter words 2,3
+    uint32_t row_offset;    // global index of row 0 (chain sharding)
+    const float* uniforms;  // optional explicit uniforms [rows x ldu], row-major fp32
+    int64_t ldu;
+    MatView out;            // output state (not used by EPI_AIS_RATIO)
+    MatView prev;           // mean-field: previous value of the same layer (p0 == nullptr: off)
+    unsigned int* delta_bits; // mean-field: max |prev-new| as float bits (atomicMax)
+    float t1, t2;           // AIS temperatures
+    double* logw;           // AIS: per-row accumulator
+    float* out_f32;         // EPI_RAW_F32 destination [M x ldo]
+    int64_t ldo;
+};
+
+// One GEMM operand, element (mn, k) at base[mn * s_mn + k * s_k]; value is
+// p0 + p1 (bf16 planes) or f (fp32).  `scale` multiplies the A operand of a
+// source (gradient: +1/n_pos, -1/n_neg).
+struct Operand {
+    const __nv_bfloat16* p0;
+    const __nv_bfloat16* p1;
+    const float* f;
+    int64_t s_mn, s_k;
+};
+struct GemmSource {
+    Operand a, b;
+    int64_t K;
+    float scale;
+};
+struct GemmArgs {
+    GemmSource src[2];
+    int32_t nsrc;
+    int64_t M, N;
+    EpiParams epi;
+};
+
+}  // namespace scdbm

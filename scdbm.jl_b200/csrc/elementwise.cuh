@@ -1,0 +1,218 @@
+// Elementwise / reduction kernels around the sweep GEMMs: layout+dtype
+// conversion at the boundary, fused parameter update (+clamps, +operand
+// refresh), column sums, particle init, row gather, column statistics.
+// All are HBM-bound: coalesced, vectorised where alignment allows.
+#pragma once
+#include "epilogue.cuh"
+
+namespace scdbm {
+
+// ---- host (column-major fp64, leading dimension ld) <-> device planes
+// 32x32 smem transpose so both sides are coalesced.
+__global__ void k_upload_f64(const double* __restrict__ src, int64_t lds, MatView dst) {
+    __shared__ float t[32][33];
+    const int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int64_t r = r0 + threadIdx.x, c = c0 + j;
+        t[j][threadIdx.x] = (r < dst.rows && c < dst.cols) ? (float)src[c * lds + r] : 0.0f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int64_t r = r0 + j, c = c0 + threadIdx.x;
+        if (r < dst.rows && c < dst.cols) {
+            __nv_bfloat16 a, b;
+            split_value(dst.kind, t[threadIdx.x][j], a, b);
+            dst.p0[r * dst.ld + c] = a;
+            if (dst.p1) dst.p1[r * dst.ld + c] = b;
+        }
+    }
+}
+
+__global__ void k_download_f64(MatView src, double* __restrict__ dst, int64_t ldd) {
+    __shared__ float t[32][33];
+    const int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int64_t r = r0 + j, c = c0 + threadIdx.x;
+        t[j][threadIdx.x] = (r < src.rows && c < src.cols) ? mat_load(src, r, c) : 0.0f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int64_t r = r0 + threadIdx.x, c = c0 + j;
+        if (r < src.rows && c < src.cols) dst[c * ldd + r] = (double)t[threadIdx.x][j];
+    }
+}
+
+// row-major compact download of counts / binary states
+__global__ void k_download_u16(MatView src, uint16_t* __restrict__ dst) {
+    const int64_t n = src.rows * src.cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / src.cols, c = i % src.cols;
+        dst[i] = (uint16_t)fminf(fmaxf(mat_load(src, r, c), 0.0f), 65535.0f);
+    }
+}
+
+__global__ void k_upload_uniforms(const double* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t rows,
+                                  int64_t cols, int64_t ldd) {
+    const int64_t n = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i % rows, c = i / rows;
+        dst[r * ldd + c] = (float)src[c * lds + r];
+    }
+}
+
+// ---- weights: fp32 master W[V x H] row-major -> bf16 hi/lo operand planes in
+// both orientations (W[V x ldH] for the down-sweep, Wt[H x ldV] for the up-sweep)
+__global__ void k_refresh_operands(const float* __restrict__ W, int V, int H, __nv_bfloat16* w0, __nv_bfloat16* w1,
+                                   int64_t ldh, __nv_bfloat16* t0, __nv_bfloat16* t1, int64_t ldv) {
+    __shared__ float t[32][33];
+    const int v0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int v = v0 + j, h = h0 + threadIdx.x;
+        float x = 0.0f;
+        if (v < V && h < H) {
+            x = W[(int64_t)v * H + h];
+            const __nv_bfloat16 a = __float2bfloat16_rn(x);
+            w0[(int64_t)v * ldh + h] = a;
+            w1[(int64_t)v * ldh + h] = __float2bfloat16_rn(x - __bfloat162float(a));
+        }
+        t[j][threadIdx.x] = x;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int h = h0 + j, v = v0 + threadIdx.x;
+        if (v < V && h < H) {
+            const float x = t[threadIdx.x][j];
+            const __nv_bfloat16 a = __float2bfloat16_rn(x);
+            t0[(int64_t)h * ldv + v] = a;
+            t1[(int64_t)h * ldv + v] = __float2bfloat16_rn(x - __bfloat162float(a));
+        }
+    }
+}
+
+// ---- fused update: theta += lr * grad, NB clamps (src/optimizers.jl:478-485,513-520)
+__global__ void k_update(float* __restrict__ theta, const float* __restrict__ grad, int64_t n, float lr, float hi_clamp,
+                         int clamp) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float t = fmaf(lr, grad[i], theta[i]);
+        if (clamp) t = fminf(t, hi_clamp);
+        theta[i] = t;
+    }
+}
+
+// ---- column sums of a state matrix: out[c] (+)= scale * sum_r m(r, c)
+__global__ void k_colsum(MatView m, float scale, float* __restrict__ out, int accumulate) {
+    // block = 32 columns x 8 row-lanes; grid.x over column blocks, grid.y over row slabs
+    __shared__ float red[8][33];
+    const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    float s = 0.0f;
+    if (c < m.cols)
+        for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < m.rows; r += (int64_t)gridDim.y * 8) s += mat_load(m, r, c);
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < m.cols) {
+        float tot = 0.0f;
+        for (int j = 0; j < 8; ++j) tot += red[j][threadIdx.x];
+        atomicAdd(&out[c], scale * tot);
+    }
+}
+
+__global__ void k_fill_f32(float* p, int64_t n, float v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ---- row gather: dst[i, :] = src[idx[i], :]   (minibatch, src/rbmtraining.jl:544)
+__global__ void k_gather_rows(MatView src, const int32_t* __restrict__ idx, MatView dst) {
+    const int64_t r = blockIdx.x;
+    const int64_t s = idx[r];
+    for (int64_t c = threadIdx.x; c < dst.ld; c += blockDim.x) {
+        dst.p0[r * dst.ld + c] = src.p0[s * src.ld + c];
+        if (dst.p1) dst.p1[r * dst.ld + c] = src.p1 ? src.p1[s * src.ld + c] : __float2bfloat16_rn(0.0f);
+    }
+}
+
+__global__ void k_copy_rows(MatView src, MatView dst, int64_t rows) {
+    const int64_t r = blockIdx.x;
+    if (r >= rows) return;
+    for (int64_t c = threadIdx.x; c < dst.ld; c += blockDim.x) {
+        dst.p0[r * dst.ld + c] = src.p0[r * src.ld + c];
+        if (dst.p1) dst.p1[r * dst.ld + c] = src.p1 ? src.p1[r * src.ld + c] : __float2bfloat16_rn(0.0f);
+    }
+}
+
+// ---- in-place Bernoulli sampling of a matrix of probabilities (bernoulli!,
+// src/gibbssampling.jl:40-45) -> dst (BINARY or REAL kind)
+struct DrawAddr {
+    uint32_t k0, k1, tick, stream, row_offset;
+    const float* uniforms;
+    int64_t ldu;
+};
+__global__ void k_bernoulli(MatView prob, MatView dst, DrawAddr d) {
+    const int64_t groups = (prob.cols + 3) / 4;
+    const int64_t n = prob.rows * groups;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / groups, gidx = i % groups, c0 = gidx * 4;
+        const int nvalid = (int)min((int64_t)4, prob.cols - c0);
+        float u[4];
+        if (d.uniforms) {
+            for (int j = 0; j < 4; ++j) u[j] = j < nvalid ? d.uniforms[r * d.ldu + c0 + j] : 1.0f;
+        } else {
+            const uint4 w = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)r + d.row_offset, d.tick, d.stream), d.k0, d.k1);
+            u[0] = u23(w.x); u[1] = u23(w.y); u[2] = u23(w.z); u[3] = u23(w.w);
+        }
+        float o[4] = {0, 0, 0, 0};
+        for (int j = 0; j < nvalid; ++j) o[j] = (u[j] < mat_load(prob, r, c0 + j)) ? 1.0f : 0.0f;
+        mat_store4(dst, r, c0, o, nvalid);
+    }
+}
+
+// ---- particle / chain-state initialisation
+// mode 0: fair coin (u < 0.5); 1: Bernoulli(sigm(bias[c])); 2: raw uniform (PCD chain state,
+// src/rbmtraining.jl:141); 3: NB visible init (src/gibbssampling.jl:512-531)
+__global__ void k_init(MatView dst, int mode, const float* __restrict__ bias, const float* __restrict__ r, uint32_t k0,
+                       uint32_t k1, uint32_t layer, uint32_t row_offset) {
+    const int64_t groups = (dst.cols + 3) / 4;
+    const int64_t n = dst.rows * groups;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / groups, gidx = i % groups, c0 = gidx * 4;
+        const int nvalid = (int)min((int64_t)4, dst.cols - c0);
+        const uint4 w = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)row + row_offset, 0u, stream_id(layer, P_INIT)), k0, k1);
+        const float u[4] = {u23(w.x), u23(w.y), u23(w.z), u23(w.w)};
+        float o[4] = {0, 0, 0, 0};
+        if (mode == 3) {
+            const uint4 w2 = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)row + row_offset, 0u, stream_id(layer, P_INIT2)), k0, k1);
+            const float u2[4] = {u23(w2.x), u23(w2.y), u23(w2.z), u23(w2.w)};
+            for (int j = 0; j < nvalid; ++j) {
+                const float v0 = nb_inversion(1.0f, 1.0f, u[j], 0.0f);
+                o[j] = nb_inversion(v0, r[c0 + j], u2[j], 1e-6f);
+            }
+        } else {
+            for (int j = 0; j < nvalid; ++j) {
+                if (mode == 0) o[j] = u[j] < 0.5f ? 1.0f : 0.0f;
+                else if (mode == 1) o[j] = u[j] < sigmf(bias[c0 + j]) ? 1.0f : 0.0f;
+                else o[j] = u[j];
+            }
+        }
+        mat_store4(dst, row, c0, o, nvalid);
+    }
+}
+
+// ---- per-column mean / variance / zero fraction (the paper's sample-quality
+// statistics, src/NegativeBinomialRBMPlots.jl:148-182,428-462)
+__global__ void k_colstats(MatView m, double* __restrict__ sum, double* __restrict__ sumsq, double* __restrict__ zeros) {
+    __shared__ double rs[8][33], rq[8][33], rz[8][33];
+    const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    double s = 0, q = 0, z = 0;
+    if (c < m.cols)
+        for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < m.rows; r += (int64_t)gridDim.y * 8) {
+            const double v = mat_load(m, r, c);
+            s += v; q += v * v; z += (v == 0.0);
+        }
+    rs[threadIdx.y][threadIdx.x] = s; rq[threadIdx.y][threadIdx.x] = q; rz[threadIdx.y][threadIdx.x] = z;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < m.cols) {
+        for (int j = 1; j < 8; ++j) { s += rs[j][threadIdx.x]; q += rq[j][threadIdx.x]; z += rz[j][threadIdx.x]; }
+        atomicAdd(&sum[c], s); atomicAdd(&sumsq[c], q); atomicAdd(&zeros[c], z);
+    }
+}
+
+}  // namespace scdbm

@@ -1,0 +1,122 @@
+// The fused epilogue shared by the SIMT and tcgen05 sweep GEMMs.
+// Processes 4 consecutive columns (col0 % 4 == 0) of one row: adds biases,
+// applies the factor, activation and (optionally) the Philox draw, and writes
+// the result as bf16 operand planes for the next contraction.
+#pragma once
+#include "samplers.cuh"
+
+namespace scdbm {
+
+__device__ __forceinline__ float mat_load(const MatView& m, int64_t row, int64_t col) {
+    const int64_t i = row * m.ld + col;
+    float v = __bfloat162float(m.p0[i]);
+    if (m.p1) v += __bfloat162float(m.p1[i]);
+    return v;
+}
+
+__device__ __forceinline__ void split_value(int kind, float v, __nv_bfloat16& a, __nv_bfloat16& b) {
+    if (kind == MAT_COUNT) {
+        const float hi = floorf(v * (1.0f / 256.0f)) * 256.0f;
+        a = __float2bfloat16_rn(v - hi);
+        b = __float2bfloat16_rn(hi);
+    } else {
+        a = __float2bfloat16_rn(v);
+        b = __float2bfloat16_rn(v - __bfloat162float(a));
+    }
+}
+
+// write up to 4 consecutive values; 8-byte vector store when all 4 are in range
+__device__ __forceinline__ void mat_store4(const MatView& m, int64_t row, int64_t col0, const float (&v)[4], int nvalid) {
+    __nv_bfloat16 a[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_value(m.kind, v[j], a[j], b[j]);
+    const int64_t i = row * m.ld + col0;
+    if (nvalid == 4) {
+        uint2 pa, pb;
+        pa.x = (uint32_t)__bfloat16_as_ushort(a[0]) | ((uint32_t)__bfloat16_as_ushort(a[1]) << 16);
+        pa.y = (uint32_t)__bfloat16_as_ushort(a[2]) | ((uint32_t)__bfloat16_as_ushort(a[3]) << 16);
+        *reinterpret_cast<uint2*>(m.p0 + i) = pa;
+        if (m.p1) {
+            pb.x = (uint32_t)__bfloat16_as_ushort(b[0]) | ((uint32_t)__bfloat16_as_ushort(b[1]) << 16);
+            pb.y = (uint32_t)__bfloat16_as_ushort(b[2]) | ((uint32_t)__bfloat16_as_ushort(b[3]) << 16);
+            *reinterpret_cast<uint2*>(m.p1 + i) = pb;
+        }
+    } else {
+        for (int j = 0; j < nvalid; ++j) {
+            m.p0[i + j] = a[j];
+            if (m.p1) m.p1[i + j] = b[j];
+        }
+    }
+}
+
+// log((1+e^{y1})/(1+e^{y2})) without cancellation: log1p(sigm(y2) * expm1(y1-y2))
+__device__ __forceinline__ float softplus_diff(float y2, float dy) { return log1pf(sigmf(y2) * expm1f(dy)); }
+
+// Returns the AIS partial row sum (0 for other modes).  `row` is local to the
+// matrix; nvalid = number of in-range columns among col0..col0+3.
+__device__ __forceinline__ float epi_apply4(const EpiParams& e, int64_t row, int64_t col0, const float (&acc)[4],
+                                            int nvalid, float& delta_local) {
+    float x[4], out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float b = 0.0f;
+        if (j < nvalid) {
+            if (e.bias0) b += e.bias0[col0 + j];
+            if (e.bias1) b += e.bias1[col0 + j];
+        }
+        if (e.addend && j < nvalid) b += e.addend[row * e.ld_add + col0 + j];
+        x[j] = e.factor * (e.wscale * acc[j] + b);
+    }
+    if (e.mode == EPI_AIS_RATIO) {
+        float s = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < nvalid) {
+                float b = 0.0f;
+                if (e.bias0) b += e.bias0[col0 + j];
+                if (e.bias1) b += e.bias1[col0 + j];
+                s += softplus_diff(e.t2 * acc[j] + b, (e.t1 - e.t2) * acc[j]);
+            }
+        }
+        return s;
+    }
+    if (e.mode == EPI_RAW_F32) {
+        for (int j = 0; j < nvalid; ++j) e.out_f32[row * e.ldo + col0 + j] = acc[j];
+        return 0.0f;
+    }
+    uint4 w = make_uint4(0, 0, 0, 0);
+    float u[4] = {0.5f, 0.5f, 0.5f, 0.5f};
+    if (e.mode == EPI_SIGM_BERN || e.mode == EPI_NB_DRAW) {
+        if (e.uniforms) {
+            for (int j = 0; j < nvalid; ++j) u[j] = e.uniforms[row * e.ldu + col0 + j];
+        } else {
+            w = philox_group(e, (uint32_t)row, (uint32_t)(col0 >> 2));
+            u[0] = u23(w.x); u[1] = u23(w.y); u[2] = u23(w.z); u[3] = u23(w.w);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float o = 0.0f;
+        if (j < nvalid) {
+            switch (e.mode) {
+                case EPI_INPUT: o = x[j]; break;
+                case EPI_SIGM: o = sigmf(x[j]); break;
+                case EPI_SIGM_BERN: o = (u[j] < sigmf(x[j])) ? 1.0f : 0.0f; break;
+                case EPI_NBMEAN: o = nb_mean(x[j], e.r[col0 + j]); break;
+                case EPI_NB_DRAW: {
+                    const float r = e.r[col0 + j];
+                    const RngAddr g{e.k0, e.k1, (uint32_t)row + e.row_offset, (uint32_t)(col0 + j), e.tick,
+                                    e.stream & 0xFFu};
+                    o = nb_draw(nb_mean(x[j], r), r, u[j], e.pshift, e.mu_inv_max, g);
+                } break;
+                default: break;
+            }
+            if (e.prev.p0) delta_local = fmaxf(delta_local, fabsf(mat_load(e.prev, row, col0 + j) - o));
+        }
+        out[j] = o;
+    }
+    mat_store4(e.out, row, col0, out, nvalid);
+    return 0.0f;
+}
+
+}  // namespace scdbm

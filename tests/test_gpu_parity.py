@@ -1,0 +1,426 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle.
+
+Gates (BASELINE.json north_star):
+  G1 deterministic quantities agree within 1e-4 relative;
+  G2 sampled states are identical when both sides consume the same uniforms,
+     except inside the fp32-vs-fp64 ambiguity band around a decision boundary;
+  G3 free-running statistics agree with exact values within k standard errors.
+"""
+import numpy as np
+import pytest
+
+from conftest import to_pkg_model, relerr
+from oracle import model as om, philox as px, sampling as osp, ais as oais, exact, synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4   # gate G1 (north_star: "within 1e-4 relative")
+SEED = 20261019
+
+
+def small_dbm(units=(40, 24, 12), seed=3, wscale=(0.02, 0.2)):
+    return synth.random_dbm(list(units), seed, wscale=wscale)
+
+
+def dm_of(pkg, ctx, bm):
+    return pkg.DeviceModel.from_host(to_pkg_model(pkg, bm), ctx)
+
+
+# ------------------------------------------------------------ boundary
+def test_upload_download_roundtrip(pkg, ctx):
+    g = np.random.default_rng(0)
+    for rows, cols in [(1, 1), (7, 5), (33, 70), (130, 257)]:
+        x = g.poisson(3.0, (rows, cols)).astype(float)
+        x[0, 0] = 65535
+        assert np.array_equal(pkg.Mat.from_host(ctx, x, pkg.MAT_COUNT).to_host(), x)
+        assert np.array_equal(pkg.Mat.from_host(ctx, x, pkg.MAT_COUNT).to_host_u16(), x.astype(np.uint16))
+        b = (g.random((rows, cols)) < 0.5).astype(float)
+        assert np.array_equal(pkg.Mat.from_host(ctx, b, pkg.MAT_BINARY).to_host(), b)
+        r = g.normal(0, 3, (rows, cols))
+        assert relerr(pkg.Mat.from_host(ctx, r, pkg.MAT_REAL).to_host(), r) < 2e-5
+
+
+def test_error_codes(pkg, ctx):
+    with pytest.raises(pkg.ScdbmError) as e:
+        pkg.Mat.from_host(ctx, np.array([[np.nan]]), pkg.MAT_REAL)
+    assert e.value.code == -1
+    with pytest.raises(pkg.ScdbmError):
+        pkg.Mat.from_host(ctx, np.array([[-1.0]]), pkg.MAT_COUNT)
+    with pytest.raises(pkg.ScdbmError):
+        pkg.Mat.from_host(ctx, np.array([[0.5]]), pkg.MAT_BINARY)
+    dbm = small_dbm()
+    bad = to_pkg_model(pkg, dbm)
+    bad[0].visbias = np.abs(bad[0].visbias)          # NB validity needs a < 0
+    with pytest.raises(pkg.ScdbmError):
+        pkg.DeviceModel.from_host(bad, ctx)
+    m = dm_of(pkg, ctx, dbm)
+    with pytest.raises(pkg.ScdbmError):              # wrong width
+        pkg.hiddenpotential(m, np.zeros((3, 41)), ctx=ctx)
+    with pytest.raises(ValueError):                   # the reference's error text
+        pkg.fitrbm(np.ones((3, 4)), nhidden=2, batchsize=5, ctx=ctx)
+
+
+def test_empty_inputs(pkg, ctx):
+    m = dm_of(pkg, ctx, small_dbm())
+    assert pkg.hiddenpotential(m, np.zeros((0, 40)), ctx=ctx).shape == (0, 24)
+    p = pkg.initparticles(m, 0, device=True)
+    pkg.gibbssample_(p, m, 2)
+    assert [x.shape for x in p.to_host()] == [(0, 40), (0, 24), (0, 12)]
+
+
+# ------------------------------------------------- G1: deterministic ops
+@pytest.mark.parametrize("n,units", [(5, (7, 5, 3)), (64, (40, 24, 12)), (129, (130, 67, 33)), (257, (256, 128, 64))])
+def test_conditionals_deterministic(pkg, ctx, n, units):
+    dbm = small_dbm(units)
+    m = dm_of(pkg, ctx, dbm)
+    g = np.random.default_rng(1)
+    v = g.poisson(1.5, (n, units[0])).astype(float)
+    v[0, 0] = 3000.0                                    # a count above 2048 (needs the high plane)
+    h1 = (g.random((n, units[1])) < 0.5).astype(float)
+    h2 = (g.random((n, units[2])) < 0.5).astype(float)
+    assert relerr(pkg.hiddeninput(m, v), om.hiddeninput(dbm[0], v), 1e-6) < RTOL
+    for f in (1.0, 2.0):
+        assert relerr(pkg.hiddenpotential(m, v, f), om.hiddenpotential(dbm[0], v, f)) < RTOL
+    assert relerr(pkg.visibleinput(m, h1), om.visibleinput(dbm[0], h1)) < RTOL
+    # NB mean; the NB method ignores `factor` (quirk B1)
+    assert relerr(pkg.visiblepotential(m, h1, 2.0), om.visiblepotential(dbm[0], h1, 2.0)) < RTOL
+    # upper (Bernoulli) RBM
+    assert relerr(pkg.hiddenpotential(m, h1, 1.0, layer=1), om.hiddenpotential(dbm[1], h1)) < RTOL
+    assert relerr(pkg.visiblepotential(m, h2, 2.0, layer=1), om.visiblepotential(dbm[1], h2, 2.0)) < RTOL
+    # intermediate DBM layer: both neighbours, both biases
+    ref = osp.sigm(om.dbm_layer_input(dbm, [v, h1, h2], 1))
+    assert relerr(pkg.dbmlayer(m, 1, v, h2), ref) < RTOL
+
+
+def test_nb_mean_adversarial(pkg, ctx):
+    """x -> 0- (huge means) and very negative x."""
+    V, H = 16, 8
+    W = -np.abs(np.random.default_rng(2).normal(0, 1e-3, (V, H)))
+    a = -np.logspace(-6, 1.3, V)                        # from -1e-6 to -20
+    rbm = om.NegativeBinomialBernoulliRBM(W, a, np.zeros(H), np.full(V, 0.5))
+    m = dm_of(pkg, ctx, rbm)
+    h = np.zeros((4, H)); h[1:, :] = 1.0
+    assert relerr(pkg.visiblepotential(m, h), om.visiblepotential(rbm, h)) < RTOL
+
+
+# --------------------------------------------- G2: same uniforms, same states
+def band_check(u, p_ref, got, ref, band=4e-6):
+    """every mismatching Bernoulli element must have |u - p| inside the band"""
+    bad = got != ref
+    assert np.all(np.abs(u[bad] - p_ref[bad]) <= band * np.maximum(1.0, 0)), "mismatch outside the ambiguity band"
+    return int(bad.sum())
+
+
+def test_bernoulli_same_uniforms(pkg, ctx):
+    dbm = small_dbm((130, 67, 33))
+    m = dm_of(pkg, ctx, dbm)
+    g = np.random.default_rng(4)
+    n = 200
+    v = g.poisson(1.0, (n, 130)).astype(float)
+    u = (np.floor(g.random((n, 67)) * 2**23) + 0.5) / 2**23
+    got = pkg.samplehidden(m, v, u=u)
+    p = om.hiddenpotential(dbm[0], v)
+    nbad = band_check(u, p, got, osp.bernoulli(p, u))
+    assert nbad <= 2
+    # adversarial: uniforms placed just beside the probability
+    u2 = np.clip(np.round(p * 2**23 - 0.5) + 0.5 + g.integers(-3, 4, p.shape), 0.5, 2**23 - 0.5) / 2**23
+    got2 = pkg.samplehidden(m, v, u=u2)
+    band_check(u2, p, got2, osp.bernoulli(p, u2))
+
+
+def test_nb_same_uniforms(pkg, ctx):
+    dbm = small_dbm((64, 24, 12))
+    m = dm_of(pkg, ctx, dbm)
+    g = np.random.default_rng(5)
+    n = 300
+    h1 = (g.random((n, 24)) < 0.5).astype(float)
+    u = (np.floor(g.random((n, 64)) * 2**23) + 0.5) / 2**23
+    mu = om.visiblepotential(dbm[0], h1)
+    inv = mu <= osp.MU_INV_MAX
+    got = pkg.samplevisible(m, h1, u=u, tick=9)
+    ref = om.samplevisible(dbm[0], h1, px.Rng(SEED), 0, 9, u=u)
+    bad = (got != ref) & inv
+    # an inversion draw can only differ where u falls within fp32 round-off of a CDF step
+    assert bad.sum() <= max(2, int(2e-4 * inv.sum())), f"{bad.sum()} inversion mismatches of {inv.sum()}"
+    assert np.all(np.abs(got[bad] - ref[bad]) <= 1)
+    # tiny K: exact equality expected
+    tiny = small_dbm((8, 4, 2), seed=9)
+    mt = dm_of(pkg, ctx, tiny)
+    ht = (g.random((50, 4)) < 0.5).astype(float)
+    ut = (np.floor(g.random((50, 8)) * 2**23) + 0.5) / 2**23
+    mut = om.visiblepotential(tiny[0], ht)
+    sel = mut <= osp.MU_INV_MAX
+    assert np.array_equal(pkg.samplevisible(mt, ht, u=ut)[sel], om.samplevisible(tiny[0], ht, px.Rng(SEED), 0, 0, u=ut)[sel])
+
+
+def test_philox_fed_draws_match_oracle(pkg, ctx):
+    """No explicit uniforms: both sides derive them from Philox(seed, stream, tick, row, col)."""
+    dbm = small_dbm((130, 67, 33))
+    m = dm_of(pkg, ctx, dbm)
+    g = np.random.default_rng(6)
+    n = 150
+    v = g.poisson(1.0, (n, 130)).astype(float)
+    h1 = (g.random((n, 67)) < 0.5).astype(float)
+    rng = px.Rng(SEED)
+    assert np.mean(pkg.samplehidden(m, v, tick=5) != om.samplehidden(dbm[0], v, rng, 1, 5)) < 5e-4
+    got, ref = pkg.samplevisible(m, h1, tick=6), om.samplevisible(dbm[0], h1, rng, 0, 6)
+    assert np.mean(got != ref) < 2e-3
+    # the high-mean genes went through the gamma-Poisson branch on both sides
+    assert (om.visiblepotential(dbm[0], h1) > osp.MU_INV_MAX).any()
+
+
+def test_gamma_poisson_branch_statistics(pkg, ctx):
+    """Force every draw through Marsaglia-Tsang + PTRS and compare moments with NB theory."""
+    V, H, n = 8, 4, 40000
+    mus = np.array([9.0, 15.0, 40.0, 120.0, 9.0, 15.0, 40.0, 400.0])
+    r = np.array([0.5, 0.5, 0.5, 0.5, 3.0, 3.0, 20.0, 1.0])
+    rbm = om.NegativeBinomialBernoulliRBM(np.zeros((V, H)), np.log(mus / (mus + r)), np.zeros(H), r)
+    m = dm_of(pkg, ctx, rbm)
+    x = pkg.samplevisible(m, np.zeros((n, H)), tick=3)
+    ref = om.samplevisible(rbm, np.zeros((n, H)), px.Rng(SEED), 0, 3)
+    assert np.mean(x != ref) < 5e-3                      # same algorithm, same Philox stream
+    var = mus + mus**2 / r
+    se_mean = np.sqrt(var / n)
+    assert np.all(np.abs(x.mean(0) - mus) < 5 * se_mean)
+    assert np.all(np.abs(x.var(0) / var - 1) < 0.15)
+
+
+# ----------------------------------------------------------- chains
+def test_initparticles_exact(pkg, ctx):
+    dbm = small_dbm((130, 67, 33))
+    m = dm_of(pkg, ctx, dbm)
+    for biased in (False, True):
+        got = pkg.initparticles(m, 77, biased=biased)
+        ref = om.initparticles(dbm, 77, px.Rng(SEED), biased=biased)
+        for a, b in zip(got, ref):
+            assert np.array_equal(a, b)
+
+
+def test_gibbs_dbm_matches_oracle(pkg, ctx):
+    dbm = small_dbm((130, 67, 33))
+    m = dm_of(pkg, ctx, dbm)
+    p = pkg.initparticles(m, 96, device=True)
+    ref = om.initparticles(dbm, 96, px.Rng(SEED))
+    pkg.gibbssample_(p, m, 4)
+    om.gibbssample_dbm(ref, dbm, px.Rng(SEED), 4)
+    assert p.clock == ref.clock
+    for a, b in zip(p.to_host(), ref):
+        assert np.mean(a != b) < 5e-3
+    # 3-RBM DBM (two intermediate layers)
+    dbm3 = synth.random_dbm([64, 32, 16, 8], 5, wscale=(0.02, 0.2))
+    m3 = dm_of(pkg, ctx, dbm3)
+    p3 = pkg.initparticles(m3, 50, device=True)
+    r3 = om.initparticles(dbm3, 50, px.Rng(SEED))
+    pkg.gibbssample_(p3, m3, 3)
+    om.gibbssample_dbm(r3, dbm3, px.Rng(SEED), 3)
+    for a, b in zip(p3.to_host(), r3):
+        assert np.mean(a != b) < 5e-3
+
+
+def test_gibbs_rbm_and_nb_variant(pkg, ctx):
+    rbm = small_dbm((40, 24, 12))[0]
+    m = dm_of(pkg, ctx, rbm)
+    p = pkg.initparticles(m, 64, device=True)
+    ref = om.initparticles(rbm, 64, px.Rng(SEED))
+    pkg.gibbssample_(p, m, 3)
+    om.gibbssample_rbm(ref, rbm, px.Rng(SEED), 3)
+    for a, b in zip(p.to_host(), ref):
+        assert np.mean(a != b) < 5e-3
+    p2 = pkg.initparticles(m, 64, device=True)
+    ref2 = om.initparticles(rbm, 64, px.Rng(SEED))
+    pkg.gibbssamplenegativebinomial_(p2, m, 3)
+    om.gibbssamplenegativebinomial_rbm(ref2, rbm, px.Rng(SEED), 3)
+    for a, b in zip(p2.to_host(), ref2):
+        assert np.mean(a != b) < 5e-3
+
+
+def test_sharding_invariance(pkg, ctx):
+    """Chains are addressed by their global index: 1 shard == 2 shards, bit for bit."""
+    dbm = small_dbm((40, 24, 12))
+    m = dm_of(pkg, ctx, dbm)
+    whole = pkg.sampleparticles(m, 100, burnin=3)
+    a = pkg.sampleparticles(m, 60, burnin=3, row_offset=0)
+    b = pkg.sampleparticles(m, 40, burnin=3, row_offset=60)
+    for w, x, y in zip(whole, a, b):
+        assert np.array_equal(w, np.vstack([x, y]))
+
+
+def test_samples_api(pkg, ctx):
+    dbm = small_dbm((40, 24, 12))
+    m = dm_of(pkg, ctx, dbm)
+    x = pkg.samples(m, 30, burnin=4)
+    ref = om.samples(dbm, 30, px.Rng(SEED), burnin=4)
+    assert x.shape == (30, 40) and np.mean(x != ref) < 5e-3
+    assert np.array_equal(pkg.samples(m, 30, burnin=4, dtype=np.uint16), x.astype(np.uint16))
+    pot = pkg.samples(m, 30, burnin=4, samplelast=False)
+    assert relerr(pot, om.samples(dbm, 30, px.Rng(SEED), burnin=4, samplelast=False)) < 5e-2  # few flipped h1 bits upstream
+
+
+# -------------------------------------------------------- mean-field
+@pytest.mark.parametrize("units", [(40, 24, 12), (64, 32, 16, 8), (30, 10)])
+def test_meanfield(pkg, ctx, units):
+    dbm = synth.random_dbm(list(units), 7, wscale=(0.02, 0.2))
+    m = dm_of(pkg, ctx, dbm if len(dbm) > 1 else dbm[0])
+    x = np.random.default_rng(8).poisson(1.0, (70, units[0])).astype(float)
+    for maxiter in (1, 3):
+        got = pkg.meanfield(m, x, eps=0.0, maxiter=maxiter)
+        ref, _, _ = om.meanfield(dbm, x, eps=0.0, maxiter=maxiter)
+        for a, b in zip(got[1:], ref[1:]):
+            assert relerr(a, b) < RTOL
+    got, it, delta = pkg.meanfield(m, x, eps=1e-6, return_info=True)
+    ref, rit, rdelta = om.meanfield(dbm, x, eps=1e-6)
+    assert abs(it - rit) <= 1 and delta <= 2e-6
+    for a, b in zip(got[1:], ref[1:]):
+        assert relerr(a, b) < RTOL
+    _, it3, _ = pkg.meanfield(m, x, eps=1e-3, return_info=True)
+    assert it3 == om.meanfield(dbm, x, eps=1e-3)[1]
+
+
+# ------------------------------------------------ gradient and update
+def test_gradient_and_update(pkg, ctx):
+    dbm = small_dbm((130, 67, 33))
+    m = dm_of(pkg, ctx, dbm)
+    g = np.random.default_rng(9)
+    v = g.poisson(1.0, (50, 130)).astype(float)
+    vm = g.gamma(0.5, 2.0, (37, 130))
+    h, hm = g.random((50, 67)), g.random((37, 67))
+    opt = pkg.loglikelihoodoptimizer(m, learningrate=0.01)
+    pkg.computegradient_(opt, v, vm, h, hm, m)
+    ref = om.computegradient(v, vm, h, hm)
+    W, a, b = opt.gradient(0)
+    scale = np.abs(ref.weights).max()
+    assert np.max(np.abs(W - ref.weights)) < RTOL * scale
+    assert np.max(np.abs(a - ref.visbias)) < RTOL * np.abs(ref.visbias).max()
+    assert np.max(np.abs(b - ref.hidbias)) < RTOL * np.abs(ref.hidbias).max()
+    # update with the NB clamps (W <= 0, a <= -1e-10)
+    opt.learningrate = 5.0                              # large step so the clamps bite
+    pkg.updateparameters_(m, opt) if False else opt.updateparameters_(m, 0)
+    import copy
+    r0 = copy.deepcopy(dbm[0])
+    om.updateparameters(r0, ref, 5.0)
+    got = m.get_layer(0)
+    assert (got.weights <= 0).all() and (got.visbias <= -1e-10 * 0.999).all()
+    assert np.max(np.abs(got.weights - r0.weights)) < RTOL * np.abs(r0.weights).max() + 1e-7
+    assert np.max(np.abs(got.hidbias - r0.hidbias)) < RTOL * np.abs(r0.hidbias).max() + 1e-7
+    assert (np.asarray(got.weights == 0) == (r0.weights == 0)).mean() > 0.999
+
+
+# ------------------------------------------------------- RBM training
+@pytest.mark.parametrize("pcd,cdsteps,n,B", [(False, 1, 60, 20), (True, 1, 60, 20), (False, 2, 50, 16), (True, 1, 50, 16)])
+def test_trainrbm_epoch(pkg, ctx, pcd, cdsteps, n, B):
+    V, H = 40, 16
+    x, _, _ = synth.counts(n, V, seed=1)
+    x[:, 0] += 1.0                                       # no all-zero gene
+    rng = px.Rng(SEED)
+    rbm = om.initrbm(x, H, rng, "nb")
+    tr = om.RBMTrainer(rbm, B, rng, pcd)
+    xm = pkg.Mat.from_host(ctx, x, pkg.MAT_COUNT)
+    m = pkg.DeviceModel(ctx, [V, H], pkg.VIS_NEGBIN)
+    m.init_layer(0, xm, seed=SEED)
+    g0 = m.get_layer(0)
+    assert relerr(g0.weights, rbm.weights) < 1e-6 and relerr(g0.visbias, rbm.visbias) < 1e-5
+    dt = pkg.RBMTrainer(m, B, pcd)
+    if pcd:
+        assert relerr(dt.chainstate().to_host(), tr.chainstate) < 1e-4
+    for epoch in range(3):
+        om.trainrbm(rbm, x, tr, 1e-3, cdsteps)
+        pkg.trainrbm_(m, xm, dt, 1e-3, cdsteps)
+    assert dt.clock == tr.clock
+    got = m.get_layer(0)
+    # parameters move by ~lr * gradient; compare the *change* so the gate is not trivially met
+    d_ref, d_got = rbm.weights - g0.weights, got.weights - g0.weights
+    assert np.max(np.abs(d_got - d_ref)) < 0.02 * np.abs(d_ref).max() + 1e-9
+    assert relerr(got.weights, rbm.weights) < RTOL
+    assert relerr(got.visbias, rbm.visbias) < RTOL
+    assert np.max(np.abs(got.hidbias - rbm.hidbias)) < RTOL * np.abs(rbm.hidbias).max() + 1e-8
+
+
+def test_fitrbm_bernoulli_upper_layer(pkg, ctx):
+    """A Bernoulli RBM trained on hidden potentials, with DBM pre-training factors."""
+    g = np.random.default_rng(3)
+    x = g.random((48, 20))
+    ctx.set("seed", 77)
+    got = pkg.fitrbm(x, nhidden=8, epochs=2, batchsize=12, learningrate=0.05, upfactor=1.0, downfactor=2.0, pcd=True, ctx=ctx)
+    ref = om.fitrbm(x, px.Rng(77), nhidden=8, epochs=2, batchsize=12, learningrate=0.05, upfactor=1.0, downfactor=2.0, pcd=True)
+    ctx.set("seed", SEED)
+    assert np.max(np.abs(got.weights - ref.weights)) < 2e-3 * np.abs(ref.weights).max()
+    assert np.max(np.abs(got.hidbias - ref.hidbias)) < 2e-3 * max(np.abs(ref.hidbias).max(), 1e-3)
+
+
+# ------------------------------------------------------------- DBM
+def test_traindbm_step_and_fitdbm(pkg, ctx):
+    units = [40, 16, 8]
+    x, _, _ = synth.counts(60, units[0], seed=2)
+    x[:, 0] += 1.0
+    dbm = synth.random_dbm(units, 4, wscale=(0.02, 0.1))
+    m = dm_of(pkg, ctx, dbm)
+    import copy
+    ref = copy.deepcopy(dbm)
+    om.traindbm(ref, x, px.Rng(SEED), epochs=2, nparticles=32, learningrate=0.01)
+    pkg.traindbm_(m, x, epochs=2, nparticles=32, learningrate=0.01, ctx=ctx)
+    for l in range(2):
+        got = m.get_layer(l)
+        dref = ref[l].weights - dbm[l].weights
+        assert np.max(np.abs((got.weights - dbm[l].weights) - dref)) < 0.05 * np.abs(dref).max() + 1e-9
+    # fitdbm == stackrbms + traindbm under one seed (test/BMTest.jl:699-722)
+    tl = [pkg.TrainLayer(nhidden=16, rbmtype=pkg.NegativeBinomialBernoulliRBM, batchsize=20, learningrate=1e-3),
+          pkg.TrainLayer(nhidden=8, batchsize=20, learningrate=0.01)]
+    a = pkg.fitdbm(x, pretraining=tl, epochs=2, nparticles=16, learningrate=1e-3, seed=5, ctx=ctx)
+    pre = pkg.stackrbms(x, trainlayers=tl, epochs=2, predbm=True, learningrate=1e-3, seed=5, device=True, ctx=ctx)
+    b = pkg.traindbm_(pre, x, epochs=2, nparticles=16, learningrate=1e-3, ctx=ctx)
+    ctx.set("seed", SEED)
+    for ra, rb in zip(a, b):
+        assert np.array_equal(ra.weights, rb.weights) and np.array_equal(ra.hidbias, rb.hidbias)
+    otl = [om.TrainLayer(nhidden=16, rbmtype="nb", batchsize=20, learningrate=1e-3),
+           om.TrainLayer(nhidden=8, batchsize=20, learningrate=0.01)]
+    oref = om.fitdbm(x, px.Rng(5), pretraining=otl, epochs=2, nparticles=16, learningrate=1e-3)
+    for ra, rr in zip(a, oref):
+        assert np.max(np.abs(ra.weights - rr.weights)) < 2e-3 * np.abs(rr.weights).max()
+
+
+# ------------------------------------------------------------- AIS
+def test_ais_matches_oracle_and_exact(pkg, ctx):
+    g = np.random.default_rng(0)
+    rbm = om.BernoulliRBM(g.normal(0, 0.5, (6, 4)), g.normal(0, .3, 6), g.normal(0, .3, 4))
+    m = dm_of(pkg, ctx, rbm)
+    w = pkg.aislogimpweights(m, ntemperatures=200, nparticles=512, ctx=ctx)
+    wr = oais.aislogimpweights(rbm, px.Rng(SEED), ntemperatures=200, nparticles=512)
+    assert np.mean(np.abs(w - wr) > 1e-3) < 0.05          # same Philox stream -> same trajectories
+    lz = exact.exactlogpartitionfunction_rbm(rbm)
+    assert abs(pkg.logpartitionfunction(m, logr=pkg.logmeanexp(w)) - lz) < 0.02 * abs(lz)
+    dbm = [om.BernoulliRBM(g.normal(0, 0.5, (5, 4)), g.normal(0, .3, 5), g.normal(0, .3, 4)),
+           om.BernoulliRBM(g.normal(0, 0.5, (4, 3)), g.normal(0, .3, 4), g.normal(0, .3, 3))]
+    md = dm_of(pkg, ctx, dbm)
+    wd = pkg.aislogimpweights(md, ntemperatures=200, nparticles=512, ctx=ctx)
+    wdr = oais.aislogimpweights(dbm, px.Rng(SEED), ntemperatures=200, nparticles=512)
+    assert np.mean(np.abs(wd - wdr) > 1e-3) < 0.05
+    lzd = exact.exactlogpartitionfunction_dbm(dbm)
+    assert abs(pkg.logpartitionfunction(md, logr=pkg.logmeanexp(wd)) - lzd) < 0.02 * abs(lzd)
+    # NB-visible 3-RBM DBM: fixed-trajectory increments agree (deterministic part of the gate)
+    nb = synth.random_dbm([24, 12, 8, 4], 6, wscale=(0.02, 0.2))
+    mn = dm_of(pkg, ctx, nb)
+    wn = pkg.aislogimpweights(mn, ntemperatures=50, nparticles=256, ctx=ctx)
+    wnr = oais.aislogimpweights(nb, px.Rng(SEED), ntemperatures=50, nparticles=256)
+    assert np.mean(np.abs(wn - wnr) > 1e-3 * np.maximum(1, np.abs(wnr))) < 0.05
+    # sharded == unsharded (test/BMTest.jl:442-492 serial vs parallelized)
+    w2 = np.concatenate([pkg.aislogimpweights(mn, ntemperatures=50, nparticles=128, ctx=ctx),
+                         pkg.aislogimpweights(mn, ntemperatures=50, nparticles=128, row_offset=128, ctx=ctx)])
+    assert np.array_equal(w2, wn)
+
+
+# ------------------------------------------------ G3: free-running statistics
+def test_free_running_statistics_vs_exact(pkg, ctx):
+    """Per-gene mean / variance / zero fraction of generated cells vs the exact
+    NB-RBM marginal (H = 6 hidden units enumerated)."""
+    g = np.random.default_rng(12)
+    V, H, n = 12, 6, 200000
+    means = np.array([.05, .1, .2, .4, .8, 1.5, 3., 6., 12., 0.3, 0.6, 25.])
+    rbm = om.NegativeBinomialBernoulliRBM(-g.uniform(0.05, 0.5, (V, H)), np.log(means / (means + 0.5)),
+                                          g.normal(0, .5, H), np.full(V, 0.5))
+    m = dm_of(pkg, ctx, rbm)
+    p = pkg.sampleparticles(m, n, burnin=40, device=True)
+    mean, var, zf = p.layer(0).column_stats()
+    emean, evar, ezf = exact.nbrbm_visible_moments(rbm, eps=1e-6)
+    se = np.sqrt(evar / n)
+    assert np.all(np.abs(mean - emean) < 5 * se), (mean, emean)
+    assert np.all(np.abs(zf - ezf) < 5 * np.sqrt(ezf * (1 - ezf) / n) + 1e-4)
+    assert np.all(np.abs(var / evar - 1) < 0.12)          # heavy-tailed (r = 0.5): 4th-moment driven
