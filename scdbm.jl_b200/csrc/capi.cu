@@ -163,7 +163,13 @@ struct SweepSrc {
 
 static void run_gemm(scdbm_ctx* ctx, GemmArgs& g, const SweepSrc* srcs, int nsrc) {
     bool use_tc = false;
-    if (ctx->engine != SCDBM_ENGINE_SIMT && srcs) use_tc = tc_supported(g, nsrc);
+    if (ctx->engine != SCDBM_ENGINE_SIMT && srcs) {
+        use_tc = tc_supported(g, nsrc);
+        // AUTO: tiny problems are launch-latency-bound; the FFMA kernel has no descriptor set-up cost
+        double work = 0.0;
+        for (int s = 0; s < nsrc; ++s) work += (double)g.M * (double)g.N * (double)g.src[s].K;
+        if (ctx->engine == SCDBM_ENGINE_AUTO && work < (double)(1 << 22)) use_tc = false;
+    }
     if (ctx->engine == SCDBM_ENGINE_TC && !use_tc && srcs)
         throw Err(SCDBM_EUNSUP, "engine=tc requested but the shape is not tiled by the tcgen05 kernel");
     if (use_tc) {

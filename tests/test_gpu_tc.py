@@ -1,0 +1,81 @@
+"""The tcgen05/TMA/TMEM engine forced on (engine=2), checked against the oracle
+and against the CUDA-core engine on the same inputs."""
+import numpy as np
+import pytest
+
+from conftest import to_pkg_model, relerr
+from oracle import model as om, philox as px, sampling as osp, synth, ais as oais
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+SEED = 20261019
+
+
+@pytest.fixture(scope="module")
+def tc(pkg):
+    c = pkg.Context(0, SEED)
+    c.set("engine", pkg.ENGINE_TC)
+    return c
+
+
+@pytest.fixture(scope="module")
+def simt(pkg):
+    c = pkg.Context(0, SEED)
+    c.set("engine", pkg.ENGINE_SIMT)
+    return c
+
+
+@pytest.mark.parametrize("n,units", [(5, (7, 5, 3)), (128, (64, 64, 64)), (129, (130, 67, 33)), (300, (500, 256, 64)),
+                                     (1000, (2000, 256, 64))])
+def test_tc_conditionals(pkg, tc, n, units):
+    dbm = synth.random_dbm(list(units), 3, wscale=(0.002, 0.02))
+    m = pkg.DeviceModel.from_host(to_pkg_model(pkg, dbm), tc)
+    g = np.random.default_rng(1)
+    v = g.poisson(1.5, (n, units[0])).astype(float)
+    v[0, 0] = 3000.0
+    h1 = (g.random((n, units[1])) < 0.5).astype(float)
+    h2 = (g.random((n, units[2])) < 0.5).astype(float)
+    tc.launch_count(reset=True)
+    assert relerr(pkg.hiddeninput(m, v, ctx=tc), om.hiddeninput(dbm[0], v), 1e-6) < RTOL
+    assert relerr(pkg.hiddenpotential(m, v, 2.0, ctx=tc), om.hiddenpotential(dbm[0], v, 2.0)) < RTOL
+    assert relerr(pkg.visibleinput(m, h1, ctx=tc), om.visibleinput(dbm[0], h1)) < RTOL
+    assert relerr(pkg.visiblepotential(m, h1, ctx=tc), om.visiblepotential(dbm[0], h1)) < RTOL
+    assert relerr(pkg.hiddenpotential(m, h1, layer=1, ctx=tc), om.hiddenpotential(dbm[1], h1)) < RTOL
+    assert relerr(pkg.visiblepotential(m, h2, 2.0, layer=1, ctx=tc), om.visiblepotential(dbm[1], h2, 2.0)) < RTOL
+    mu1 = g.random((n, units[1]))                       # real-valued (mean-field) operand: hi+lo planes
+    assert relerr(pkg.hiddenpotential(m, mu1, layer=1, ctx=tc), om.hiddenpotential(dbm[1], mu1)) < RTOL
+    ref = osp.sigm(om.dbm_layer_input(dbm, [v, h1, h2], 1))
+    assert relerr(pkg.dbmlayer(m, 1, v, h2, ctx=tc), ref) < RTOL
+    assert tc.get("tc_launches") >= 8                   # the tensor-core kernel really ran
+
+
+def test_tc_sampling_matches_simt_and_oracle(pkg, tc, simt):
+    units = [500, 256, 64]
+    dbm = synth.random_dbm(units, 3)
+    pm = to_pkg_model(pkg, dbm)
+    mt, ms = pkg.DeviceModel.from_host(pm, tc), pkg.DeviceModel.from_host(pm, simt)
+    n = 400
+    pt = pkg.DeviceParticles(mt, n).init(False)
+    ps = pkg.DeviceParticles(ms, n).init(False)
+    ref = om.initparticles(dbm, n, px.Rng(SEED))
+    pkg.gibbssample_(pt, mt, 4)
+    pkg.gibbssample_(ps, ms, 4)
+    om.gibbssample_dbm(ref, dbm, px.Rng(SEED), 4)
+    for a, b, c in zip(pt.to_host(), ps.to_host(), ref):
+        assert np.mean(a != b) < 2e-3                   # two GPU engines: same draws up to accumulation-order flips
+        assert np.mean(a != c) < 5e-3
+
+
+def test_tc_meanfield_and_ais(pkg, tc):
+    units = [300, 128, 64, 32]
+    dbm = synth.random_dbm(units, 7, wscale=(0.002, 0.02))
+    m = pkg.DeviceModel.from_host(to_pkg_model(pkg, dbm), tc)
+    x = np.random.default_rng(8).poisson(1.0, (200, units[0])).astype(float)
+    got, it, delta = pkg.meanfield(m, x, eps=1e-6, return_info=True, ctx=tc)
+    ref, rit, _ = om.meanfield(dbm, x, eps=1e-6)
+    assert abs(it - rit) <= 1
+    for a, b in zip(got[1:], ref[1:]):
+        assert relerr(a, b) < RTOL
+    w = pkg.aislogimpweights(m, ntemperatures=20, nparticles=256, ctx=tc)
+    wr = oais.aislogimpweights(dbm, px.Rng(SEED), ntemperatures=20, nparticles=256)
+    assert np.mean(np.abs(w - wr) > 1e-3 * np.maximum(1, np.abs(wr))) < 0.05
