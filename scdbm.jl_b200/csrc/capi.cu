@@ -58,7 +58,24 @@ struct scdbm_ctx {
     int64_t tc_launches = 0;
     int num_sms = 148;
     TcContext tc;
+    float* scratch = nullptr;   // reduction workspace (column-sum partials)
+    int64_t scratch_cap = 0;
+    int64_t live = 0;      // child handles still alive
+    bool closed = false;   // scdbm_ctx_destroy was called; freed when `live` drops to 0
 };
+static void ctx_free(scdbm_ctx* c) {
+    cudaStreamSynchronize(c->stream);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaFree(c->d_delta);
+    cudaFree(c->scratch);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+static void ctx_retain(scdbm_ctx* c) { c->live++; }
+static void ctx_release(scdbm_ctx* c) {
+    if (--c->live == 0 && c->closed) ctx_free(c);
+}
 
 struct Layer {
     int V = 0, H = 0, kind = SCDBM_VIS_BERNOULLI;
@@ -70,9 +87,26 @@ struct Layer {
 struct scdbm_model {
     scdbm_ctx* ctx;
     std::vector<Layer> L;
+    int64_t live = 0;
+    bool closed = false;
     int units(int layer) const { return layer == 0 ? L[0].V : L[layer - 1].H; }
     int nlayers() const { return (int)L.size() + 1; }
 };
+
+static void model_free(scdbm_model* m) {
+    cudaStreamSynchronize(m->ctx->stream);
+    for (auto& L : m->L) {
+        cudaFree(L.W); cudaFree(L.a); cudaFree(L.b); cudaFree(L.r);
+        cudaFree(L.w0); cudaFree(L.w1); cudaFree(L.t0); cudaFree(L.t1);
+    }
+    scdbm_ctx* c = m->ctx;
+    delete m;
+    ctx_release(c);
+}
+static void model_retain(scdbm_model* m) { m->live++; }
+static void model_release(scdbm_model* m) {
+    if (--m->live == 0 && m->closed) model_free(m);
+}
 
 struct scdbm_mat {
     scdbm_ctx* ctx;
@@ -111,10 +145,29 @@ struct scdbm_trainer {
 // ------------------------------------------------------------------ helpers
 static inline int grid1d(int64_t n, int block = 256) { return (int)std::min<int64_t>((n + block - 1) / block, 148 * 16); }
 
+// out[c] (+)= scale * sum_r m(r, c), deterministic
+static void colsum(scdbm_ctx* c, const MatView& m, float scale, float* out, bool accumulate) {
+    if (m.cols == 0) return;
+    const int nslabs = (int)std::max<int64_t>(1, std::min<int64_t>((m.rows + 255) / 256, 256));
+    const int64_t need = (int64_t)nslabs * m.cols;
+    if (c->scratch_cap < need) {
+        cudaStreamSynchronize(c->stream);
+        cudaFree(c->scratch);
+        c->scratch = nullptr;
+        if (cudaMalloc(&c->scratch, need * sizeof(float)) != cudaSuccess) throw Err(SCDBM_ENOMEM, "column-sum workspace");
+        c->scratch_cap = need;
+    }
+    dim3 grid((unsigned)((m.cols + 31) / 32), (unsigned)nslabs), block(32, 8);
+    k_colsum_partial<<<grid, block, 0, c->stream>>>(m, c->scratch);
+    k_colsum_final<<<(unsigned)((m.cols + 127) / 128), 128, 0, c->stream>>>(c->scratch, nslabs, m.cols, scale, out, accumulate ? 1 : 0);
+    c->launches += 2;
+}
+
 static scdbm_mat* mat_new(scdbm_ctx* ctx, int64_t rows, int64_t cols, int kind) {
     REQUIRE(rows >= 0 && cols >= 0, "matrix dimensions must be non-negative");
     REQUIRE(kind >= 0 && kind <= 2, "unknown matrix kind");
     auto* m = new scdbm_mat{ctx, {}, true};
+    ctx_retain(ctx);
     m->v.rows = rows;
     m->v.cols = cols;
     m->v.ld = round_up(std::max<int64_t>(cols, 1), 64);
@@ -126,6 +179,10 @@ static scdbm_mat* mat_new(scdbm_ctx* ctx, int64_t rows, int64_t cols, int kind) 
         CK(cudaMalloc(&m->v.p1, bytes));
         CK(cudaMemsetAsync(m->v.p1, 0, bytes, ctx->stream));
     }
+    if (kind == MAT_REAL) {
+        CK(cudaMalloc(&m->v.f, bytes * 2));
+        CK(cudaMemsetAsync(m->v.f, 0, bytes * 2, ctx->stream));
+    }
     return m;
 }
 static void mat_free(scdbm_mat* m) {
@@ -133,6 +190,11 @@ static void mat_free(scdbm_mat* m) {
     if (m->owns) {
         cudaFree(m->v.p0);
         cudaFree(m->v.p1);
+        cudaFree(m->v.f);
+        scdbm_ctx* c = m->ctx;
+        delete m;
+        ctx_release(c);
+        return;
     }
     delete m;
 }
@@ -204,7 +266,7 @@ static void run_sweep(scdbm_ctx* ctx, const SweepSrc* srcs, int nsrc, int64_t M,
         REQUIRE(a.cols == K, "state width does not match the weight matrix");
         REQUIRE(a.rows >= M, "state has fewer rows than requested");
         REQUIRE((srcs[s].up ? L.H : L.V) == N, "output width does not match the weight matrix");
-        g.src[s].a = Operand{a.p0, a.p1, nullptr, a.ld, 1};
+        g.src[s].a = a.f ? Operand{nullptr, nullptr, a.f, a.ld, 1} : Operand{a.p0, a.p1, nullptr, a.ld, 1};
         g.src[s].b = srcs[s].up ? Operand{nullptr, nullptr, L.W, 1, (int64_t)L.H} : Operand{nullptr, nullptr, L.W, (int64_t)L.H, 1};
         g.src[s].K = K;
         g.src[s].scale = 1.0f;
@@ -357,12 +419,8 @@ int32_t scdbm_ctx_create(int32_t device, uint64_t seed, void* stream, scdbm_ctx*
 int32_t scdbm_ctx_destroy(scdbm_ctx* c) {
     API_BEGIN
     if (!c) return SCDBM_OK;
-    cudaStreamSynchronize(c->stream);
-    cudaEventDestroy(c->ev0);
-    cudaEventDestroy(c->ev1);
-    cudaFree(c->d_delta);
-    if (c->own_stream) cudaStreamDestroy(c->stream);
-    delete c;
+    c->closed = true;   // children (models, matrices, ...) may outlive the Python/Julia wrapper of the context
+    if (c->live == 0) ctx_free(c);
     API_END
 }
 
@@ -429,6 +487,7 @@ int32_t scdbm_model_create(scdbm_ctx* c, int32_t nrbms, const int32_t* units, in
     REQUIRE(visible_kind == SCDBM_VIS_BERNOULLI || visible_kind == SCDBM_VIS_NEGBIN, "unknown visible kind");
     for (int i = 0; i <= nrbms; ++i) REQUIRE(units[i] > 0, "layer sizes must be positive");
     auto* m = new scdbm_model{c, {}};
+    ctx_retain(c);
     m->L.resize(nrbms);
     for (int l = 0; l < nrbms; ++l) {
         Layer& L = m->L[l];
@@ -458,12 +517,8 @@ int32_t scdbm_model_create(scdbm_ctx* c, int32_t nrbms, const int32_t* units, in
 int32_t scdbm_model_destroy(scdbm_model* m) {
     API_BEGIN
     if (!m) return SCDBM_OK;
-    cudaStreamSynchronize(m->ctx->stream);
-    for (auto& L : m->L) {
-        cudaFree(L.W); cudaFree(L.a); cudaFree(L.b); cudaFree(L.r);
-        cudaFree(L.w0); cudaFree(L.w1); cudaFree(L.t0); cudaFree(L.t1);
-    }
-    delete m;
+    m->closed = true;   // particles / optimizers / trainers keep the parameters alive
+    if (m->live == 0) model_free(m);
     API_END
 }
 
@@ -586,9 +641,7 @@ int32_t scdbm_model_init_layer(scdbm_model* m, int32_t l, const scdbm_mat* x, co
     float* d_sum = nullptr;
     CK(cudaMalloc(&d_sum, L.V * sizeof(float)));
     CK(cudaMemsetAsync(d_sum, 0, L.V * sizeof(float), c->stream));
-    dim3 grid((L.V + 31) / 32, (unsigned)std::min<int64_t>((x->v.rows + 7) / 8, 64)), block(32, 8);
-    k_colsum<<<grid, block, 0, c->stream>>>(x->v, 1.0f, d_sum, 1);
-    c->launches++;
+    colsum(c, x->v, 1.0f, d_sum, false);
     std::vector<float> s(L.V);
     CK(cudaMemcpyAsync(s.data(), d_sum, L.V * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -654,6 +707,7 @@ int32_t scdbm_mat_upload(scdbm_mat* m, const double* x, int64_t ld) {
         MatView sub = m->v;
         sub.p0 += c0;
         if (sub.p1) sub.p1 += c0;
+        if (sub.f) sub.f += c0;
         sub.cols = nc;
         dim3 grid((unsigned)((m->v.rows + 31) / 32), (unsigned)((nc + 31) / 32)), block(32, 8);
         k_upload_f64<<<grid, block, 0, c->stream>>>(stage, ld, sub);
@@ -680,6 +734,7 @@ int32_t scdbm_mat_download(const scdbm_mat* m, double* x, int64_t ld) {
         MatView sub = m->v;
         sub.p0 += c0;
         if (sub.p1) sub.p1 += c0;
+        if (sub.f) sub.f += c0;
         sub.cols = nc;
         dim3 grid((unsigned)((m->v.rows + 31) / 32), (unsigned)((nc + 31) / 32)), block(32, 8);
         k_download_f64<<<grid, block, 0, c->stream>>>(sub, stage, ld);
@@ -803,6 +858,7 @@ int32_t scdbm_particles_create(scdbm_model* m, int64_t n, uint64_t row_offset, i
     REQUIRE(n >= 0, "nparticles must be non-negative");
     REQUIRE(row_offset + (uint64_t)n <= 0xFFFFFFFFull, "global particle index exceeds 2^32");
     auto* p = new scdbm_particles{m, n, row_offset, 1, real_valued != 0, {}, {}};
+    model_retain(m);
     const int nl = m->nlayers();
     for (int i = 0; i < nl; ++i) {
         int kind = i == 0 ? (m->L[0].kind == SCDBM_VIS_NEGBIN ? MAT_COUNT : MAT_BINARY) : MAT_BINARY;
@@ -823,7 +879,9 @@ int32_t scdbm_particles_destroy(scdbm_particles* p) {
     for (auto* x : p->nxt) mat_free(x);
     if (p->alias0) delete p->alias0;
     cudaFree(p->hoist);
+    scdbm_model* pm = p->model;
     delete p;
+    model_release(pm);
     API_END
 }
 
@@ -1000,7 +1058,10 @@ static void meanfield_impl(scdbm_model* m, const scdbm_mat* x, double eps, int m
     }
     double delta = 1.0;
     int it = 0;
-    while (delta > eps && (maxiter <= 0 || it < maxiter)) {
+    // the reference loops without a cap; fp32 round-off can keep delta above a tiny eps forever, so stop
+    // after MF_ITER_CAP sweeps and report the delta reached (the caller sees delta > eps)
+    const int MF_ITER_CAP = 10000;
+    while (delta > eps && it < (maxiter > 0 ? maxiter : MF_ITER_CAP)) {
         CK(cudaMemsetAsync(c->d_delta, 0, sizeof(unsigned int), c->stream));
         for (int i = 1; i < nl - 1; ++i) {
             const MatView& cur = mu->cur[i]->v;
@@ -1046,6 +1107,7 @@ int32_t scdbm_opt_create(scdbm_model* m, scdbm_opt** out) {
     API_BEGIN
     REQUIRE(m && out, "NULL argument");
     auto* o = new scdbm_opt{m};
+    model_retain(m);
     int64_t off = 0;
     for (auto& L : m->L) {
         o->offW.push_back(off); off += (int64_t)L.V * L.H;
@@ -1060,7 +1122,13 @@ int32_t scdbm_opt_create(scdbm_model* m, scdbm_opt** out) {
 }
 int32_t scdbm_opt_destroy(scdbm_opt* o) {
     API_BEGIN
-    if (o) { cudaStreamSynchronize(o->model->ctx->stream); cudaFree(o->buf); delete o; }
+    if (o) {
+        cudaStreamSynchronize(o->model->ctx->stream);
+        cudaFree(o->buf);
+        scdbm_model* om_ = o->model;
+        delete o;
+        model_release(om_);
+    }
     API_END
 }
 
@@ -1077,12 +1145,13 @@ static void gradient_layer(scdbm_opt* o, int l, const MatView& v, const MatView&
     g.nsrc = 2;
     g.M = L.V;
     g.N = L.H;
-    g.src[0].a = Operand{v.p0, v.p1, nullptr, 1, v.ld};
-    g.src[0].b = Operand{h.p0, h.p1, nullptr, 1, h.ld};
+    auto opT = [](const MatView& x) { return x.f ? Operand{nullptr, nullptr, x.f, 1, x.ld} : Operand{x.p0, x.p1, nullptr, 1, x.ld}; };
+    g.src[0].a = opT(v);
+    g.src[0].b = opT(h);
     g.src[0].K = v.rows;
     g.src[0].scale = pos_scale;
-    g.src[1].a = Operand{vm.p0, vm.p1, nullptr, 1, vm.ld};
-    g.src[1].b = Operand{hm.p0, hm.p1, nullptr, 1, hm.ld};
+    g.src[1].a = opT(vm);
+    g.src[1].b = opT(hm);
     g.src[1].K = vm.rows;
     g.src[1].scale = -neg_scale;
     g.epi = epi_base(c);
@@ -1103,16 +1172,10 @@ static void gradient_layer(scdbm_opt* o, int l, const MatView& v, const MatView&
     float* ga = o->buf + o->offA[l];
     float* gb = o->buf + o->offB[l];
     CK(cudaMemsetAsync(ga, 0, (size_t)(L.V + L.H) * sizeof(float), c->stream));  // offA and offB are adjacent
-    auto colsum = [&](const MatView& s, float scale, float* out) {
-        if (s.rows == 0) return;
-        dim3 grid((unsigned)((s.cols + 31) / 32), (unsigned)std::min<int64_t>((s.rows + 7) / 8, 128)), block(32, 8);
-        k_colsum<<<grid, block, 0, c->stream>>>(s, scale, out, 1);
-        c->launches++;
-    };
-    colsum(v, pos_scale, ga);
-    colsum(vm, -neg_scale, ga);
-    colsum(h, pos_scale, gb);
-    colsum(hm, -neg_scale, gb);
+    colsum(c, v, pos_scale, ga, true);
+    colsum(c, vm, -neg_scale, ga, true);
+    colsum(c, h, pos_scale, gb, true);
+    colsum(c, hm, -neg_scale, gb, true);
     CK(cudaGetLastError());
 }
 
@@ -1205,6 +1268,7 @@ int32_t scdbm_trainer_create(scdbm_model* m, int32_t l, int32_t B, int32_t pcd, 
     scdbm_ctx* c = m->ctx;
     Layer& L = m->L[l];
     auto* t = new scdbm_trainer{m, l, B, pcd, 1};
+    model_retain(m);
     const int vkind = L.kind == SCDBM_VIS_NEGBIN ? MAT_COUNT : MAT_REAL;  // upper layers train on potentials
     t->v = mat_new(c, B, L.V, vkind);
     t->h = mat_new(c, B, L.H, MAT_REAL);
@@ -1232,7 +1296,9 @@ int32_t scdbm_trainer_destroy(scdbm_trainer* t) {
     mat_free(t->chain); mat_free(t->v); mat_free(t->h); mat_free(t->hm); mat_free(t->hs); mat_free(t->vm); mat_free(t->vs);
     scdbm_opt_destroy(t->opt);
     cudaFree(t->d_perm);
+    scdbm_model* tm = t->model;
     delete t;
+    model_release(tm);
     API_END
 }
 

@@ -14,11 +14,14 @@ namespace scdbm {
 //   BINARY : p0 in {0,1}                                   (exact)
 //   COUNT  : p0 = v mod 256, p1 = v - p0  (multiple of 256) (exact to 65535)
 //   REAL   : p0 = bf16(v),   p1 = bf16(v - p0)             (16 significant bits)
+//            plus an fp32 master copy `f` (what downloads, mean-field deltas and the
+//            CUDA-core engine read; the planes are the tensor-core operands)
 enum MatKind : int32_t { MAT_BINARY = 0, MAT_COUNT = 1, MAT_REAL = 2 };
 
 struct MatView {
     __nv_bfloat16* p0;
     __nv_bfloat16* p1;     // nullptr for BINARY
+    float* f;              // fp32 master copy, REAL only (else nullptr)
     int64_t rows, cols, ld; // ld (elements) is a multiple of 64
     int32_t kind;
 };

@@ -24,6 +24,7 @@ __global__ void k_upload_f64(const double* __restrict__ src, int64_t lds, MatVie
             split_value(dst.kind, t[threadIdx.x][j], a, b);
             dst.p0[r * dst.ld + c] = a;
             if (dst.p1) dst.p1[r * dst.ld + c] = b;
+            if (dst.f) dst.f[r * dst.ld + c] = t[threadIdx.x][j];
         }
     }
 }
@@ -99,8 +100,9 @@ __global__ void k_update(float* __restrict__ theta, const float* __restrict__ gr
     }
 }
 
-// ---- column sums of a state matrix: out[c] (+)= scale * sum_r m(r, c)
-__global__ void k_colsum(MatView m, float scale, float* __restrict__ out, int accumulate) {
+// ---- column sums of a state matrix, deterministic (no float atomics):
+// pass 1: partial[slab][c] = sum over the slab's rows; pass 2: out[c] (+)= scale * sum_slabs (fixed order)
+__global__ void k_colsum_partial(MatView m, float* __restrict__ partial) {
     // block = 32 columns x 8 row-lanes; grid.x over column blocks, grid.y over row slabs
     __shared__ float red[8][33];
     const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
@@ -112,8 +114,16 @@ __global__ void k_colsum(MatView m, float scale, float* __restrict__ out, int ac
     if (threadIdx.y == 0 && c < m.cols) {
         float tot = 0.0f;
         for (int j = 0; j < 8; ++j) tot += red[j][threadIdx.x];
-        atomicAdd(&out[c], scale * tot);
+        partial[(int64_t)blockIdx.y * m.cols + c] = tot;
     }
+}
+__global__ void k_colsum_final(const float* __restrict__ partial, int nslabs, int64_t cols, float scale,
+                               float* __restrict__ out, int accumulate) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float tot = 0.0f;
+    for (int s = 0; s < nslabs; ++s) tot += partial[(int64_t)s * cols + c];
+    out[c] = (accumulate ? out[c] : 0.0f) + scale * tot;
 }
 
 __global__ void k_fill_f32(float* p, int64_t n, float v) {
@@ -127,6 +137,7 @@ __global__ void k_gather_rows(MatView src, const int32_t* __restrict__ idx, MatV
     for (int64_t c = threadIdx.x; c < dst.ld; c += blockDim.x) {
         dst.p0[r * dst.ld + c] = src.p0[s * src.ld + c];
         if (dst.p1) dst.p1[r * dst.ld + c] = src.p1 ? src.p1[s * src.ld + c] : __float2bfloat16_rn(0.0f);
+        if (dst.f) dst.f[r * dst.ld + c] = src.f ? src.f[s * src.ld + c] : (c < src.cols ? mat_load(src, s, c) : 0.0f);
     }
 }
 
@@ -136,6 +147,7 @@ __global__ void k_copy_rows(MatView src, MatView dst, int64_t rows) {
     for (int64_t c = threadIdx.x; c < dst.ld; c += blockDim.x) {
         dst.p0[r * dst.ld + c] = src.p0[r * src.ld + c];
         if (dst.p1) dst.p1[r * dst.ld + c] = src.p1 ? src.p1[r * src.ld + c] : __float2bfloat16_rn(0.0f);
+        if (dst.f) dst.f[r * dst.ld + c] = src.f ? src.f[r * src.ld + c] : (c < src.cols ? mat_load(src, r, c) : 0.0f);
     }
 }
 

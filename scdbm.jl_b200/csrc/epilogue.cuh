@@ -9,6 +9,7 @@ namespace scdbm {
 
 __device__ __forceinline__ float mat_load(const MatView& m, int64_t row, int64_t col) {
     const int64_t i = row * m.ld + col;
+    if (m.f) return m.f[i];
     float v = __bfloat162float(m.p0[i]);
     if (m.p1) v += __bfloat162float(m.p1[i]);
     return v;
@@ -31,6 +32,10 @@ __device__ __forceinline__ void mat_store4(const MatView& m, int64_t row, int64_
 #pragma unroll
     for (int j = 0; j < 4; ++j) split_value(m.kind, v[j], a[j], b[j]);
     const int64_t i = row * m.ld + col0;
+    if (m.f) {
+        if (nvalid == 4) *reinterpret_cast<float4*>(m.f + i) = make_float4(v[0], v[1], v[2], v[3]);
+        else for (int j = 0; j < nvalid; ++j) m.f[i + j] = v[j];
+    }
     if (nvalid == 4) {
         uint2 pa, pb;
         pa.x = (uint32_t)__bfloat16_as_ushort(a[0]) | ((uint32_t)__bfloat16_as_ushort(a[1]) << 16);

@@ -13,8 +13,11 @@ __device__ __forceinline__ float sigmf(float x) { return 1.0f / (1.0f + expf(-x)
 
 // src/gibbssampling.jl:1018 : r e^x/(1-e^x) + 1e-6, with 1-e^x = -expm1(x)
 __device__ __forceinline__ float nb_mean(float x, float r) {
-    const float em1 = expm1f(x);
-    return r * (em1 + 1.0f) / (-em1) + 1e-6f;
+    // numerator e^x directly (expm1(x)+1 cancels for very negative x); denominator via expm1 only
+    // where 1-e^x itself would cancel (x -> 0-)
+    const float ex = expf(x);
+    const float den = (x > -0.6931472f) ? -expm1f(x) : 1.0f - ex;
+    return r * ex / den + 1e-6f;
 }
 
 // chop-down inversion of a pmf with P_{k+1} = P_k * ratio(k)

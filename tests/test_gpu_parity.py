@@ -87,8 +87,12 @@ def test_conditionals_deterministic(pkg, ctx, n, units):
     assert relerr(pkg.hiddenpotential(m, h1, 1.0, layer=1), om.hiddenpotential(dbm[1], h1)) < RTOL
     assert relerr(pkg.visiblepotential(m, h2, 2.0, layer=1), om.visiblepotential(dbm[1], h2, 2.0)) < RTOL
     # intermediate DBM layer: both neighbours, both biases
+    # probabilities: relative gate with a 1e-7 floor (sigm of a very negative input turns an absolute
+    # input error into a relative output error; the input itself is gated below)
     ref = osp.sigm(om.dbm_layer_input(dbm, [v, h1, h2], 1))
-    assert relerr(pkg.dbmlayer(m, 1, v, h2), ref) < RTOL
+    assert relerr(pkg.dbmlayer(m, 1, v, h2), ref, 1e-7) < RTOL
+    xin = om.dbm_layer_input(dbm, [v, h1, h2], 1)       # sum of two contractions: norm-wise gate (cancellation)
+    assert relerr(pkg.dbmlayer(m, 1, v, h2, what=pkg.OUT_INPUT), xin, 0.05 * np.abs(xin).max()) < RTOL
 
 
 def test_nb_mean_adversarial(pkg, ctx):
@@ -155,6 +159,8 @@ def test_nb_same_uniforms(pkg, ctx):
 def test_philox_fed_draws_match_oracle(pkg, ctx):
     """No explicit uniforms: both sides derive them from Philox(seed, stream, tick, row, col)."""
     dbm = small_dbm((130, 67, 33))
+    dbm[0].visbias[:10] = np.log(30.0 / 30.5)           # ten high-mean genes -> gamma-Poisson branch
+    dbm[0].weights[:10] *= 0.001
     m = dm_of(pkg, ctx, dbm)
     g = np.random.default_rng(6)
     n = 150
@@ -191,7 +197,10 @@ def test_initparticles_exact(pkg, ctx):
     for biased in (False, True):
         got = pkg.initparticles(m, 77, biased=biased)
         ref = om.initparticles(dbm, 77, px.Rng(SEED), biased=biased)
-        for a, b in zip(got, ref):
+        # hidden layers: u < 0.5 / u < sigm(b) -- exact.  NB visible init: two chained fp32 inversions,
+        # may differ from the fp64 oracle where u sits within round-off of a CDF step
+        assert np.mean(got[0] != ref[0]) < 1e-3
+        for a, b in zip(got[1:], ref[1:]):
             assert np.array_equal(a, b)
 
 
@@ -309,7 +318,7 @@ def test_gradient_and_update(pkg, ctx):
 def test_trainrbm_epoch(pkg, ctx, pcd, cdsteps, n, B):
     V, H = 40, 16
     x, _, _ = synth.counts(n, V, seed=1)
-    x[:, 0] += 1.0                                       # no all-zero gene
+    x[0, :] += 1.0                                       # no all-zero gene (log(0) = -Inf in initrbm)
     rng = px.Rng(SEED)
     rbm = om.initrbm(x, H, rng, "nb")
     tr = om.RBMTrainer(rbm, B, rng, pcd)
@@ -329,8 +338,9 @@ def test_trainrbm_epoch(pkg, ctx, pcd, cdsteps, n, B):
     # parameters move by ~lr * gradient; compare the *change* so the gate is not trivially met
     d_ref, d_got = rbm.weights - g0.weights, got.weights - g0.weights
     assert np.max(np.abs(d_got - d_ref)) < 0.02 * np.abs(d_ref).max() + 1e-9
-    assert relerr(got.weights, rbm.weights) < RTOL
-    assert relerr(got.visbias, rbm.visbias) < RTOL
+    # norm-wise gate: entries driven to ~0 by the W <= 0 clamp have no meaningful relative error
+    assert np.max(np.abs(got.weights - rbm.weights)) < RTOL * np.abs(rbm.weights).max()
+    assert np.max(np.abs(got.visbias - rbm.visbias)) < RTOL * np.abs(rbm.visbias).max()
     assert np.max(np.abs(got.hidbias - rbm.hidbias)) < RTOL * np.abs(rbm.hidbias).max() + 1e-8
 
 
@@ -350,7 +360,7 @@ def test_fitrbm_bernoulli_upper_layer(pkg, ctx):
 def test_traindbm_step_and_fitdbm(pkg, ctx):
     units = [40, 16, 8]
     x, _, _ = synth.counts(60, units[0], seed=2)
-    x[:, 0] += 1.0
+    x[0, :] += 1.0
     dbm = synth.random_dbm(units, 4, wscale=(0.02, 0.1))
     m = dm_of(pkg, ctx, dbm)
     import copy
@@ -404,7 +414,7 @@ def test_ais_matches_oracle_and_exact(pkg, ctx):
     # sharded == unsharded (test/BMTest.jl:442-492 serial vs parallelized)
     w2 = np.concatenate([pkg.aislogimpweights(mn, ntemperatures=50, nparticles=128, ctx=ctx),
                          pkg.aislogimpweights(mn, ntemperatures=50, nparticles=128, row_offset=128, ctx=ctx)])
-    assert np.array_equal(w2, wn)
+    assert np.allclose(w2, wn, rtol=1e-12, atol=1e-12)   # double atomics: order of the row-sum pieces may differ
 
 
 # ------------------------------------------------ G3: free-running statistics

@@ -45,7 +45,9 @@ def test_tc_conditionals(pkg, tc, n, units):
     mu1 = g.random((n, units[1]))                       # real-valued (mean-field) operand: hi+lo planes
     assert relerr(pkg.hiddenpotential(m, mu1, layer=1, ctx=tc), om.hiddenpotential(dbm[1], mu1)) < RTOL
     ref = osp.sigm(om.dbm_layer_input(dbm, [v, h1, h2], 1))
-    assert relerr(pkg.dbmlayer(m, 1, v, h2, ctx=tc), ref) < RTOL
+    assert relerr(pkg.dbmlayer(m, 1, v, h2, ctx=tc), ref, 1e-7) < RTOL
+    xin = om.dbm_layer_input(dbm, [v, h1, h2], 1)
+    assert relerr(pkg.dbmlayer(m, 1, v, h2, what=pkg.OUT_INPUT, ctx=tc), xin, 0.05 * np.abs(xin).max()) < RTOL
     assert tc.get("tc_launches") >= 8                   # the tensor-core kernel really ran
 
 
