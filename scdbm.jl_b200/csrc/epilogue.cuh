@@ -124,4 +124,59 @@ __device__ __forceinline__ float epi_apply4(const EpiParams& e, int64_t row, int
     return 0.0f;
 }
 
+// ---- specialised sampling epilogues (tensor-core engine, Philox-fed): 4 consecutive columns
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+__device__ __forceinline__ void epi_nb_draw4(const EpiParams& e, int64_t row, int64_t col0, const float (&acc)[4], int nvalid) {
+    const uint4 w = philox_group(e, (uint32_t)row, (uint32_t)(col0 >> 2));
+    const float u[4] = {u23(w.x), u23(w.y), u23(w.z), u23(w.w)};
+    float lo[4], hi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float k = 0.0f;
+        if (j < nvalid) {
+            const float r = __ldg(e.r + col0 + j);
+            const float x = fmaf(e.wscale, acc[j], __ldg(e.bias0 + col0 + j));
+            const RngAddr g{e.k0, e.k1, (uint32_t)row + e.row_offset, (uint32_t)(col0 + j), e.tick, e.stream & 0xFFu};
+            k = nb_draw_fast(x, r, __fdividef(1e-6f, r), u[j], e.pshift, e.mu_inv_max, g);
+        }
+        hi[j] = (k >= 256.0f) ? floorf(k * (1.0f / 256.0f)) * 256.0f : 0.0f;
+        lo[j] = k - hi[j];
+    }
+    const int64_t i = row * e.out.ld + col0;
+    if (nvalid == 4) {
+        *reinterpret_cast<uint2*>(e.out.p0 + i) = make_uint2(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));
+        *reinterpret_cast<uint2*>(e.out.p1 + i) = make_uint2(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]));
+    } else {
+        for (int j = 0; j < nvalid; ++j) {
+            e.out.p0[i + j] = __float2bfloat16_rn(lo[j]);
+            e.out.p1[i + j] = __float2bfloat16_rn(hi[j]);
+        }
+    }
+}
+
+__device__ __forceinline__ void epi_bern4(const EpiParams& e, int64_t row, int64_t col0, const float (&acc)[4], int nvalid) {
+    const uint4 w = philox_group(e, (uint32_t)row, (uint32_t)(col0 >> 2));
+    const float u[4] = {u23(w.x), u23(w.y), u23(w.z), u23(w.w)};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float b = 0.0f;
+        if (j < nvalid) {
+            b = __ldg(e.bias0 + col0 + j);
+            if (e.bias1) b += __ldg(e.bias1 + col0 + j);
+        }
+        o[j] = (j < nvalid) ? bern_draw_fast(e.factor * fmaf(e.wscale, acc[j], b), u[j]) : 0.0f;
+    }
+    const int64_t i = row * e.out.ld + col0;
+    if (nvalid == 4) {
+        *reinterpret_cast<uint2*>(e.out.p0 + i) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+    } else {
+        for (int j = 0; j < nvalid; ++j) e.out.p0[i + j] = __float2bfloat16_rn(o[j]);
+    }
+}
+
 }  // namespace scdbm

@@ -26,7 +26,7 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
 
 struct TcContext {
     PFN_tmapEncodeTiled encode = nullptr;
-    bool attr_set[4] = {false, false, false, false};
+    bool attr_set[6] = {false, false, false, false, false, false};
 };
 
 struct TcOperandPlanes {
@@ -133,17 +133,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------ kernel
-template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant__ TcMaps maps, const TcParams p) {
+// EK: epilogue class -- 0 generic (all modes, accurate math, explicit uniforms), 1 Philox-fed NB draw
+// (fast math), 2 Philox-fed Bernoulli draw (fast math).  Separate instantiations keep each kernel's
+// code small enough for the instruction cache.
+template <int BN, int EK>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
     constexpr int NS = TC_EPW / 4;       // column slices per tile
     constexpr int CW = BN / NS;          // columns per epilogue warp per tile (16 or 32)
     constexpr int B_TILE = BN * TC_BK * 2;
     constexpr uint32_t TMEM_COLS = 2 * BN;
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     static_assert(CW == 16 || CW == 32, "epilogue slice must be 16 or 32 columns");
+    (void)tmem_ld16;
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_tfull[2], bar_tempty[2];
@@ -242,33 +251,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
             mbar_wait(smem_u32(&bar_tfull[astage]), aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(astage * BN + slice * CW);
-            uint32_t r[CW];
-            if constexpr (CW == 16) {
-                tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-            } else {
-                tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-                tmem_ld16(taddr + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+            const int64_t row = m0 + q * 32 + lane;
+            float rowsum = 0.0f;
+            // one 4-column group at a time straight out of TMEM: a single copy of the epilogue body
+#pragma unroll 1
+            for (int g = 0; g < CW / 4; ++g) {
+                uint32_t r[4];
+                tmem_ld4(taddr + g * 4, r);          // warp-collective: outside any row/column predicate
+                tmem_wait_ld();
+                const int64_t col0 = n0 + slice * CW + g * 4;
+                const int nvalid = (int)max((int64_t)0, min((int64_t)4, p.N - col0));
+                if (row < p.M && nvalid > 0) {
+                    const float acc[4] = {__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3])};
+                    if constexpr (EK == 1) epi_nb_draw4(p.epi, row, col0, acc, nvalid);
+                    else if constexpr (EK == 2) epi_bern4(p.epi, row, col0, acc, nvalid);
+                    else rowsum += epi_apply4(p.epi, row, col0, acc, nvalid, delta_local);
+                }
             }
-            tmem_wait_ld();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[astage]));   // TMEM stage can be overwritten
             if (++astage == 2) { astage = 0; aphase ^= 1u; }
-
-            const int64_t row = m0 + q * 32 + lane;
-            float rowsum = 0.0f;
-            if (row < p.M) {
-#pragma unroll
-                for (int g = 0; g < CW / 4; ++g) {
-                    const int64_t col0 = n0 + slice * CW + g * 4;
-                    const int nvalid = (int)max((int64_t)0, min((int64_t)4, p.N - col0));
-                    if (nvalid > 0) {
-                        const float acc[4] = {__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
-                                              __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3])};
-                        rowsum += epi_apply4(p.epi, row, col0, acc, nvalid, delta_local);
-                    }
-                }
-                if (p.epi.mode == EPI_AIS_RATIO) atomicAdd(&p.epi.logw[row], (double)rowsum);
+            if constexpr (EK == 0) {
+                if (p.epi.mode == EPI_AIS_RATIO && row < p.M) atomicAdd(&p.epi.logw[row], (double)rowsum);
             }
         }
         if (p.epi.prev.p0 && p.epi.delta_bits) {
@@ -306,19 +311,20 @@ inline bool tc_supported(const GemmArgs& g, int nsrc) {
 inline bool tc_grad_supported(const TcGradArgs&) { return false; }
 inline cudaError_t launch_grad_tc(TcContext&, const TcGradArgs&, int, cudaStream_t) { return cudaErrorNotSupported; }
 
-template <int BN>
-inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, int num_sms, cudaStream_t stream, int slot) {
+template <int BN, int EK>
+inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, int num_sms, cudaStream_t stream) {
+    const int slot = (BN == 64 ? 0 : 3) + EK;
     constexpr int B_TILE = BN * TC_BK * 2;
     p.stage_bytes = 2 * TC_A_TILE + 2 * B_TILE;
     p.stages = std::min(TC_MAX_STAGES, TC_SMEM_BUDGET / p.stage_bytes);
     const int smem = p.stages * p.stage_bytes + 1024;
     if (!t.attr_set[slot]) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024);
         if (e != cudaSuccess) return e;
         t.attr_set[slot] = true;
     }
     const int grid = std::min(p.m_tiles * p.n_tiles, num_sms);
-    k_gemm_tc<BN><<<grid, TC_THREADS, smem, stream>>>(maps, p);
+    k_gemm_tc<BN, EK><<<grid, TC_THREADS, smem, stream>>>(maps, p);
     return cudaGetLastError();
 }
 
@@ -348,7 +354,21 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
         if (!ok) return cudaErrorInvalidValue;
     }
     if (nsrc == 1) { maps.a[1][0] = maps.a[0][0]; maps.a[1][1] = maps.a[0][1]; maps.b[1][0] = maps.b[0][0]; maps.b[1][1] = maps.b[0][1]; }
-    return BN == 64 ? tc_launch_bn<64>(t, maps, p, num_sms, stream, 0) : tc_launch_bn<128>(t, maps, p, num_sms, stream, 1);
+    // epilogue class: the fast sampling kernels need Philox-fed draws into the canonical plane layout
+    const EpiParams& e = g.epi;
+    int ek = 0;
+    if (!e.uniforms && !e.addend && !e.prev.p0) {
+        if (e.mode == EPI_NB_DRAW && e.factor == 1.0f && e.bias0 && !e.bias1 && e.out.p1 && !e.out.f && e.out.kind == MAT_COUNT) ek = 1;
+        if (e.mode == EPI_SIGM_BERN && e.bias0 && !e.out.p1 && !e.out.f) ek = 2;
+    }
+    if (BN == 64) {
+        if (ek == 1) return tc_launch_bn<64, 1>(t, maps, p, num_sms, stream);
+        if (ek == 2) return tc_launch_bn<64, 2>(t, maps, p, num_sms, stream);
+        return tc_launch_bn<64, 0>(t, maps, p, num_sms, stream);
+    }
+    if (ek == 1) return tc_launch_bn<128, 1>(t, maps, p, num_sms, stream);
+    if (ek == 2) return tc_launch_bn<128, 2>(t, maps, p, num_sms, stream);
+    return tc_launch_bn<128, 0>(t, maps, p, num_sms, stream);
 }
 
 }  // namespace scdbm

@@ -43,7 +43,7 @@ struct RngAddr {
     uint32_t k0, k1, row, col, tick, layer;
 };
 
-__device__ inline float gamma_mt(float a, const RngAddr& g) {
+__device__ __noinline__ float gamma_mt(float a, const RngAddr& g) {
     const bool small = a < 1.0f;
     const float d = (small ? a + 1.0f : a) - (1.0f / 3.0f);
     const float c = 1.0f / sqrtf(9.0f * d);
@@ -59,7 +59,7 @@ __device__ inline float gamma_mt(float a, const RngAddr& g) {
     return a;
 }
 
-__device__ inline float poisson_draw(float lam, const RngAddr& g) {
+__device__ __noinline__ float poisson_draw(float lam, const RngAddr& g) {
     if (lam < 10.0f) {
         const uint4 w = philox_element(g.k0, g.k1, g.row, g.col, g.tick, stream_id(g.layer, P_POIS, 0));
         return invert_pmf(u23(w.x), expf(-lam), [=](float k) { return lam / (k + 1.0f); });
@@ -88,6 +88,59 @@ __device__ __forceinline__ float nb_draw(float mu, float r, float u, float pshif
     const float p = r / (mu + r) - pshift;
     const float lam = gamma_mt(r, g) * ((1.0f - p) / p);
     return fminf(poisson_draw(lam, g), KMAX_F);
+}
+
+// ---- fast-math variants used by the tensor-core engine's sampling epilogues (Philox-fed draws).
+// Same algorithm and the same uniforms as above; MUFU ex2/lg2/rcp approximations instead of the
+// IEEE library calls.  A draw can differ from the accurate path only where u sits within ~1e-6
+// (relative) of a CDF step.
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __noinline__ float nb_draw_slow(float x, float r, float pshift, RngAddr g) {
+    const float mu = nb_mean(x, r);
+    const float p = r / (mu + r) - pshift;
+    const float lam = gamma_mt(r, g) * ((1.0f - p) / p);
+    return fminf(poisson_draw(lam, g), KMAX_F);
+}
+
+// x: pre-activation (< 0), r: inverse dispersion, c = 1e-6 / r, u: uniform
+__device__ __forceinline__ float nb_draw_fast(float x, float r, float c, float u, float pshift, float mu_inv_max,
+                                              const RngAddr& g) {
+    const float E = fast_ex2(x * 1.4426950408889634f);
+    float om = 1.0f - E;                         // 1 - e^x
+    if (x > -0.125f) om = -expm1f(x);            // cancellation region (large means)
+    // mu = r E / om + 1e-6 > mu_inv_max  <=>  r E > (mu_inv_max - 1e-6) om
+    if (r * E > (mu_inv_max - 1e-6f) * om) return nb_draw_slow(x, r, pshift, g);
+    // p = r / (mu + r) = om / (1 + c om)
+    const float p = om * fast_rcp(fmaf(c, om, 1.0f)) - pshift;
+    const float q = 1.0f - p;
+    float P = fast_ex2(r * fast_lg2(p));
+    float k = 0.0f;
+    while (u >= P && P > PMIN_F && k < KMAX_F) {
+        u -= P;
+        P *= q * (k + r) * fast_rcp(k + 1.0f);
+        k += 1.0f;
+    }
+    return k;
+}
+
+// u < sigm(x)  <=>  u (1 + e^-x) < 1
+__device__ __forceinline__ float bern_draw_fast(float x, float u) {
+    return (u * (1.0f + fast_ex2(-x * 1.4426950408889634f)) < 1.0f) ? 1.0f : 0.0f;
 }
 
 }  // namespace scdbm
