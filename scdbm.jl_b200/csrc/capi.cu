@@ -81,6 +81,7 @@ struct Layer {
     int V = 0, H = 0, kind = SCDBM_VIS_BERNOULLI;
     float *W = nullptr, *a = nullptr, *b = nullptr, *r = nullptr;
     __nv_bfloat16 *w0 = nullptr, *w1 = nullptr, *t0 = nullptr, *t1 = nullptr;  // W[V x ldh], Wt[H x ldv] hi/lo
+    float4* nbc = nullptr;  // NB layer: per-gene {a, r, 1e-6/r, r-1}
     int64_t ldh = 0, ldv = 0;
 };
 
@@ -97,7 +98,7 @@ static void model_free(scdbm_model* m) {
     cudaStreamSynchronize(m->ctx->stream);
     for (auto& L : m->L) {
         cudaFree(L.W); cudaFree(L.a); cudaFree(L.b); cudaFree(L.r);
-        cudaFree(L.w0); cudaFree(L.w1); cudaFree(L.t0); cudaFree(L.t1);
+        cudaFree(L.w0); cudaFree(L.w1); cudaFree(L.t0); cudaFree(L.t1); cudaFree(L.nbc);
     }
     scdbm_ctx* c = m->ctx;
     delete m;
@@ -297,6 +298,12 @@ static void upload_uniforms(scdbm_ctx* ctx, const double* u, int64_t ldu, int64_
     cudaFree(stage);
 }
 
+static void refresh_nbc(scdbm_ctx* ctx, Layer& L) {
+    if (!L.nbc) return;
+    k_refresh_nbc<<<(L.V + 255) / 256, 256, 0, ctx->stream>>>(L.a, L.r, L.nbc, L.V);
+    ctx->launches++;
+}
+
 static void refresh_operands(scdbm_ctx* ctx, Layer& L) {
     dim3 grid((L.V + 31) / 32, (L.H + 31) / 32), block(32, 8);
     k_refresh_operands<<<grid, block, 0, ctx->stream>>>(L.W, L.V, L.H, L.w0, L.w1, L.ldh, L.t0, L.t1, L.ldv);
@@ -348,6 +355,7 @@ static void op_visible(scdbm_model* m, int l, const MatView& h, const MatView& o
     if (what == SCDBM_OUT_INPUT) e.factor = 1.0f;
     e.wscale = d.wscale;
     e.r = L.r;
+    e.nbc = L.nbc;
     if (d.pshift >= 0.0f) e.pshift = d.pshift;
     e.stream = d.stream; e.tick = d.tick; e.row_offset = d.row_offset;
     e.uniforms = d.uniforms; e.ldu = d.ldu;
@@ -500,6 +508,7 @@ int32_t scdbm_model_create(scdbm_ctx* c, int32_t nrbms, const int32_t* units, in
         CK(cudaMalloc(&L.a, (size_t)L.V * sizeof(float)));
         CK(cudaMalloc(&L.b, (size_t)L.H * sizeof(float)));
         CK(cudaMalloc(&L.r, (size_t)L.V * sizeof(float)));
+        if (L.kind == SCDBM_VIS_NEGBIN) CK(cudaMalloc(&L.nbc, (size_t)L.V * sizeof(float4)));
         CK(cudaMemsetAsync(L.W, 0, (size_t)L.V * L.H * sizeof(float), c->stream));
         CK(cudaMemsetAsync(L.a, 0, (size_t)L.V * sizeof(float), c->stream));
         CK(cudaMemsetAsync(L.b, 0, (size_t)L.H * sizeof(float), c->stream));
@@ -509,6 +518,7 @@ int32_t scdbm_model_create(scdbm_ctx* c, int32_t nrbms, const int32_t* units, in
         CK(cudaMalloc(&L.t0, tb)); CK(cudaMalloc(&L.t1, tb));
         CK(cudaMemsetAsync(L.w0, 0, wb, c->stream)); CK(cudaMemsetAsync(L.w1, 0, wb, c->stream));
         CK(cudaMemsetAsync(L.t0, 0, tb, c->stream)); CK(cudaMemsetAsync(L.t1, 0, tb, c->stream));
+        refresh_nbc(c, L);
     }
     *out = m;
     API_END
@@ -560,6 +570,7 @@ int32_t scdbm_model_set_layer(scdbm_model* m, int32_t l, const double* W, int64_
         REQUIRE(L.kind == SCDBM_VIS_NEGBIN, "inversedispersion given for a non-NB layer");
         up(L.r, r, L.V, "inversedispersion", true, false);
     }
+    refresh_nbc(m->ctx, L);
     API_END
 }
 
@@ -603,6 +614,7 @@ int32_t scdbm_model_copy_layer(scdbm_model* dst, int32_t dl, scdbm_model* src, i
     CK(cudaMemcpyAsync(D.b, S.b, (size_t)D.H * sizeof(float), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(D.r, S.r, (size_t)D.V * sizeof(float), cudaMemcpyDeviceToDevice, st));
     refresh_operands(dst->ctx, D);
+    refresh_nbc(dst->ctx, D);
     API_END
 }
 
@@ -1219,6 +1231,7 @@ static void update_layer(scdbm_model* m, scdbm_opt* o, int l, float lr) {
     CK(cudaGetLastError());
     c->launches += 3;
     refresh_operands(c, L);
+    refresh_nbc(c, L);
 }
 
 int32_t scdbm_update_parameters(scdbm_model* m, scdbm_opt* o, int32_t l, double lr) {

@@ -126,6 +126,12 @@ __global__ void k_colsum_final(const float* __restrict__ partial, int nslabs, in
     out[c] = (accumulate ? out[c] : 0.0f) + scale * tot;
 }
 
+// per-gene constants of the fast NB epilogue: {a, r, 1e-6/r, r-1}
+__global__ void k_refresh_nbc(const float* __restrict__ a, const float* __restrict__ r, float4* __restrict__ nbc, int V) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < V) nbc[i] = make_float4(a[i], r[i], 1e-6f / r[i], r[i] - 1.0f);
+}
+
 __global__ void k_fill_f32(float* p, int64_t n, float v) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }

@@ -132,19 +132,49 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 __device__ __forceinline__ void epi_nb_draw4(const EpiParams& e, int64_t row, int64_t col0, const float (&acc)[4], int nvalid) {
     const uint4 w = philox_group(e, (uint32_t)row, (uint32_t)(col0 >> 2));
-    const float u[4] = {u23(w.x), u23(w.y), u23(w.z), u23(w.w)};
+    float u[4] = {u23(w.x), u23(w.y), u23(w.z), u23(w.w)};
+    // phase 1 (straight-line, the 4 elements interleave): P0 = p^r, q, loop constants
+    float P[4], q[4], qr1[4], k[4];
+    unsigned slow = 0;
+    const float thr = e.mu_inv_max - 1e-6f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 c = __ldg(e.nbc + col0 + min(j, nvalid - 1));   // {a, r, 1e-6/r, r-1}
+        const float x = fmaf(e.wscale, acc[j], c.x);
+        const float E = fast_ex2(x * 1.4426950408889634f);
+        const float om = 1.0f - E;                                   // 1 - e^x
+        // mu = r E / om + 1e-6 > mu_inv_max  <=>  r E > (mu_inv_max - 1e-6) om ;  x -> 0-: cancellation
+        if (c.y * E > thr * om || x > -0.125f) slow |= 1u << j;
+        const float p = om * fast_rcp(fmaf(c.z, om, 1.0f)) - e.pshift;   // r/(mu+r) = om/(1 + (1e-6/r) om)
+        q[j] = 1.0f - p;
+        qr1[j] = q[j] * c.w;
+        P[j] = fast_ex2(c.y * fast_lg2(p));
+        k[j] = 0.0f;
+    }
+    // phase 2: chop-down inversion; P_{k+1} = P_k q (k+r)/(k+1) = P_k (q + q (r-1)/(k+1))
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j < nvalid) {
+            if (slow & (1u << j)) {
+                const float4 c = __ldg(e.nbc + col0 + j);
+                const RngAddr g{e.k0, e.k1, (uint32_t)row + e.row_offset, (uint32_t)(col0 + j), e.tick, e.stream & 0xFFu};
+                k[j] = nb_draw_slow(fmaf(e.wscale, acc[j], c.x), c.y, u[j], e.pshift, e.mu_inv_max, g);
+            } else {
+                float uu = u[j], PP = P[j], kk = 0.0f;
+                while (uu >= PP && PP > PMIN_F) {
+                    uu -= PP;
+                    kk += 1.0f;
+                    PP *= fmaf(qr1[j], fast_rcp(kk), q[j]);
+                }
+                k[j] = kk;
+            }
+        }
+    }
     float lo[4], hi[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        float k = 0.0f;
-        if (j < nvalid) {
-            const float r = __ldg(e.r + col0 + j);
-            const float x = fmaf(e.wscale, acc[j], __ldg(e.bias0 + col0 + j));
-            const RngAddr g{e.k0, e.k1, (uint32_t)row + e.row_offset, (uint32_t)(col0 + j), e.tick, e.stream & 0xFFu};
-            k = nb_draw_fast(x, r, __fdividef(1e-6f, r), u[j], e.pshift, e.mu_inv_max, g);
-        }
-        hi[j] = (k >= 256.0f) ? floorf(k * (1.0f / 256.0f)) * 256.0f : 0.0f;
-        lo[j] = k - hi[j];
+        hi[j] = (k[j] >= 256.0f) ? floorf(k[j] * (1.0f / 256.0f)) * 256.0f : 0.0f;
+        lo[j] = k[j] - hi[j];
     }
     const int64_t i = row * e.out.ld + col0;
     if (nvalid == 4) {

@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile % p.m_tiles) * TC_BM, n0 = (tile / p.m_tiles) * BN;
+                const int m0 = (tile / p.n_tiles) * TC_BM, n0 = (tile % p.n_tiles) * BN;   // n fastest: CTAs sharing an A tile run together (L2)
                 for (int s = 0; s < p.nsrc; ++s) {
                     const uint32_t tx = (uint32_t)(p.nA[s] * TC_A_TILE + 2 * B_TILE);
                     for (int kb = 0; kb < p.kblocks[s]; ++kb) {
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
         uint32_t aphase = 0;
         float delta_local = 0.0f;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int64_t m0 = (int64_t)(tile % p.m_tiles) * TC_BM, n0 = (int64_t)(tile / p.m_tiles) * BN;
+            const int64_t m0 = (int64_t)(tile / p.n_tiles) * TC_BM, n0 = (int64_t)(tile % p.n_tiles) * BN;
             mbar_wait(smem_u32(&bar_tfull[astage]), aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(astage * BN + slice * CW);
@@ -358,7 +358,7 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
     const EpiParams& e = g.epi;
     int ek = 0;
     if (!e.uniforms && !e.addend && !e.prev.p0) {
-        if (e.mode == EPI_NB_DRAW && e.factor == 1.0f && e.bias0 && !e.bias1 && e.out.p1 && !e.out.f && e.out.kind == MAT_COUNT) ek = 1;
+        if (e.mode == EPI_NB_DRAW && e.factor == 1.0f && e.nbc && !e.bias1 && e.out.p1 && !e.out.f && e.out.kind == MAT_COUNT) ek = 1;
         if (e.mode == EPI_SIGM_BERN && e.bias0 && !e.out.p1 && !e.out.f) ek = 2;
     }
     if (BN == 64) {

@@ -110,32 +110,9 @@ __device__ __forceinline__ float fast_rcp(float x) {
     return y;
 }
 
-__device__ __noinline__ float nb_draw_slow(float x, float r, float pshift, RngAddr g) {
-    const float mu = nb_mean(x, r);
-    const float p = r / (mu + r) - pshift;
-    const float lam = gamma_mt(r, g) * ((1.0f - p) / p);
-    return fminf(poisson_draw(lam, g), KMAX_F);
-}
-
-// x: pre-activation (< 0), r: inverse dispersion, c = 1e-6 / r, u: uniform
-__device__ __forceinline__ float nb_draw_fast(float x, float r, float c, float u, float pshift, float mu_inv_max,
-                                              const RngAddr& g) {
-    const float E = fast_ex2(x * 1.4426950408889634f);
-    float om = 1.0f - E;                         // 1 - e^x
-    if (x > -0.125f) om = -expm1f(x);            // cancellation region (large means)
-    // mu = r E / om + 1e-6 > mu_inv_max  <=>  r E > (mu_inv_max - 1e-6) om
-    if (r * E > (mu_inv_max - 1e-6f) * om) return nb_draw_slow(x, r, pshift, g);
-    // p = r / (mu + r) = om / (1 + c om)
-    const float p = om * fast_rcp(fmaf(c, om, 1.0f)) - pshift;
-    const float q = 1.0f - p;
-    float P = fast_ex2(r * fast_lg2(p));
-    float k = 0.0f;
-    while (u >= P && P > PMIN_F && k < KMAX_F) {
-        u -= P;
-        P *= q * (k + r) * fast_rcp(k + 1.0f);
-        k += 1.0f;
-    }
-    return k;
+// rare path of the fast epilogue: large means (gamma-Poisson) or x -> 0- (1 - e^x cancels); accurate math
+__device__ __noinline__ float nb_draw_slow(float x, float r, float u, float pshift, float mu_inv_max, RngAddr g) {
+    return nb_draw(nb_mean(x, r), r, u, pshift, mu_inv_max, g);
 }
 
 // u < sigm(x)  <=>  u (1 + e^-x) < 1
