@@ -160,11 +160,14 @@ __device__ __forceinline__ void epi_nb_draw4(const EpiParams& e, int64_t row, in
                 const RngAddr g{e.k0, e.k1, (uint32_t)row + e.row_offset, (uint32_t)(col0 + j), e.tick, e.stream & 0xFFu};
                 k[j] = nb_draw_slow(fmaf(e.wscale, acc[j], c.x), c.y, u[j], e.pshift, e.mu_inv_max, g);
             } else {
-                float uu = u[j], PP = P[j], kk = 0.0f;
+                // 1/(k+1) for the next step is issued one iteration ahead, off the u/P dependency chain
+                float uu = u[j], PP = P[j], kk = 0.0f, rk = 1.0f;
                 while (uu >= PP && PP > PMIN_F) {
                     uu -= PP;
                     kk += 1.0f;
-                    PP *= fmaf(qr1[j], fast_rcp(kk), q[j]);
+                    const float ratio = fmaf(qr1[j], rk, q[j]);
+                    rk = fast_rcp(kk + 1.0f);
+                    PP *= ratio;
                 }
                 k[j] = kk;
             }

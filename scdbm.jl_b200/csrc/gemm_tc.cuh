@@ -97,6 +97,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (!done && ++spins > (1u << 26)) __trap();  // never hang the GPU: a protocol bug becomes a launch error
     } while (!done);
 }
+// service warps (TMA producer, MMA issuer) share an SM sub-partition with epilogue warps: back off
+// between polls so that their spin does not take issue slots from the sampler
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(200);
+        if (++spins > (1u << 24)) __trap();
+    }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
@@ -194,7 +212,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
                 for (int s = 0; s < p.nsrc; ++s) {
                     const uint32_t tx = (uint32_t)(p.nA[s] * TC_A_TILE + 2 * B_TILE);
                     for (int kb = 0; kb < p.kblocks[s]; ++kb) {
-                        mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+                        mbar_wait_backoff(smem_u32(&bar_empty[stage]), phase ^ 1u);
                         const uint32_t full = smem_u32(&bar_full[stage]);
                         const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
                         mbar_expect_tx(full, tx);
@@ -212,13 +230,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
             int stage = 0, astage = 0;
             uint32_t phase = 0, aphase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(smem_u32(&bar_tempty[astage]), aphase ^ 1u);
+                mbar_wait_backoff(smem_u32(&bar_tempty[astage]), aphase ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)astage * BN;
                 uint32_t accumulate = 0;
                 for (int s = 0; s < p.nsrc; ++s) {
                     for (int kb = 0; kb < p.kblocks[s]; ++kb) {
-                        mbar_wait(smem_u32(&bar_full[stage]), phase);
+                        mbar_wait_backoff(smem_u32(&bar_full[stage]), phase);
                         tc_fence_after();
                         const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
                         const uint32_t sb = sa + 2 * TC_A_TILE;
