@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""Data-parallel DBM PCD (`traindbm!`, src/dbmtraining.jl:287-297) over N GPUs:
+data rows and persistent particles are sharded by rank; per step one NCCL
+allreduce(sum) of the contiguous gradient block {dW_l, da_l, db_l}.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29511 examples/dp_pcd.py --cells 20000 --units 2000 256 64 --steps 5 [--check]
+
+--check: rank 0 also runs the same steps on one GPU over all rows / particles and
+compares the parameters (fp32 reduction-order tolerance).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+from bench import make_model  # noqa: E402
+
+
+class NcclAllreduce:
+    """allreduce hook for pkg.traindbm_: wraps the library's gradient buffer (raw device pointer)
+    as a torch tensor and sums it over ranks with NCCL."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bytes = 0
+
+    def global_counts(self, nrows, nparticles):
+        t = torch.tensor([nrows, nparticles], dtype=torch.float64, device=self.device)
+        dist.all_reduce(t)
+        return float(t[0].item()), float(t[1].item())
+
+    def __call__(self, ptr, nfloats):
+        class _Arr:  # __cuda_array_interface__ view of the library-owned buffer
+            __cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+        t = torch.as_tensor(_Arr(), device=self.device)
+        dist.all_reduce(t)
+        torch.cuda.current_stream().synchronize()
+        self.bytes += nfloats * 4
+
+
+def counts(n, V, seed):
+    g = np.random.default_rng(seed)
+    m = np.clip(np.exp(g.normal(-1.5, 1.5, V)), 1e-3, 50.0)
+    s = np.exp(g.normal(0.0, 0.3, n))
+    lam = g.gamma(0.5, s[:, None] * m[None, :] / 0.5)
+    x = g.poisson(lam).astype(np.float64)
+    x[0, :] += 1.0
+    return np.minimum(x, 60000.0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cells", type=int, default=20000)
+    ap.add_argument("--units", type=int, nargs="+", default=[2000, 256, 64])
+    ap.add_argument("--particles", type=int, default=4096)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--check", action="store_true")
+    a = ap.parse_args()
+    world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    pkg = entry.load_package()
+    layers = make_model(a.units)
+    host = [pkg.NegativeBinomialBernoulliRBM(**layers[0])] + [pkg.BernoulliRBM(**l) for l in layers[1:]]
+    x = counts(a.cells, a.units[0], seed=4)
+    rows = np.array_split(np.arange(a.cells), world)[rank]
+    pshard = pkg.mostevenbatches(a.particles, world)
+    poff = sum(pshard[:rank])
+
+    ctx = pkg.Context(local, 20261019)
+    dm = pkg.DeviceModel.from_host(host, ctx)
+    xm = pkg.Mat.from_host(ctx, x[rows], pkg.MAT_COUNT)
+    p = pkg.DeviceParticles(dm, pshard[rank], row_offset=poff).init(False)
+    hook = NcclAllreduce(dev)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ctx.timer_start()
+    pkg.traindbm_(dm, xm, epochs=a.steps, learningrate=1e-3, particles=p, allreduce=hook, device=True, ctx=ctx)
+    ms = ctx.timer_stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res = {"n_gpus": world, "cells": a.cells, "units": a.units, "particles": a.particles, "steps": a.steps,
+           "ms_per_step": float(t.item()) / a.steps, "pcd_steps_per_sec": a.steps / (float(t.item()) * 1e-3),
+           "allreduce_bytes_per_step": hook.bytes // a.steps}
+    if a.check and rank == 0:
+        ctx1 = pkg.Context(local, 20261019)
+        dm1 = pkg.DeviceModel.from_host(host, ctx1)
+        x1 = pkg.Mat.from_host(ctx1, x, pkg.MAT_COUNT)
+        p1 = pkg.DeviceParticles(dm1, a.particles).init(False)
+        pkg.traindbm_(dm1, x1, epochs=a.steps, learningrate=1e-3, particles=p1, device=True, ctx=ctx1)
+        errs = []
+        for l in range(len(host)):
+            g, r = dm.get_layer(l), dm1.get_layer(l)
+            d0 = np.abs(r.weights - host[l].weights).max()
+            errs.append(float(np.abs(g.weights - r.weights).max() / max(d0, 1e-30)))
+        res["max_update_mismatch_vs_1gpu"] = errs
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
