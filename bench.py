@@ -206,12 +206,74 @@ def run_ours(args):
         "gpu_launches": launches, "tc_launches": tc_launches,
         "e2e": e2e, "roofline": roofline, "clocks": sampler.summary(),
     }
+    if rank == 0 and world == 1 and not args.no_training:
+        line["training"] = training_metrics(pkg, ctx, with_cpu=not args.no_cpu_baseline)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(layers, burnin=5, chains=args.cpu_chains, workers=os.cpu_count() or 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---------------------------------------- secondary metric: CD / PCD epochs per second
+def synth_counts(n, V, seed, r=0.5):
+    g = np.random.default_rng(seed)
+    m = np.clip(np.exp(g.normal(-1.5, 1.5, V)), 1e-3, 50.0)
+    s = np.exp(g.normal(0.0, 0.3, n))
+    x = g.poisson(g.gamma(r, s[:, None] * m[None, :] / r)).astype(np.float64)
+    x[0, :] += 1.0            # no all-zero gene (log(0) in initrbm)
+    return x
+
+
+def training_metrics(pkg, ctx, with_cpu=True):
+    """BASELINE.json's second metric, "PCD epochs/sec", on configs C1 and C2 (reported beside the
+    headline; timed with CUDA events, data resident)."""
+    out = {}
+    # C1: NB-Bernoulli RBM, fitrbm CD-1, 500 cells x 1000 genes, 128 hidden, batchsize 100
+    x1 = synth_counts(500, 1000, seed=1)
+    xm = pkg.Mat.from_host(ctx, x1, pkg.MAT_COUNT)
+    m = pkg.DeviceModel(ctx, [1000, 128], pkg.VIS_NEGBIN)
+    m.init_layer(0, xm, seed=SEED)
+    tr = pkg.RBMTrainer(m, 100, pcd=False)
+    for _ in range(3):
+        pkg.trainrbm_(m, xm, tr, 1e-4, 1)
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(20):
+        pkg.trainrbm_(m, xm, tr, 1e-4, 1)
+    ms = ctx.timer_stop()
+    out["C1_rbm_cd1_epochs_per_sec"] = 20 / (ms * 1e-3)
+    # C2: DBM 2000 -> 256 -> 64, 5000 cells, full-batch PCD step (one traindbm! "epoch"), 100 particles
+    x2 = synth_counts(5000, 2000, seed=2)
+    layers = make_model()
+    dm = pkg.DeviceModel.from_host([pkg.NegativeBinomialBernoulliRBM(**layers[0]), pkg.BernoulliRBM(**layers[1])], ctx)
+    x2m = pkg.Mat.from_host(ctx, x2, pkg.MAT_COUNT)
+    p = pkg.DeviceParticles(dm, 100).init(False)
+    pkg.traindbm_(dm, x2m, epochs=3, particles=p, learningrate=1e-4, device=True, ctx=ctx)
+    ctx.sync()
+    ctx.timer_start()
+    pkg.traindbm_(dm, x2m, epochs=20, particles=p, learningrate=1e-4, device=True, ctx=ctx)
+    ms = ctx.timer_stop()
+    out["C2_dbm_pcd_epochs_per_sec"] = 20 / (ms * 1e-3)
+    if with_cpu:
+        from oracle import model as om, philox as px
+        rng = px.Rng(SEED)
+        rbm = om.initrbm(x1, 128, rng, "nb")
+        otr = om.RBMTrainer(rbm, 100, rng, pcd=False)
+        om.trainrbm(rbm, x1, otr, 1e-4)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            om.trainrbm(rbm, x1, otr, 1e-4)
+        out["C1_cpu_port_epochs_per_sec"] = 5 / (time.perf_counter() - t0)
+        dbm = [om.NegativeBinomialBernoulliRBM(**layers[0]), om.BernoulliRBM(**layers[1])]
+        parts = om.initparticles(dbm, 100, rng)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            om.traindbm_step(dbm, x2, parts, rng, 1e-4)
+        out["C2_cpu_port_epochs_per_sec"] = 2 / (time.perf_counter() - t0)
+        out["cpu_note"] = "oracle (NumPy/OpenBLAS, all BLAS threads), not Julia"
+    return out
 
 
 # --------------------------------------------------------- CPU baseline arm
@@ -281,6 +343,7 @@ def main():
     ap.add_argument("--burnin", type=int, default=50)
     ap.add_argument("--cpu-chains", type=int, default=1500, help="chains per worker in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-training", action="store_true", help="skip the secondary CD/PCD epochs/sec metrics")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
