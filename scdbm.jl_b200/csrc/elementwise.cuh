@@ -126,10 +126,29 @@ __global__ void k_colsum_final(const float* __restrict__ partial, int nslabs, in
     out[c] = (accumulate ? out[c] : 0.0f) + scale * tot;
 }
 
-// per-gene constants of the fast NB epilogue: {a, r, 1e-6/r, r-1}
-__global__ void k_refresh_nbc(const float* __restrict__ a, const float* __restrict__ r, float4* __restrict__ nbc, int V) {
+// per-gene constants of the fast NB epilogue: {a, r, 1e-6/r, r-1}, and a lower bound L on the zero
+// probability P0 = p^r valid for every hidden state h in [0,1]^H and every temperature in [0,1]:
+// x = a + t * sum_h W h <= a + sum_h max(W, 0) =: xmax, and P0 is decreasing in x.  (The reference
+// clamps W <= 0 for NB layers, src/optimizers.jl:482, so xmax = a there.)  u < L  =>  the draw is 0.
+// The shortcut only holds where the draw is the single-uniform inversion: a gene whose mean can exceed
+// mu_inv_max (gamma-Poisson branch, which does not consume u) gets L = 0.
+__global__ void k_refresh_nbc(const float* __restrict__ a, const float* __restrict__ r, const float* __restrict__ W, int V,
+                              int H, float mu_inv_max, float4* __restrict__ nbc, float* __restrict__ nbL) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < V) nbc[i] = make_float4(a[i], r[i], 1e-6f / r[i], r[i] - 1.0f);
+    if (i >= V) return;
+    const float rr = r[i], c = 1e-6f / rr;
+    nbc[i] = make_float4(a[i], rr, c, rr - 1.0f);
+    float pos = 0.0f;
+    for (int h = 0; h < H; ++h) pos += fmaxf(W[(int64_t)i * H + h], 0.0f);
+    const float xmax = a[i] + pos;
+    float L = 0.0f;
+    if (xmax < 0.0f) {
+        const float om = -expm1f(xmax);
+        const float p = om / (1.0f + c * om) - 1e-6f;          // largest pshift in use
+        const float mu_max = rr * expf(xmax) / om + 1e-6f;      // the mean is increasing in x
+        if (p > 0.0f && mu_max < 0.99f * mu_inv_max) L = expf(rr * logf(p)) * (1.0f - 2e-5f);   // margin: fast-math P0 of pass B
+    }
+    nbL[i] = L;
 }
 
 __global__ void k_fill_f32(float* p, int64_t n, float v) {

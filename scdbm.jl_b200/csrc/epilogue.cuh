@@ -191,6 +191,33 @@ __device__ __forceinline__ void epi_nb_draw4(const EpiParams& e, int64_t row, in
     }
 }
 
+// ---- two-pass NB epilogue (tensor-core engine).  Pass B: one queued element per lane.
+__device__ __forceinline__ float nb_entry_draw(const EpiParams& e, float acc, float u, uint32_t grow, uint32_t col) {
+    const float4 c = __ldg(e.nbc + col);                             // {a, r, 1e-6/r, r-1}
+    const float x = fmaf(e.wscale, acc, c.x);
+    const float E = fast_ex2(x * 1.4426950408889634f);
+    float om = 1.0f - E;
+    // x -> 0-: 1 - e^x cancels; -expm1(x) = -x (1 + x/2 + x^2/6 + x^3/24 + x^4/120 + x^5/720), |err| < 2e-9 on (-1/8, 0)
+    if (x > -0.125f)
+        om = -x * fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, 1.0f / 720.0f, 1.0f / 120.0f), 1.0f / 24.0f), 1.0f / 6.0f), 0.5f), 1.0f);
+    if (c.y * E > (e.mu_inv_max - 1e-6f) * om) {                     // mean above mu_inv_max: gamma-Poisson, out of line
+        const RngAddr g{e.k0, e.k1, grow, col, e.tick, e.stream & 0xFFu};
+        return nb_draw_slow(x, c.y, u, e.pshift, e.mu_inv_max, g);
+    }
+    const float p = om * fast_rcp(fmaf(c.z, om, 1.0f)) - e.pshift;
+    const float q = 1.0f - p, qr1 = q * c.w;
+    float P = fast_ex2(c.y * fast_lg2(p));
+    float k = 0.0f, rk = 1.0f;
+    while (u >= P && P > PMIN_F) {
+        u -= P;
+        k += 1.0f;
+        const float ratio = fmaf(qr1, rk, q);
+        rk = fast_rcp(k + 1.0f);
+        P *= ratio;
+    }
+    return k;
+}
+
 __device__ __forceinline__ void epi_bern4(const EpiParams& e, int64_t row, int64_t col0, const float (&acc)[4], int nvalid) {
     const uint4 w = philox_group(e, (uint32_t)row, (uint32_t)(col0 >> 2));
     const float u[4] = {u23(w.x), u23(w.y), u23(w.z), u23(w.w)};

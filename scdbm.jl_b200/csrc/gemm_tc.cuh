@@ -26,7 +26,7 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
 
 struct TcContext {
     PFN_tmapEncodeTiled encode = nullptr;
-    bool attr_set[6] = {false, false, false, false, false, false};
+    bool attr_set[9] = {};
 };
 
 struct TcOperandPlanes {
@@ -42,9 +42,14 @@ struct TcGradArgs {
     int64_t V, H;
 };
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_EPW = 16, TC_THREADS = 32 * (4 + TC_EPW);
+constexpr int TC_BM = 128, TC_BK = 64;
 constexpr int TC_A_TILE = TC_BM * TC_BK * 2;  // 16 KB
 constexpr int TC_MAX_STAGES = 8;
+// two-pass NB epilogue: queue entries per epilogue warp ({acc, u, pos} = 12 B each), sized to the shared
+// memory left beside the GEMM stages
+__host__ __device__ constexpr int tc_qcap(int epw) { return epw > 16 ? 256 : 384; }
+// per epilogue warp: queue (12 B per entry) + a 32 x CW bf16 staging tile of the lo count plane
+__host__ __device__ constexpr int tc_epi_smem(int epw, int cw) { return tc_qcap(epw) * 12 + 32 * cw * 2; }
 constexpr int TC_SMEM_BUDGET = 200 * 1024;
 
 struct alignas(64) TcMaps {
@@ -60,6 +65,9 @@ struct TcParams {
     int64_t M, N;
     int32_t m_tiles, n_tiles;
     int32_t stages, stage_bytes;
+    int32_t a_tiles;      // A-plane tiles reserved per stage (1 or 2)
+    int32_t sched;        // 1: a CTA owns whole m-tiles and walks all n-tiles (balanced over genes, A re-used
+                          //    back-to-back); 0: flat round-robin over (m, n) tiles, n fastest (few m-tiles)
     EpiParams epi;
 };
 
@@ -111,8 +119,24 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) break;
-        __nanosleep(200);
-        if (++spins > (1u << 24)) __trap();
+        __nanosleep(1000);
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_wait_epi(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(100);
+        if (++spins > (1u << 25)) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
@@ -158,16 +182,29 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// tile schedule shared by the three warp roles: it = 0, 1, ... -> flat tile id m * n_tiles + n, or -1 at the end
+__device__ __forceinline__ int tc_tile(const TcParams& p, int it) {
+    if (p.sched) {
+        const int m = (int)blockIdx.x + (it / p.n_tiles) * (int)gridDim.x;
+        return m < p.m_tiles ? m * p.n_tiles + it % p.n_tiles : -1;
+    }
+    const int t = (int)blockIdx.x + it * (int)gridDim.x;
+    return t < p.m_tiles * p.n_tiles ? t : -1;
+}
+
 // ------------------------------------------------------------------ kernel
 // EK: epilogue class -- 0 generic (all modes, accurate math, explicit uniforms), 1 Philox-fed NB draw
 // (fast math), 2 Philox-fed Bernoulli draw (fast math).  Separate instantiations keep each kernel's
 // code small enough for the instruction cache.
-template <int BN, int EK>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
-    constexpr int NS = TC_EPW / 4;       // column slices per tile
+// EPW: number of epilogue warps (4 per column slice).  The sampling epilogue is latency-bound, so the NB
+// kernel runs 24 epilogue warps on 192-column tiles; the others 16 warps on 64/128-column tiles.
+template <int BN, int EK, int EPW>
+__global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
+    constexpr int NS = EPW / 4;          // column slices per tile
     constexpr int CW = BN / NS;          // columns per epilogue warp per tile (16 or 32)
     constexpr int B_TILE = BN * TC_BK * 2;
-    constexpr uint32_t TMEM_COLS = 2 * BN;
+    constexpr int ASTAGES = 2;    // TMEM accumulator stages (4 x 128 = all 512 columns; 4 x 64 = 256)
+    constexpr uint32_t TMEM_COLS = (ASTAGES * BN <= 128) ? 128 : (ASTAGES * BN <= 256) ? 256 : 512;
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     static_assert(CW == 16 || CW == 32, "epilogue slice must be 16 or 32 columns");
     (void)tmem_ld16;
@@ -178,16 +215,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = p.m_tiles * p.n_tiles;
 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < p.stages; ++i) {
             mbar_init(smem_u32(&bar_full[i]), 1);
             mbar_init(smem_u32(&bar_empty[i]), 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < ASTAGES; ++i) {
             mbar_init(smem_u32(&bar_tfull[i]), 1);
-            mbar_init(smem_u32(&bar_tempty[i]), TC_EPW);
+            mbar_init(smem_u32(&bar_tempty[i]), EPW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -207,8 +243,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
             // ===================== TMA producer
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / p.n_tiles) * TC_BM, n0 = (tile % p.n_tiles) * BN;   // n fastest: CTAs sharing an A tile run together (L2)
+            for (int it = 0, tile; (tile = tc_tile(p, it)) >= 0; ++it) {
+                const int m0 = (tile / p.n_tiles) * TC_BM, n0 = (tile % p.n_tiles) * BN;
                 for (int s = 0; s < p.nsrc; ++s) {
                     const uint32_t tx = (uint32_t)(p.nA[s] * TC_A_TILE + 2 * B_TILE);
                     for (int kb = 0; kb < p.kblocks[s]; ++kb) {
@@ -218,7 +254,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
                         mbar_expect_tx(full, tx);
                         for (int pa = 0; pa < p.nA[s]; ++pa) tma_load_2d(sa + pa * TC_A_TILE, &maps.a[s][pa], full, kb * TC_BK, m0);
                         for (int pb = 0; pb < 2; ++pb)
-                            tma_load_2d(sa + 2 * TC_A_TILE + pb * B_TILE, &maps.b[s][pb], full, kb * TC_BK, n0);
+                            tma_load_2d(sa + (uint32_t)p.a_tiles * TC_A_TILE + pb * B_TILE, &maps.b[s][pb], full, kb * TC_BK, n0);
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -229,7 +265,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
             // ===================== MMA issuer
             int stage = 0, astage = 0;
             uint32_t phase = 0, aphase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int it = 0; tc_tile(p, it) >= 0; ++it) {
                 mbar_wait_backoff(smem_u32(&bar_tempty[astage]), aphase ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)astage * BN;
@@ -239,7 +275,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
                         mbar_wait_backoff(smem_u32(&bar_full[stage]), phase);
                         tc_fence_after();
                         const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
-                        const uint32_t sb = sa + 2 * TC_A_TILE;
+                        const uint32_t sb = sa + (uint32_t)p.a_tiles * TC_A_TILE;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             if (!((p.combos[s] >> c) & 1u)) continue;
@@ -255,7 +291,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
                     }
                 }
                 tc_commit(smem_u32(&bar_tfull[astage]));          // accumulator ready for the epilogue
-                if (++astage == 2) { astage = 0; aphase ^= 1u; }
+                if (++astage == ASTAGES) { astage = 0; aphase ^= 1u; }
             }
         }
     } else if (warp >= 4) {
@@ -264,13 +300,111 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
         int astage = 0;
         uint32_t aphase = 0;
         float delta_local = 0.0f;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        // two-pass NB epilogue state (EK == 1): per-warp queue in dynamic shared memory behind the GEMM stages
+        float* q_acc = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (uint32_t)p.stages * (uint32_t)p.stage_bytes +
+                                                (uint32_t)(warp - 4) * (uint32_t)tc_epi_smem(EPW, CW));
+        float* q_u = q_acc + tc_qcap(EPW);
+        uint32_t* q_pos = reinterpret_cast<uint32_t*>(q_u + tc_qcap(EPW));
+        __nv_bfloat16* s_lo = reinterpret_cast<__nv_bfloat16*>(q_pos + tc_qcap(EPW));   // [32][CW] staging tile, 16 B aligned
+        int64_t cur_m0 = 0, cur_n0 = 0;
+        const uint32_t lt = (1u << lane) - 1u;
+        int qn = 0;
+        auto drain = [&]() {
+            const EpiParams& e = p.epi;
+            __syncwarp();
+            for (int i0 = 0; i0 < qn; i0 += 32) {
+                const int i = i0 + lane;
+                if (i < qn) {
+                    const uint32_t pos = q_pos[i];
+                    const int rl = (int)(pos & 31u), cl = (int)(pos >> 5);
+                    const int64_t r2 = cur_m0 + q * 32 + rl;
+                    const int64_t c2 = cur_n0 + slice * CW + cl;
+                    const float k = nb_entry_draw(e, q_acc[i], q_u[i], (uint32_t)r2 + e.row_offset, (uint32_t)c2);
+                    const float hi = (k >= 256.0f) ? floorf(k * (1.0f / 256.0f)) * 256.0f : 0.0f;
+                    s_lo[rl * CW + cl] = __float2bfloat16_rn(k - hi);
+                    if (hi > 0.0f) e.out.p1[r2 * e.out.ld + c2] = __float2bfloat16_rn(hi);   // rare: count >= 256
+                }
+            }
+            __syncwarp();
+            qn = 0;
+        };
+        for (int it = 0, tile; (tile = tc_tile(p, it)) >= 0; ++it) {
             const int64_t m0 = (int64_t)(tile / p.n_tiles) * TC_BM, n0 = (int64_t)(tile % p.n_tiles) * BN;
-            mbar_wait(smem_u32(&bar_tfull[astage]), aphase);
+            if constexpr (EK == 1) {
+                // lo count plane: staged in the warp's shared-memory tile (zeroed here, patched by pass B, written
+                // out coalesced at the end of the tile).  hi plane (counts >= 256, rare): coalesced zero-fill now
+                // (full 32 B sectors: 4 lanes x 16 B per row, 8 rows per store), scattered patches from pass B.
+                cur_m0 = m0; cur_n0 = n0;
+                const MatView& o = p.epi.out;
+#pragma unroll
+                for (int i = 0; i < (32 * CW * 2) / (32 * 16); ++i) {
+                    const int idx = i * 32 + lane;                   // 16-byte chunk index within the region
+                    const int rr = idx / (CW / 8), ch = idx % (CW / 8);
+                    const int64_t r2 = m0 + q * 32 + rr, c2 = n0 + slice * CW + ch * 8;
+                    reinterpret_cast<uint4*>(s_lo)[idx] = make_uint4(0u, 0u, 0u, 0u);
+                    if (r2 < p.M && c2 < o.ld) *reinterpret_cast<uint4*>(o.p1 + r2 * o.ld + c2) = make_uint4(0u, 0u, 0u, 0u);
+                }
+                __syncwarp();
+            }
+            mbar_wait_epi(smem_u32(&bar_tfull[astage]), aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(astage * BN + slice * CW);
             const int64_t row = m0 + q * 32 + lane;
             float rowsum = 0.0f;
+            if constexpr (EK == 1) {
+                // ---- two-pass NB draw.  Pass A (all elements): Philox uniform vs the per-gene lower bound L of
+                // the zero probability; u < L => 0 (placeholder zeros are stored for every element).  The
+                // other ~20 % are queued in shared memory and drawn densely, one per lane, in pass B.  The
+                // queue persists across tiles (entries carry the tile index), so a warp with expensive genes
+                // does not hold back the per-tile TMEM hand-over.
+                const EpiParams& e = p.epi;
+#pragma unroll 2
+                for (int g = 0; g < CW / 4; ++g) {
+                    uint32_t r[4];
+                    tmem_ld4(taddr + g * 4, r);
+                    tmem_wait_ld();
+                    const int64_t col0 = n0 + slice * CW + g * 4;
+                    const int nvalid = (int)max((int64_t)0, min((int64_t)4, p.N - col0));
+                    const bool live = row < p.M && nvalid > 0;
+                    float u[4] = {0.f, 0.f, 0.f, 0.f};
+                    float4 L = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (live) {
+                        const uint4 w = philox_group(e, (uint32_t)row, (uint32_t)(col0 >> 2));
+                        u[0] = u23(w.x); u[1] = u23(w.y); u[2] = u23(w.z); u[3] = u23(w.w);
+                        L = __ldg(reinterpret_cast<const float4*>(e.nbL + col0));   // padded to a multiple of 4
+                    }
+                    const float Lj[4] = {L.x, L.y, L.z, L.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool nz = live && j < nvalid && u[j] >= Lj[j];
+                        const uint32_t mask = __ballot_sync(0xffffffffu, nz);
+                        if (nz) {
+                            const int slot = qn + __popc(mask & lt);
+                            q_acc[slot] = __uint_as_float(r[j]);
+                            q_u[slot] = u[j];
+                            q_pos[slot] = ((uint32_t)(g * 4 + j) << 5) | (uint32_t)lane;
+                        }
+                        qn += __popc(mask);
+                    }
+                    if (qn > tc_qcap(EPW) - 128) drain();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[astage]));
+                if (++astage == ASTAGES) { astage = 0; aphase ^= 1u; }
+                drain();
+                {   // coalesced write-out of the staged lo plane
+                    const MatView& o = p.epi.out;
+#pragma unroll
+                    for (int i = 0; i < (32 * CW * 2) / (32 * 16); ++i) {
+                        const int idx = i * 32 + lane;
+                        const int rr = idx / (CW / 8), ch = idx % (CW / 8);
+                        const int64_t r2 = m0 + q * 32 + rr, c2 = n0 + slice * CW + ch * 8;
+                        if (r2 < p.M && c2 < o.ld) *reinterpret_cast<uint4*>(o.p0 + r2 * o.ld + c2) = reinterpret_cast<const uint4*>(s_lo)[idx];
+                    }
+                    __syncwarp();
+                }
+            } else {
             // one 4-column group at a time straight out of TMEM: a single copy of the epilogue body
 #pragma unroll 1
             for (int g = 0; g < CW / 4; ++g) {
@@ -281,17 +415,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
                 const int nvalid = (int)max((int64_t)0, min((int64_t)4, p.N - col0));
                 if (row < p.M && nvalid > 0) {
                     const float acc[4] = {__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3])};
-                    if constexpr (EK == 1) epi_nb_draw4(p.epi, row, col0, acc, nvalid);
-                    else if constexpr (EK == 2) epi_bern4(p.epi, row, col0, acc, nvalid);
+                    if constexpr (EK == 2) epi_bern4(p.epi, row, col0, acc, nvalid);
                     else rowsum += epi_apply4(p.epi, row, col0, acc, nvalid, delta_local);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[astage]));   // TMEM stage can be overwritten
-            if (++astage == 2) { astage = 0; aphase ^= 1u; }
+            if (++astage == ASTAGES) { astage = 0; aphase ^= 1u; }
             if constexpr (EK == 0) {
                 if (p.epi.mode == EPI_AIS_RATIO && row < p.M) atomicAdd(&p.epi.logw[row], (double)rowsum);
+            }
             }
         }
         if (p.epi.prev.p0 && p.epi.delta_bits) {
@@ -329,27 +463,38 @@ inline bool tc_supported(const GemmArgs& g, int nsrc) {
 inline bool tc_grad_supported(const TcGradArgs&) { return false; }
 inline cudaError_t launch_grad_tc(TcContext&, const TcGradArgs&, int, cudaStream_t) { return cudaErrorNotSupported; }
 
-template <int BN, int EK>
+template <int BN, int EK, int EPW>
 inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, int num_sms, cudaStream_t stream) {
-    const int slot = (BN == 64 ? 0 : 3) + EK;
+    const int slot = (BN == 64 ? 0 : BN == 128 ? 3 : 6) + EK;
     constexpr int B_TILE = BN * TC_BK * 2;
-    p.stage_bytes = 2 * TC_A_TILE + 2 * B_TILE;
-    p.stages = std::min(TC_MAX_STAGES, TC_SMEM_BUDGET / p.stage_bytes);
-    const int smem = p.stages * p.stage_bytes + 1024;
+    const int qbytes = (EK == 1) ? EPW * tc_epi_smem(EPW, BN / (EPW / 4)) : 0;
+    p.a_tiles = std::max(p.nA[0], p.nsrc > 1 ? p.nA[1] : 1);
+    p.stage_bytes = p.a_tiles * TC_A_TILE + 2 * B_TILE;
+    p.stages = std::max(2, std::min(TC_MAX_STAGES, (TC_SMEM_BUDGET - qbytes) / p.stage_bytes));
+    const int smem = p.stages * p.stage_bytes + 1024 + qbytes;
     if (!t.attr_set[slot]) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, EK, EPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e != cudaSuccess) return e;
         t.attr_set[slot] = true;
     }
-    const int grid = std::min(p.m_tiles * p.n_tiles, num_sms);
-    k_gemm_tc<BN, EK><<<grid, TC_THREADS, smem, stream>>>(maps, p);
+    p.sched = p.m_tiles >= num_sms ? 1 : 0;
+    const int grid = p.sched ? std::min(p.m_tiles, num_sms) : std::min(p.m_tiles * p.n_tiles, num_sms);
+    k_gemm_tc<BN, EK, EPW><<<grid, 32 * (4 + EPW), smem, stream>>>(maps, p);
     return cudaGetLastError();
 }
 
 inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int nsrc, const GemmArgs& g, int num_sms,
                                   cudaStream_t stream) {
     if (!t.encode) return cudaErrorNotSupported;
-    const int BN = g.N <= 64 ? 64 : 128;
+    // epilogue class: the fast sampling kernels need Philox-fed draws into the canonical plane layout
+    const EpiParams& e = g.epi;
+    int ek = 0;
+    if (!e.uniforms && !e.addend && !e.prev.p0) {
+        if (e.mode == EPI_NB_DRAW && e.factor == 1.0f && e.nbc && e.nbL && !e.bias1 && e.out.p1 && !e.out.f && e.out.kind == MAT_COUNT &&
+            nsrc == 1 && ops[0].a.kind == MAT_BINARY && e.wscale >= 0.0f && e.wscale <= 1.0f) ek = 1;
+        if (e.mode == EPI_SIGM_BERN && e.bias0 && !e.out.p1 && !e.out.f) ek = 2;
+    }
+    const int BN = g.N <= 64 ? 64 : 128;   // (a 192-column / 24-epilogue-warp NB variant measured slower: L1/L2 request-bound)
     TcMaps maps;
     TcParams p;
     memset(&p, 0, sizeof(p));
@@ -372,21 +517,15 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
         if (!ok) return cudaErrorInvalidValue;
     }
     if (nsrc == 1) { maps.a[1][0] = maps.a[0][0]; maps.a[1][1] = maps.a[0][1]; maps.b[1][0] = maps.b[0][0]; maps.b[1][1] = maps.b[0][1]; }
-    // epilogue class: the fast sampling kernels need Philox-fed draws into the canonical plane layout
-    const EpiParams& e = g.epi;
-    int ek = 0;
-    if (!e.uniforms && !e.addend && !e.prev.p0) {
-        if (e.mode == EPI_NB_DRAW && e.factor == 1.0f && e.nbc && !e.bias1 && e.out.p1 && !e.out.f && e.out.kind == MAT_COUNT) ek = 1;
-        if (e.mode == EPI_SIGM_BERN && e.bias0 && !e.out.p1 && !e.out.f) ek = 2;
-    }
     if (BN == 64) {
-        if (ek == 1) return tc_launch_bn<64, 1>(t, maps, p, num_sms, stream);
-        if (ek == 2) return tc_launch_bn<64, 2>(t, maps, p, num_sms, stream);
-        return tc_launch_bn<64, 0>(t, maps, p, num_sms, stream);
+        if (ek == 1) return tc_launch_bn<64, 1, 16>(t, maps, p, num_sms, stream);
+        if (ek == 2) return tc_launch_bn<64, 2, 16>(t, maps, p, num_sms, stream);
+        return tc_launch_bn<64, 0, 16>(t, maps, p, num_sms, stream);
     }
-    if (ek == 1) return tc_launch_bn<128, 1>(t, maps, p, num_sms, stream);
-    if (ek == 2) return tc_launch_bn<128, 2>(t, maps, p, num_sms, stream);
-    return tc_launch_bn<128, 0>(t, maps, p, num_sms, stream);
+    if (BN == 192) return tc_launch_bn<192, 1, 24>(t, maps, p, num_sms, stream);
+    if (ek == 1) return tc_launch_bn<128, 1, 16>(t, maps, p, num_sms, stream);
+    if (ek == 2) return tc_launch_bn<128, 2, 16>(t, maps, p, num_sms, stream);
+    return tc_launch_bn<128, 0, 16>(t, maps, p, num_sms, stream);
 }
 
 }  // namespace scdbm
