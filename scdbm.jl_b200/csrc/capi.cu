@@ -182,6 +182,11 @@ static scdbm_mat* mat_new(scdbm_ctx* ctx, int64_t rows, int64_t cols, int kind) 
         CK(cudaMalloc(&m->v.p1, bytes));
         CK(cudaMemsetAsync(m->v.p1, 0, bytes, ctx->stream));
     }
+    if (kind == MAT_COUNT) {
+        const size_t fb = (size_t)((std::max<int64_t>(rows, 1) + 127) / 128) * sizeof(uint32_t);
+        CK(cudaMalloc(&m->v.hiflag, fb));
+        CK(cudaMemsetAsync(m->v.hiflag, 0, fb, ctx->stream));   // planes start zeroed
+    }
     if (kind == MAT_REAL) {
         CK(cudaMalloc(&m->v.f, bytes * 2));
         CK(cudaMemsetAsync(m->v.f, 0, bytes * 2, ctx->stream));
@@ -194,6 +199,7 @@ static void mat_free(scdbm_mat* m) {
         cudaFree(m->v.p0);
         cudaFree(m->v.p1);
         cudaFree(m->v.f);
+        cudaFree(m->v.hiflag);
         scdbm_ctx* c = m->ctx;
         delete m;
         ctx_release(c);
@@ -205,6 +211,14 @@ static MatView rows_view(const MatView& v, int64_t rows) {
     MatView r = v;
     r.rows = std::min(rows, v.rows);
     return r;
+}
+
+// hi-plane flags of a COUNT matrix: `all` = true after any writer that does not maintain them
+// (upload, gather, copies, generic epilogues); the two-pass NB epilogue starts from all-clear
+static void set_hiflags(scdbm_ctx* ctx, const MatView& v, bool all) {
+    if (!v.hiflag) return;
+    const size_t fb = (size_t)((std::max<int64_t>(v.rows, 1) + 127) / 128) * sizeof(uint32_t);
+    cudaMemsetAsync(v.hiflag, all ? 0x01 : 0x00, fb, ctx->stream);
 }
 
 static EpiParams epi_base(scdbm_ctx* ctx) {
@@ -248,9 +262,13 @@ static void run_gemm(scdbm_ctx* ctx, GemmArgs& g, const SweepSrc* srcs, int nsrc
             ops[s].N = srcs[s].up ? L.H : L.V;
             ops[s].K = srcs[s].up ? L.V : L.H;
         }
+        // the Philox-fed tensor-core NB epilogue maintains the hi-plane flags itself (from all-clear); every
+        // other writer of a COUNT matrix marks all row tiles as "hi plane possibly in use"
+        set_hiflags(ctx, g.epi.out, tc_epilogue_class(g, ops, nsrc) != 1);
         CK(launch_gemm_tc(ctx->tc, ops, nsrc, g, ctx->num_sms, ctx->stream));
         ctx->tc_launches++;
     } else {
+        set_hiflags(ctx, g.epi.out, true);
         CK(launch_gemm_simt(g, ctx->stream));
     }
     ctx->launches++;
@@ -731,6 +749,7 @@ int32_t scdbm_mat_upload(scdbm_mat* m, const double* x, int64_t ld) {
         if (sub.f) sub.f += c0;
         sub.cols = nc;
         dim3 grid((unsigned)((m->v.rows + 31) / 32), (unsigned)((nc + 31) / 32)), block(32, 8);
+        set_hiflags(c, m->v, true);
         k_upload_f64<<<grid, block, 0, c->stream>>>(stage, ld, sub);
         CK(cudaGetLastError());
         c->launches++;
@@ -795,6 +814,7 @@ int32_t scdbm_mat_copy(scdbm_mat* dst, const scdbm_mat* src) {
     REQUIRE(dst->v.rows == src->v.rows && dst->v.cols == src->v.cols, "shapes differ");
     REQUIRE(dst->v.kind == src->v.kind, "kinds differ");
     if (dst->v.rows == 0) return SCDBM_OK;
+    set_hiflags(dst->ctx, dst->v, true);
     k_copy_rows<<<(unsigned)dst->v.rows, 128, 0, dst->ctx->stream>>>(src->v, dst->v, dst->v.rows);
     CK(cudaGetLastError());
     dst->ctx->launches++;
@@ -923,6 +943,7 @@ int32_t scdbm_particles_init(scdbm_particles* p, int32_t biased) {
             if (m->L[0].kind == SCDBM_VIS_NEGBIN) { mode = 3; r = m->L[0].r; }
             else { mode = biased ? 1 : 0; bias = m->L[0].a; }
         } else { mode = biased ? 1 : 0; bias = m->L[i - 1].b; }
+        set_hiflags(c, v, true);
         k_init<<<grid1d(v.rows * ((v.cols + 3) / 4)), 256, 0, c->stream>>>(v, mode, bias, r, k0, k1, (uint32_t)i,
                                                                             (uint32_t)p->row_offset);
         CK(cudaGetLastError());
@@ -1365,6 +1386,7 @@ int32_t scdbm_rbm_train_epoch(scdbm_trainer* t, const scdbm_mat* x, const int32_
         const int64_t thisb = std::min<int64_t>(B, n - s);
         const int64_t mrows = t->pcd ? B : thisb;  // PCD keeps the full chain (rbmtraining.jl:548-553)
         MatView v = rows_view(t->v->v, thisb), h = rows_view(t->h->v, thisb);
+        set_hiflags(c, v, true);
         k_gather_rows<<<(unsigned)thisb, 128, 0, c->stream>>>(x->v, t->d_perm + s, v);
         c->launches++;
         DrawCfg d;

@@ -22,6 +22,7 @@ struct MatView {
     __nv_bfloat16* p0;
     __nv_bfloat16* p1;     // nullptr for BINARY
     float* f;              // fp32 master copy, REAL only (else nullptr)
+    uint32_t* hiflag;      // COUNT only: per 128-row tile, non-zero if the p1 plane may hold a non-zero entry
     int64_t rows, cols, ld; // ld (elements) is a multiple of 64
     int32_t kind;
 };

@@ -66,6 +66,7 @@ struct TcParams {
     int32_t m_tiles, n_tiles;
     int32_t stages, stage_bytes;
     int32_t a_tiles;      // A-plane tiles reserved per stage (1 or 2)
+    const uint32_t* a_hiflag[2];   // per source: COUNT operand's per-row-tile "hi plane in use" flags (nullptr: always)
     int32_t sched;        // 1: a CTA owns whole m-tiles and walks all n-tiles (balanced over genes, A re-used
                           //    back-to-back); 0: flat round-robin over (m, n) tiles, n fastest (few m-tiles)
     EpiParams epi;
@@ -246,13 +247,15 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
             for (int it = 0, tile; (tile = tc_tile(p, it)) >= 0; ++it) {
                 const int m0 = (tile / p.n_tiles) * TC_BM, n0 = (tile % p.n_tiles) * BN;
                 for (int s = 0; s < p.nsrc; ++s) {
-                    const uint32_t tx = (uint32_t)(p.nA[s] * TC_A_TILE + 2 * B_TILE);
+                    // counts >= 256 are rare: skip the hi plane of a COUNT operand unless this row tile has one
+                    const int nA = (p.a_hiflag[s] && p.nA[s] == 2 && p.a_hiflag[s][m0 / TC_BM] == 0u) ? 1 : p.nA[s];
+                    const uint32_t tx = (uint32_t)(nA * TC_A_TILE + 2 * B_TILE);
                     for (int kb = 0; kb < p.kblocks[s]; ++kb) {
                         mbar_wait_backoff(smem_u32(&bar_empty[stage]), phase ^ 1u);
                         const uint32_t full = smem_u32(&bar_full[stage]);
                         const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
                         mbar_expect_tx(full, tx);
-                        for (int pa = 0; pa < p.nA[s]; ++pa) tma_load_2d(sa + pa * TC_A_TILE, &maps.a[s][pa], full, kb * TC_BK, m0);
+                        for (int pa = 0; pa < nA; ++pa) tma_load_2d(sa + pa * TC_A_TILE, &maps.a[s][pa], full, kb * TC_BK, m0);
                         for (int pb = 0; pb < 2; ++pb)
                             tma_load_2d(sa + (uint32_t)p.a_tiles * TC_A_TILE + pb * B_TILE, &maps.b[s][pb], full, kb * TC_BK, n0);
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -265,12 +268,14 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
             // ===================== MMA issuer
             int stage = 0, astage = 0;
             uint32_t phase = 0, aphase = 0;
-            for (int it = 0; tc_tile(p, it) >= 0; ++it) {
+            for (int it = 0, tile; (tile = tc_tile(p, it)) >= 0; ++it) {
+                const int m_blk = tile / p.n_tiles;
                 mbar_wait_backoff(smem_u32(&bar_tempty[astage]), aphase ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)astage * BN;
                 uint32_t accumulate = 0;
                 for (int s = 0; s < p.nsrc; ++s) {
+                    const uint32_t combos = (p.a_hiflag[s] && p.nA[s] == 2 && p.a_hiflag[s][m_blk] == 0u) ? (p.combos[s] & 0x3u) : p.combos[s];
                     for (int kb = 0; kb < p.kblocks[s]; ++kb) {
                         mbar_wait_backoff(smem_u32(&bar_full[stage]), phase);
                         tc_fence_after();
@@ -278,7 +283,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                         const uint32_t sb = sa + (uint32_t)p.a_tiles * TC_A_TILE;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            if (!((p.combos[s] >> c) & 1u)) continue;
+                            if (!((combos >> c) & 1u)) continue;
                             const uint32_t a0 = sa + (c >> 1) * TC_A_TILE, b0 = sb + (c & 1) * B_TILE;
 #pragma unroll
                             for (int k = 0; k < TC_BK / 16; ++k) {
@@ -322,7 +327,10 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     const float k = nb_entry_draw(e, q_acc[i], q_u[i], (uint32_t)r2 + e.row_offset, (uint32_t)c2);
                     const float hi = (k >= 256.0f) ? floorf(k * (1.0f / 256.0f)) * 256.0f : 0.0f;
                     s_lo[rl * CW + cl] = __float2bfloat16_rn(k - hi);
-                    if (hi > 0.0f) e.out.p1[r2 * e.out.ld + c2] = __float2bfloat16_rn(hi);   // rare: count >= 256
+                    if (hi > 0.0f) {                                                     // rare: count >= 256
+                        e.out.p1[r2 * e.out.ld + c2] = __float2bfloat16_rn(hi);
+                        if (e.out.hiflag) e.out.hiflag[r2 / TC_BM] = 1u;
+                    }
                 }
             }
             __syncwarp();
@@ -483,10 +491,8 @@ inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, i
     return cudaGetLastError();
 }
 
-inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int nsrc, const GemmArgs& g, int num_sms,
-                                  cudaStream_t stream) {
-    if (!t.encode) return cudaErrorNotSupported;
-    // epilogue class: the fast sampling kernels need Philox-fed draws into the canonical plane layout
+// epilogue class: the fast sampling kernels need Philox-fed draws into the canonical plane layout
+inline int tc_epilogue_class(const GemmArgs& g, const TcOperandPlanes* ops, int nsrc) {
     const EpiParams& e = g.epi;
     int ek = 0;
     if (!e.uniforms && !e.addend && !e.prev.p0) {
@@ -494,6 +500,13 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
             nsrc == 1 && ops[0].a.kind == MAT_BINARY && e.wscale >= 0.0f && e.wscale <= 1.0f) ek = 1;
         if (e.mode == EPI_SIGM_BERN && e.bias0 && !e.out.p1 && !e.out.f) ek = 2;
     }
+    return ek;
+}
+
+inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int nsrc, const GemmArgs& g, int num_sms,
+                                  cudaStream_t stream) {
+    if (!t.encode) return cudaErrorNotSupported;
+    const int ek = tc_epilogue_class(g, ops, nsrc);
     const int BN = g.N <= 64 ? 64 : 128;   // (a 192-column / 24-epilogue-warp NB variant measured slower: L1/L2 request-bound)
     TcMaps maps;
     TcParams p;
@@ -507,6 +520,7 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
     for (int s = 0; s < nsrc; ++s) {
         const MatView& a = ops[s].a;
         p.kblocks[s] = (int)((ops[s].K + TC_BK - 1) / TC_BK);
+        p.a_hiflag[s] = (a.kind == MAT_COUNT) ? a.hiflag : nullptr;
         p.nA[s] = a.p1 ? 2 : 1;
         // plane products: binary x (hi,lo); count (lo,hi) x (hi,lo); real (hi,lo) x (hi,lo) minus lo*lo
         p.combos[s] = a.p1 ? (a.kind == MAT_COUNT ? 0xFu : 0x7u) : 0x3u;

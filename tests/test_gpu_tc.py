@@ -81,3 +81,38 @@ def test_tc_meanfield_and_ais(pkg, tc):
     w = pkg.aislogimpweights(m, ntemperatures=20, nparticles=256, ctx=tc)
     wr = oais.aislogimpweights(dbm, px.Rng(SEED), ntemperatures=20, nparticles=256)
     assert np.mean(np.abs(w - wr) > 1e-3 * np.maximum(1, np.abs(wr))) < 0.05
+
+
+def test_tc_large_counts_hi_plane_flags(pkg, tc, simt):
+    """Counts >= 256 are rare in scRNA data, so the up-sweep skips the hi count plane unless the row tile
+    is flagged by the sampling epilogue.  Here a few genes have means in the hundreds: the flags must be
+    set and the hi plane used -- the chain must still match the CUDA-core engine and the oracle."""
+    units = [320, 128, 64]
+    dbm = synth.random_dbm(units, 5, wscale=(0.002, 0.01))
+    big = np.array([3, 77, 200, 319])
+    dbm[0].visbias[big] = np.log(np.array([300.0, 500.0, 800.0, 400.0]) / (np.array([300.0, 500.0, 800.0, 400.0]) + 0.5))
+    dbm[0].weights[big] = -1e-6                          # keep these genes' means in the hundreds for every h
+    pm = to_pkg_model(pkg, dbm)
+    mt, ms = pkg.DeviceModel.from_host(pm, tc), pkg.DeviceModel.from_host(pm, simt)
+    n = 300
+    pt = pkg.DeviceParticles(mt, n).init(False)
+    ps = pkg.DeviceParticles(ms, n).init(False)
+    ref = om.initparticles(dbm, n, px.Rng(SEED))
+    pkg.gibbssample_(pt, mt, 4)
+    pkg.gibbssample_(ps, ms, 4)
+    om.gibbssample_dbm(ref, dbm, px.Rng(SEED), 4)
+    got = pt.to_host()
+    assert (got[0][:, big] >= 256).mean() > 0.1          # the hi plane is really in use
+    for a, b, c in zip(got, ps.to_host(), ref):
+        assert np.mean(a != b) < 3e-3
+        assert np.mean(a != c) < 6e-3
+    # a second model without large counts on the same particles' buffers: flags are cleared again
+    dbm2 = synth.random_dbm(units, 6, wscale=(0.002, 0.01))
+    m2t, m2s = pkg.DeviceModel.from_host(to_pkg_model(pkg, dbm2), tc), pkg.DeviceModel.from_host(to_pkg_model(pkg, dbm2), simt)
+    p2t = pkg.DeviceParticles(m2t, n).upload(got)
+    p2s = pkg.DeviceParticles(m2s, n).upload(got)
+    p2t.clock = p2s.clock = 9
+    pkg.gibbssample_(p2t, m2t, 3)
+    pkg.gibbssample_(p2s, m2s, 3)
+    for a, b in zip(p2t.to_host(), p2s.to_host()):
+        assert np.mean(a != b) < 3e-3
