@@ -749,7 +749,7 @@ int32_t scdbm_mat_upload(scdbm_mat* m, const double* x, int64_t ld) {
         if (sub.f) sub.f += c0;
         sub.cols = nc;
         dim3 grid((unsigned)((m->v.rows + 31) / 32), (unsigned)((nc + 31) / 32)), block(32, 8);
-        set_hiflags(c, m->v, true);
+        if (c0 == 0) set_hiflags(c, m->v, false);   // the upload kernel raises the flag of a row tile that gets a count >= 256
         k_upload_f64<<<grid, block, 0, c->stream>>>(stage, ld, sub);
         CK(cudaGetLastError());
         c->launches++;
@@ -1201,9 +1201,23 @@ static void gradient_layer(scdbm_opt* o, int l, const MatView& v, const MatView&
     g.epi.out_f32 = o->buf + o->offW[l];
     g.epi.ldo = L.H;
     bool done = false;
-    if (c->engine != SCDBM_ENGINE_SIMT) {
-        TcGradArgs ga{v, h, vm, hm, pos_scale, -neg_scale, g.epi.out_f32, L.V, L.H};
+    const double work = (double)L.V * (double)L.H * (double)(v.rows + vm.rows);
+    if (c->engine == SCDBM_ENGINE_TC || (c->engine == SCDBM_ENGINE_AUTO && work >= (double)(1 << 24))) {
+        TcGradArgs ga{v, h, vm, hm, pos_scale, -neg_scale, g.epi.out_f32, L.V, L.H, nullptr, 1};
         if (tc_grad_supported(ga)) {
+            ga.splits = tc_grad_splits(ga, c->num_sms);
+            if (ga.splits > 1) {
+                const int64_t need = (int64_t)ga.splits * L.V * L.H;
+                if (c->scratch_cap < need) {
+                    CK(cudaStreamSynchronize(c->stream));
+                    cudaFree(c->scratch);
+                    c->scratch = nullptr;
+                    c->scratch_cap = 0;
+                    CK(cudaMalloc(&c->scratch, need * sizeof(float)));
+                    c->scratch_cap = need;
+                }
+                ga.partial = c->scratch;
+            }
             CK(launch_grad_tc(c->tc, ga, c->num_sms, c->stream));
             c->tc_launches++;
             done = true;

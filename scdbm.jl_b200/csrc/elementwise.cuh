@@ -25,6 +25,7 @@ __global__ void k_upload_f64(const double* __restrict__ src, int64_t lds, MatVie
             dst.p0[r * dst.ld + c] = a;
             if (dst.p1) dst.p1[r * dst.ld + c] = b;
             if (dst.f) dst.f[r * dst.ld + c] = t[threadIdx.x][j];
+            if (dst.hiflag && __bfloat162float(b) != 0.0f) dst.hiflag[r / 128] = 1u;
         }
     }
 }

@@ -37,9 +37,11 @@ struct TcOperandPlanes {
 
 struct TcGradArgs {
     MatView v, h, vm, hm;
-    float pos_scale, neg_scale;
-    float* out;
+    float pos_scale, neg_scale;   // out = pos_scale * v'h + neg_scale * vm'hm  (neg_scale carries the minus sign)
+    float* out;                   // fp32 [V x H], row-major
     int64_t V, H;
+    float* partial;               // split-K workspace [splits][V][H] (nullptr: splits == 1)
+    int32_t splits;
 };
 
 constexpr int TC_BM = 128, TC_BK = 64;
@@ -468,8 +470,6 @@ inline bool tc_supported(const GemmArgs& g, int nsrc) {
         if (g.src[s].K < 1) return false;
     return true;
 }
-inline bool tc_grad_supported(const TcGradArgs&) { return false; }
-inline cudaError_t launch_grad_tc(TcContext&, const TcGradArgs&, int, cudaStream_t) { return cudaErrorNotSupported; }
 
 template <int BN, int EK, int EPW>
 inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, int num_sms, cudaStream_t stream) {
@@ -540,6 +540,261 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
     if (ek == 1) return tc_launch_bn<128, 1, 16>(t, maps, p, num_sms, stream);
     if (ek == 2) return tc_launch_bn<128, 2, 16>(t, maps, p, num_sms, stream);
     return tc_launch_bn<128, 0, 16>(t, maps, p, num_sms, stream);
+}
+
+// =====================================================================================
+// Gradient GEMM (K5): dW[V x H] = s0 * v' h + s1 * vm' hm, contraction over the batch axis.
+// States are stored row = sample, unit-contiguous, i.e. both operands are MN-major for this product:
+// TMA boxes of 64 samples x 64 units (128 B inner, 128B swizzle) land as the canonical MN-major UMMA
+// layout (LBO = 8 KB between 64-unit blocks, SBO = 1 KB between 8-sample groups); a_major = b_major = 1
+// in the instruction descriptor.  Positive and negative phase accumulate into two TMEM accumulators and
+// are combined with their scales in the epilogue.  Split-K over CTAs with a deterministic reduction.
+struct alignas(64) TcGradMaps {
+    CUtensorMap a[2][2];   // [source][plane]: v-like operand (V units)
+    CUtensorMap b[2][2];   // [source][plane]: h-like operand (H units)
+};
+struct TcGradParams {
+    int64_t V, H;
+    int32_t kblocks[2];
+    int32_t nA[2], nB[2];
+    uint32_t combos[2];
+    const uint32_t* a_hiflag[2];
+    float scale[2];
+    float* out;
+    float* partial;
+    int32_t m_tiles, n_tiles, splits, stages;
+};
+constexpr int TG_BN = 128, TG_THREADS = 32 * (4 + 16);
+constexpr int TG_PLANE = 128 * TC_BK * 2;           // 16 KB: [2 unit blocks][64 samples][64 units] bf16
+constexpr int TG_STAGE = 4 * TG_PLANE;              // up to 2 A planes + 2 B planes
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(8192 >> 4) << 16;    // leading byte offset: next 64-unit block
+    d |= (uint64_t)(1024 >> 4) << 32;    // stride byte offset: next group of 8 samples
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant__ TcGradMaps maps, const __grid_constant__ TcGradParams p) {
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TG_BN >> 3) << 17) |
+                               ((uint32_t)(TC_BM >> 4) << 24);
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_tfull, bar_tempty;
+    __shared__ uint32_t tmem_holder;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwork = p.m_tiles * p.n_tiles * p.splits;
+
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.stages; ++i) { mbar_init(smem_u32(&bar_full[i]), 1); mbar_init(smem_u32(&bar_empty[i]), 1); }
+        mbar_init(smem_u32(&bar_tfull), 1);
+        mbar_init(smem_u32(&bar_tempty), 16);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    } else if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_holder;
+
+    // k-block range of source s for split `sp`
+    auto kb_range = [&](int s, int sp, int& lo, int& hi) {
+        lo = (int)((int64_t)p.kblocks[s] * sp / p.splits);
+        hi = (int)((int64_t)p.kblocks[s] * (sp + 1) / p.splits);
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+                const int tile = w / p.splits, sp = w % p.splits;
+                const int m0 = (tile / p.n_tiles) * TC_BM, n0 = (tile % p.n_tiles) * TG_BN;
+                for (int s = 0; s < 2; ++s) {
+                    int lo, hi;
+                    kb_range(s, sp, lo, hi);
+                    for (int kb = lo; kb < hi; ++kb) {
+                        const int nA = (p.a_hiflag[s] && p.nA[s] == 2 && p.a_hiflag[s][kb / 2] == 0u) ? 1 : p.nA[s];
+                        mbar_wait_backoff(smem_u32(&bar_empty[stage]), phase ^ 1u);
+                        const uint32_t full = smem_u32(&bar_full[stage]);
+                        const uint32_t sa = smem_base + (uint32_t)stage * TG_STAGE, sb = sa + 2 * TG_PLANE;
+                        mbar_expect_tx(full, (uint32_t)((nA + p.nB[s]) * TG_PLANE));
+                        for (int pa = 0; pa < nA; ++pa)
+                            for (int blk = 0; blk < 2; ++blk)
+                                tma_load_2d(sa + pa * TG_PLANE + blk * 8192, &maps.a[s][pa], full, m0 + blk * 64, kb * TC_BK);
+                        for (int pb = 0; pb < p.nB[s]; ++pb)
+                            for (int blk = 0; blk < 2; ++blk)
+                                tma_load_2d(sb + pb * TG_PLANE + blk * 8192, &maps.b[s][pb], full, n0 + blk * 64, kb * TC_BK);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+                const int sp = w % p.splits;
+                mbar_wait_backoff(smem_u32(&bar_tempty), aphase ^ 1u);
+                tc_fence_after();
+                for (int s = 0; s < 2; ++s) {
+                    const uint32_t tmem_d = tmem_base + (uint32_t)s * TG_BN;
+                    uint32_t accumulate = 0;
+                    int lo, hi;
+                    kb_range(s, sp, lo, hi);
+                    for (int kb = lo; kb < hi; ++kb) {
+                        const uint32_t combos = (p.a_hiflag[s] && p.nA[s] == 2 && p.a_hiflag[s][kb / 2] == 0u) ? (p.combos[s] & 0x3u) : p.combos[s];
+                        mbar_wait_backoff(smem_u32(&bar_full[stage]), phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + (uint32_t)stage * TG_STAGE, sb = sa + 2 * TG_PLANE;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            if (!((combos >> c) & 1u)) continue;
+                            const uint32_t a0 = sa + (c >> 1) * TG_PLANE, b0 = sb + (c & 1) * TG_PLANE;
+#pragma unroll
+                            for (int k = 0; k < TC_BK / 16; ++k) {   // 16 samples = two 8-sample groups = 2 KB
+                                tc_mma_f16(tmem_d, umma_desc_mn_sw128(a0 + k * 2048), umma_desc_mn_sw128(b0 + k * 2048), IDESC, accumulate);
+                                accumulate = 1;
+                            }
+                        }
+                        tc_commit(smem_u32(&bar_empty[stage]));
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+                tc_commit(smem_u32(&bar_tfull));
+                aphase ^= 1u;
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3, slice = (warp - 4) >> 2;
+        uint32_t aphase = 0;
+        for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+            const int tile = w / p.splits, sp = w % p.splits;
+            const int64_t m0 = (int64_t)(tile / p.n_tiles) * TC_BM, n0 = (int64_t)(tile % p.n_tiles) * TG_BN;
+            int lo0, hi0, lo1, hi1;
+            kb_range(0, sp, lo0, hi0);
+            kb_range(1, sp, lo1, hi1);
+            mbar_wait_epi(smem_u32(&bar_tfull), aphase);
+            aphase ^= 1u;
+            tc_fence_after();
+            const int64_t row = m0 + q * 32 + lane;
+            float* dst = (p.splits > 1 ? p.partial + (int64_t)sp * p.V * p.H : p.out);
+#pragma unroll 1
+            for (int g = 0; g < 8; ++g) {
+                uint32_t r0[4], r1[4];
+                const uint32_t col = (uint32_t)(slice * 32 + g * 4);
+                tmem_ld4(tmem_base + ((uint32_t)(q * 32) << 16) + col, r0);
+                tmem_ld4(tmem_base + ((uint32_t)(q * 32) << 16) + TG_BN + col, r1);
+                tmem_wait_ld();
+                const int64_t c0 = n0 + col;
+                if (row < p.V) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (c0 + j < p.H) {
+                            // a source with no k-blocks in this split never wrote its accumulator: treat as zero
+                            const float a0 = hi0 > lo0 ? __uint_as_float(r0[j]) : 0.0f;
+                            const float a1 = hi1 > lo1 ? __uint_as_float(r1[j]) : 0.0f;
+                            dst[row * p.H + c0 + j] = fmaf(p.scale[0], a0, p.scale[1] * a1);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_tempty));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
+// out[i] = sum over splits (fixed order) of partial[s][i]
+__global__ void k_grad_reduce(const float* __restrict__ partial, int splits, int64_t n, float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float t = 0.0f;
+        for (int s = 0; s < splits; ++s) t += partial[(int64_t)s * n + i];
+        out[i] = t;
+    }
+}
+
+inline bool tc_make_map_mn(TcContext& t, CUtensorMap* map, const void* ptr, int64_t samples, int64_t units, int64_t ld) {
+    const cuuint64_t dims[2] = {(cuuint64_t)units, (cuuint64_t)samples};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)TC_BK};
+    const cuuint32_t estr[2] = {1, 1};
+    return t.encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline bool tc_grad_supported(const TcGradArgs& a) {
+    return a.V >= 1 && a.H >= 1 && a.v.rows >= 1 && a.vm.rows >= 1 && a.v.p0 && a.h.p0 && a.vm.p0 && a.hm.p0;
+}
+
+// number of K splits that fills the GPU when there are few output tiles
+inline int tc_grad_splits(const TcGradArgs& a, int num_sms) {
+    const int tiles = (int)((a.V + TC_BM - 1) / TC_BM) * (int)((a.H + TG_BN - 1) / TG_BN);
+    const int kb = (int)((a.v.rows + TC_BK - 1) / TC_BK);
+    if (tiles >= num_sms) return 1;
+    return std::max(1, std::min({(num_sms + tiles - 1) / tiles, kb / 4 + 1, 16}));
+}
+
+inline cudaError_t launch_grad_tc(TcContext& t, const TcGradArgs& a, int num_sms, cudaStream_t stream) {
+    if (!t.encode) return cudaErrorNotSupported;
+    TcGradMaps maps;
+    TcGradParams p;
+    memset(&p, 0, sizeof(p));
+    p.V = a.V; p.H = a.H;
+    p.out = a.out; p.partial = a.partial; p.splits = std::max(1, a.splits);
+    p.m_tiles = (int)((a.V + TC_BM - 1) / TC_BM);
+    p.n_tiles = (int)((a.H + TG_BN - 1) / TG_BN);
+    p.scale[0] = a.pos_scale; p.scale[1] = a.neg_scale;
+    const MatView* av[2] = {&a.v, &a.vm};
+    const MatView* bv[2] = {&a.h, &a.hm};
+    for (int s = 0; s < 2; ++s) {
+        const MatView& A = *av[s];
+        const MatView& B = *bv[s];
+        p.kblocks[s] = (int)((A.rows + TC_BK - 1) / TC_BK);
+        p.nA[s] = A.p1 ? 2 : 1;
+        p.nB[s] = B.p1 ? 2 : 1;
+        // plane products; real x real drops lo*lo
+        uint32_t c = 0;
+        for (int pa = 0; pa < p.nA[s]; ++pa)
+            for (int pb = 0; pb < p.nB[s]; ++pb)
+                if (!(pa == 1 && pb == 1 && A.kind == MAT_REAL && B.kind == MAT_REAL)) c |= 1u << (pa * 2 + pb);
+        p.combos[s] = c;
+        p.a_hiflag[s] = (A.kind == MAT_COUNT) ? A.hiflag : nullptr;
+        bool ok = tc_make_map_mn(t, &maps.a[s][0], A.p0, A.rows, a.V, A.ld);
+        ok = ok && tc_make_map_mn(t, &maps.a[s][1], A.p1 ? A.p1 : A.p0, A.rows, a.V, A.ld);
+        ok = ok && tc_make_map_mn(t, &maps.b[s][0], B.p0, B.rows, a.H, B.ld);
+        ok = ok && tc_make_map_mn(t, &maps.b[s][1], B.p1 ? B.p1 : B.p0, B.rows, a.H, B.ld);
+        if (!ok) return cudaErrorInvalidValue;
+    }
+    p.stages = 3;
+    const int smem = p.stages * TG_STAGE + 1024;
+    if (!t.attr_set[8]) {
+        cudaError_t e = cudaFuncSetAttribute(k_grad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        t.attr_set[8] = true;
+    }
+    const int nwork = p.m_tiles * p.n_tiles * p.splits;
+    k_grad_tc<<<std::min(nwork, num_sms), TG_THREADS, smem, stream>>>(maps, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || p.splits == 1) return e;
+    const int64_t n = a.V * a.H;
+    k_grad_reduce<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, stream>>>(a.partial, p.splits, n, a.out);
+    return cudaGetLastError();
 }
 
 }  // namespace scdbm

@@ -116,3 +116,45 @@ def test_tc_large_counts_hi_plane_flags(pkg, tc, simt):
     pkg.gibbssample_(p2s, m2s, 3)
     for a, b in zip(p2t.to_host(), p2s.to_host()):
         assert np.mean(a != b) < 3e-3
+
+
+@pytest.mark.parametrize("V,H,npos,nneg", [(130, 67, 50, 37), (256, 128, 700, 64), (2000, 256, 1500, 100)])
+def test_tc_gradient_gemm(pkg, tc, V, H, npos, nneg):
+    """K5: dW = v'h/n+ - vm'hm/n- on the tensor cores (MN-major operands, split-K), vs the oracle."""
+    g = np.random.default_rng(9)
+    rbm = synth.random_dbm([V, H, 8], 4)[0]
+    m = pkg.DeviceModel.from_host(to_pkg_model(pkg, rbm), tc)
+    v = g.poisson(1.0, (npos, V)).astype(float)
+    v[3, 5] = 3000.0                                     # hi count plane in one row tile only
+    h = g.random((npos, H))
+    for vm, hm in [(g.gamma(0.5, 2.0, (nneg, V)), g.random((nneg, H))),                                   # CD: real-valued model side
+                   (g.poisson(2.0, (nneg, V)).astype(float), (g.random((nneg, H)) < 0.5).astype(float))]:  # PCD: particles
+        opt = pkg.loglikelihoodoptimizer(m, learningrate=0.01)
+        tc.launch_count(reset=True)
+        mats = [pkg.Mat.from_host(tc, v, pkg.MAT_COUNT),
+                pkg.Mat.from_host(tc, vm, pkg.MAT_COUNT if np.all(vm == np.floor(vm)) else pkg.MAT_REAL),
+                pkg.Mat.from_host(tc, h, pkg.MAT_REAL),
+                pkg.Mat.from_host(tc, hm, pkg.MAT_BINARY if np.isin(hm, (0.0, 1.0)).all() else pkg.MAT_REAL)]
+        opt.computegradient_(*mats, m)
+        assert tc.get("tc_launches") >= 1
+        ref = om.computegradient(v, vm, h, hm)
+        W, a, b = opt.gradient(0)
+        assert np.max(np.abs(W - ref.weights)) < RTOL * np.abs(ref.weights).max()
+        assert np.max(np.abs(a - ref.visbias)) < RTOL * np.abs(ref.visbias).max()
+        assert np.max(np.abs(b - ref.hidbias)) < RTOL * np.abs(ref.hidbias).max()
+
+
+def test_tc_traindbm_matches_oracle(pkg, tc):
+    import copy
+    units = [300, 128, 64]
+    x, _, _ = synth.counts(400, units[0], seed=2)
+    x[0, :] += 1.0
+    dbm = synth.random_dbm(units, 4, wscale=(0.002, 0.02))
+    m = pkg.DeviceModel.from_host(to_pkg_model(pkg, dbm), tc)
+    ref = copy.deepcopy(dbm)
+    om.traindbm(ref, x, px.Rng(SEED), epochs=2, nparticles=256, learningrate=0.01)
+    pkg.traindbm_(m, x, epochs=2, nparticles=256, learningrate=0.01, ctx=tc)
+    for l in range(2):
+        got = m.get_layer(l)
+        dref = ref[l].weights - dbm[l].weights
+        assert np.max(np.abs((got.weights - dbm[l].weights) - dref)) < 0.05 * np.abs(dref).max() + 1e-9
