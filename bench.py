@@ -30,6 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 UNITS = [2000, 256, 64]
+NB_DRAM_BYTES_PER_CHAIN = 8829.0   # measured: (0.5845 + 8.2441) GB per NB down-sweep launch over 1e6 chains (ncu, round 1)
 MODEL_SEED = 3
 SEED = 20261019
 
@@ -160,10 +161,28 @@ def run_ours(args):
     achieved = flops / (k_ms * 1e-3) / 1e12
     roofline = {"kernel": "fused NB down-sweep GEMM (v|h1: tcgen05/SIMT GEMM + NB-mean + Philox NB draw)",
                 "bound": "tensor", "achieved": achieved, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tflops_burst"], "traffic": None, "peak_source": pk["source"] + ", burst (kernel timed alone)",
+                "frac": achieved / pk["tflops_burst"],
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel: 8.829e9 B per launch at 1,000,000 chains
+                # (ncu --set full capture, profiles/r01_ncu_summary.md); both count planes are written once per sweep
+                "traffic": NB_DRAM_BYTES_PER_CHAIN * n, "traffic_source": "ncu capture r01f scaled by chains",
+                "peak_source": pk["source"] + ", burst (kernel timed alone)",
                 "launch_ms": k_ms, "flops_per_launch": flops, "nb_draws_per_sec": n * UNITS[0] / (k_ms * 1e-3),
                 "note": "sampled sweeps are bound by the draw epilogue (issue/MUFU), not by the tensor pipe; see DESIGN.md"}
-    del vout
+    # the deterministic part of the sweep for comparison: the dual-source up-sweep (h1 | v, h2), tensor-bound
+    h1out = pkg.Mat(ctx, n, UNITS[1], pkg.MAT_BINARY)
+    v0, h2 = p.layer(0), p.layer(2)
+    for _ in range(2):
+        pkg._lib.check(lib.scdbm_dbm_layer(dm.h, 1, v0.h, h2.h, h1out.h, pkg.OUT_SAMPLE, 777, None, 0))
+    ctx.timer_start()
+    for i in range(reps):
+        pkg._lib.check(lib.scdbm_dbm_layer(dm.h, 1, v0.h, h2.h, h1out.h, pkg.OUT_SAMPLE, 2000 + i, None, 0))
+    u_ms = ctx.timer_stop() / reps
+    uflops = 2.0 * n * UNITS[1] * (UNITS[0] + UNITS[2])
+    roofline["upsweep"] = {"kernel": "dual-source up-sweep GEMM (h1|v,h2: count x W hi/lo = 2 plane products + Bernoulli draw)",
+                           "bound": "tensor", "launch_ms": u_ms, "achieved": uflops / (u_ms * 1e-3) / 1e12, "peak": pk["tflops_burst"],
+                           "unit": "TFLOP/s", "frac": uflops / (u_ms * 1e-3) / 1e12 / pk["tflops_burst"],
+                           "note": "algorithmic FLOPs (2MNK), not multiplied by the 2 bf16 plane products issued"}
+    del vout, h1out
 
     # ---- end to end through the public API: host model in, host uint16 cells out
     e2e = None
