@@ -122,8 +122,8 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) break;
-        __nanosleep(1000);
-        if (++spins > (1u << 22)) __trap();
+        __nanosleep(128);
+        if (++spins > (1u << 25)) __trap();
     }
 }
 __device__ __forceinline__ void mbar_wait_epi(uint32_t bar, uint32_t parity) {
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     const int nA = (p.a_hiflag[s] && p.nA[s] == 2 && p.a_hiflag[s][m0 / TC_BM] == 0u) ? 1 : p.nA[s];
                     const uint32_t tx = (uint32_t)(nA * TC_A_TILE + 2 * B_TILE);
                     for (int kb = 0; kb < p.kblocks[s]; ++kb) {
-                        mbar_wait_backoff(smem_u32(&bar_empty[stage]), phase ^ 1u);
+                        mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
                         const uint32_t full = smem_u32(&bar_full[stage]);
                         const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
                         mbar_expect_tx(full, tx);
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 for (int s = 0; s < p.nsrc; ++s) {
                     const uint32_t combos = (p.a_hiflag[s] && p.nA[s] == 2 && p.a_hiflag[s][m_blk] == 0u) ? (p.combos[s] & 0x3u) : p.combos[s];
                     for (int kb = 0; kb < p.kblocks[s]; ++kb) {
-                        mbar_wait_backoff(smem_u32(&bar_full[stage]), phase);
+                        mbar_wait(smem_u32(&bar_full[stage]), phase);
                         tc_fence_after();
                         const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
                         const uint32_t sb = sa + (uint32_t)p.a_tiles * TC_A_TILE;
@@ -303,7 +303,10 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
         }
     } else if (warp >= 4) {
         // ===================== epilogue warps
-        const int q = warp & 3, slice = (warp - 4) >> 2;
+        // TMEM lanes tie a warp to its row quadrant; the column slice rotates per tile so that no warp keeps the
+        // expensive genes for the whole kernel
+        const int q = warp & 3;
+        int slice = (warp - 4) >> 2;
         int astage = 0;
         uint32_t aphase = 0;
         float delta_local = 0.0f;
@@ -340,6 +343,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
         };
         for (int it = 0, tile; (tile = tc_tile(p, it)) >= 0; ++it) {
             const int64_t m0 = (int64_t)(tile / p.n_tiles) * TC_BM, n0 = (int64_t)(tile % p.n_tiles) * BN;
+            slice = (((warp - 4) >> 2) + it) % NS;
             if constexpr (EK == 1) {
                 // lo count plane: staged in the warp's shared-memory tile (zeroed here, patched by pass B, written
                 // out coalesced at the end of the tile).  hi plane (counts >= 256, rare): coalesced zero-fill now
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 }
                 __syncwarp();
             }
-            mbar_wait_epi(smem_u32(&bar_tfull[astage]), aphase);
+            mbar_wait(smem_u32(&bar_tfull[astage]), aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(astage * BN + slice * CW);
             const int64_t row = m0 + q * 32 + lane;
