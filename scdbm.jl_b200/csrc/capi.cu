@@ -176,19 +176,20 @@ static scdbm_mat* mat_new(scdbm_ctx* ctx, int64_t rows, int64_t cols, int kind) 
     m->v.ld = round_up(std::max<int64_t>(cols, 1), 64);
     m->v.kind = kind;
     const size_t bytes = (size_t)std::max<int64_t>(rows, 1) * m->v.ld * sizeof(__nv_bfloat16);
-    CK(cudaMalloc(&m->v.p0, bytes));
+    // stream-ordered pool allocations: repeated samples()/particles calls re-use the same memory
+    CK(cudaMallocAsync(&m->v.p0, bytes, ctx->stream));
     CK(cudaMemsetAsync(m->v.p0, 0, bytes, ctx->stream));
     if (kind != MAT_BINARY) {
-        CK(cudaMalloc(&m->v.p1, bytes));
+        CK(cudaMallocAsync(&m->v.p1, bytes, ctx->stream));
         CK(cudaMemsetAsync(m->v.p1, 0, bytes, ctx->stream));
     }
     if (kind == MAT_COUNT) {
         const size_t fb = (size_t)((std::max<int64_t>(rows, 1) + 127) / 128) * sizeof(uint32_t);
-        CK(cudaMalloc(&m->v.hiflag, fb));
+        CK(cudaMallocAsync(&m->v.hiflag, fb, ctx->stream));
         CK(cudaMemsetAsync(m->v.hiflag, 0, fb, ctx->stream));   // planes start zeroed
     }
     if (kind == MAT_REAL) {
-        CK(cudaMalloc(&m->v.f, bytes * 2));
+        CK(cudaMallocAsync(&m->v.f, bytes * 2, ctx->stream));
         CK(cudaMemsetAsync(m->v.f, 0, bytes * 2, ctx->stream));
     }
     return m;
@@ -196,10 +197,11 @@ static scdbm_mat* mat_new(scdbm_ctx* ctx, int64_t rows, int64_t cols, int kind) 
 static void mat_free(scdbm_mat* m) {
     if (!m) return;
     if (m->owns) {
-        cudaFree(m->v.p0);
-        cudaFree(m->v.p1);
-        cudaFree(m->v.f);
-        cudaFree(m->v.hiflag);
+        cudaStream_t st = m->ctx->stream;
+        if (m->v.p0) cudaFreeAsync(m->v.p0, st);
+        if (m->v.p1) cudaFreeAsync(m->v.p1, st);
+        if (m->v.f) cudaFreeAsync(m->v.f, st);
+        if (m->v.hiflag) cudaFreeAsync(m->v.hiflag, st);
         scdbm_ctx* c = m->ctx;
         delete m;
         ctx_release(c);
@@ -442,6 +444,13 @@ int32_t scdbm_ctx_create(int32_t device, uint64_t seed, void* stream, scdbm_ctx*
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     CK(cudaMalloc(&c->d_delta, sizeof(unsigned int)));
+    {   // keep freed state matrices in the device's default memory pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     tc_context_init(c->tc);
     *out = c;
     API_END
@@ -708,7 +717,7 @@ int32_t scdbm_mat_create(scdbm_ctx* c, int64_t rows, int64_t cols, int32_t kind,
 }
 int32_t scdbm_mat_destroy(scdbm_mat* m) {
     API_BEGIN
-    if (m) { cudaStreamSynchronize(m->ctx->stream); mat_free(m); }
+    if (m) mat_free(m);   // stream-ordered free: safe behind any work already queued on the context's stream
     API_END
 }
 int32_t scdbm_mat_shape(const scdbm_mat* m, int64_t* rows, int64_t* cols, int32_t* kind) {
@@ -798,13 +807,47 @@ int32_t scdbm_mat_download_u16(const scdbm_mat* m, uint16_t* x) {
     const int64_t n = m->v.rows * m->v.cols;
     if (n == 0) return SCDBM_OK;
     scdbm_ctx* c = m->ctx;
-    uint16_t* d = nullptr;
-    CK(cudaMalloc(&d, (size_t)n * sizeof(uint16_t)));
-    k_download_u16<<<grid1d(n), 256, 0, c->stream>>>(m->v, d);
-    c->launches++;
-    CK(cudaMemcpyAsync(x, d, (size_t)n * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    cudaFree(d);
+    // chunked and double-buffered: the plane -> uint16 conversion of chunk i+1 (context stream) overlaps the
+    // device -> host copy of chunk i (copy stream).  Pinned host memory gives full PCIe bandwidth.
+    const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(m->v.rows, (int64_t)(64ll << 20) / std::max<int64_t>(2 * m->v.cols, 1)));
+    uint16_t* stage[2] = {nullptr, nullptr};
+    cudaStream_t cs = nullptr;
+    cudaEvent_t ek[2] = {nullptr, nullptr}, ec[2] = {nullptr, nullptr};
+    auto cleanup = [&]() {
+        for (int i = 0; i < 2; ++i) { cudaFree(stage[i]); if (ek[i]) cudaEventDestroy(ek[i]); if (ec[i]) cudaEventDestroy(ec[i]); }
+        if (cs) cudaStreamDestroy(cs);
+    };
+    try {
+        CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaMalloc(&stage[i], (size_t)chunk_rows * m->v.cols * sizeof(uint16_t)));
+            CK(cudaEventCreateWithFlags(&ek[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ec[i], cudaEventDisableTiming));
+        }
+        int b = 0;
+        for (int64_t r0 = 0; r0 < m->v.rows; r0 += chunk_rows, b ^= 1) {
+            const int64_t nr = std::min(chunk_rows, m->v.rows - r0);
+            MatView sub = m->v;
+            sub.p0 += r0 * sub.ld;
+            if (sub.p1) sub.p1 += r0 * sub.ld;
+            if (sub.f) sub.f += r0 * sub.ld;
+            sub.rows = nr;
+            if (r0 >= 2 * chunk_rows) CK(cudaStreamWaitEvent(c->stream, ec[b], 0));   // staging buffer free again
+            k_download_u16<<<grid1d(nr * m->v.cols), 256, 0, c->stream>>>(sub, stage[b]);
+            CK(cudaGetLastError());
+            c->launches++;
+            CK(cudaEventRecord(ek[b], c->stream));
+            CK(cudaStreamWaitEvent(cs, ek[b], 0));
+            CK(cudaMemcpyAsync(x + r0 * m->v.cols, stage[b], (size_t)nr * m->v.cols * sizeof(uint16_t), cudaMemcpyDeviceToHost, cs));
+            CK(cudaEventRecord(ec[b], cs));
+        }
+        CK(cudaStreamSynchronize(cs));
+        CK(cudaStreamSynchronize(c->stream));
+    } catch (...) {
+        cleanup();
+        throw;
+    }
+    cleanup();
     API_END
 }
 
