@@ -153,6 +153,18 @@ int32_t scdbm_gibbs_negbin_rbm(scdbm_model* m, scdbm_particles* p, int32_t nstep
  * (src/gibbssampling.jl:677-689) */
 int32_t scdbm_particles_visible_potential(scdbm_model* m, scdbm_particles* p, scdbm_mat* out);
 
+/* gibbssamplecond! / gibbssamplenegativebinomial_cond! / gibbssamplecondrow! (src/gibbssampling.jl:1042-1237):
+ * Gibbs sampling with the masked visible entries reset to their initial values after every visible update.
+ * mask_rows == 0: `mask` is a byte vector over the visible units; otherwise a column-major
+ * (nparticles x nvisible) byte matrix with leading dimension ldmask. */
+int32_t scdbm_gibbs_cond(scdbm_model* m, scdbm_particles* p, const uint8_t* mask, int64_t mask_rows, int64_t ldmask,
+                         int32_t nsteps);
+/* sampledropout (src/rbmtraining.jl:289-311), applied as in gibbssamplenegativebinomial!(...; zeroinflation=true)
+ * (src/gibbssampling.jl:103-107,144-148): v .*= 1 - bernoulli(logistic(shape * (x' - mid))), x' = x (RBM form,
+ * nparams == 1) or log1p(x) (DBM form, per-gene parameters, nparams == nvisible). */
+int32_t scdbm_sample_dropout(scdbm_mat* v, const scdbm_mat* x, const double* mid, const double* shape, int32_t nparams,
+                             int32_t log1p_form, uint32_t tick, uint64_t row_offset);
+
 /* ---- mean-field (src/dbmtraining.jl:175-228) ------------------------------
  * mu: particles with nparticles == rows(x); layer 0 is set to x.  Runs until
  * the global max-abs change <= eps or maxiter iterations (maxiter <= 0: no cap).
@@ -186,6 +198,14 @@ int32_t scdbm_trainer_create(scdbm_model* m, int32_t l, int32_t batchsize, int32
 int32_t scdbm_trainer_destroy(scdbm_trainer* t);
 int32_t scdbm_trainer_clock(scdbm_trainer* t, int64_t* clock, int64_t set_to);
 int32_t scdbm_trainer_chainstate(scdbm_trainer* t, scdbm_mat** borrowed);
+/* `estimatedmean` of trainrbm! (src/rbmtraining.jl:536,575-576): when enabled, each epoch records the model
+ * means of its minibatches, in minibatch order, as a (nsamples x nvisible) matrix. */
+int32_t scdbm_trainer_track_mean(scdbm_trainer* t, int32_t enable);
+int32_t scdbm_trainer_estimated_mean(scdbm_trainer* t, scdbm_mat** borrowed);
+/* mle_for_θ (src/rbmtraining.jl:675-719), all genes at once: penalised Fisher scoring of the NB inverse
+ * dispersion of gene g from (x[:,g], mu[:,g]); theta[nvisible] out. */
+int32_t scdbm_mle_theta(const scdbm_mat* x, const scdbm_mat* mu, double lambda, int32_t maxiter, double convtol,
+                        double* theta);
 /* trainrbm!(rbm, x; ...) one epoch of minibatch CD-k / PCD
  * (src/rbmtraining.jl:498-591).  perm: the epoch's sample order (randombatchmasks,
  * :416-429), 0-based, length rows(x). */

@@ -387,6 +387,7 @@ def trainrbm(rbm, x, trainer, learningrate=0.005, cdsteps=1, upfactor=1.0, downf
             trainer.clock += 1
         vmodel = visiblepotential(rbm, hmodel, downfactor)           # :573
         hmodel = hiddenpotential(rbm, vmodel, upfactor)              # :578
+        trainer.last_vmodel = vmodel                                  # rows appended to `estimatedmean` (:575-576)
         if pcd:
             trainer.chainstate = hmodel                              # alias, :562
         grad = computegradient(v, vmodel[:thisb], h, hmodel[:thisb])  # :580-586
@@ -500,3 +501,124 @@ def fitdbm(x, rng, nhiddens=None, epochs=10, nparticles=100, learningrate=0.005,
                     trainlayers=pretraining, mu_inv_max=mu_inv_max)
     return traindbm(dbm, x, rng, epochs=epochs, nparticles=nparticles, learningrate=learningrate,
                     learningrates=learningrates, monitoring=monitoring, mu_inv_max=mu_inv_max)
+
+
+# ====================================================================== "next" rows
+# ------------------------------------------------------------- conditional Gibbs
+def gibbssamplecond(particles, bm, rng, mask, nsteps=5, mu_inv_max=sp.MU_INV_MAX):
+    """`gibbssamplecond!` / `gibbssamplenegativebinomial_cond!` / `gibbssamplecondrow!`
+    (src/gibbssampling.jl:1042-1237): after every visible update the masked visible entries are
+    reset to their initial values.  `mask`: bool vector (columns) or bool matrix (entries)."""
+    mask = np.asarray(mask, dtype=bool)
+    full = np.broadcast_to(mask[None, :], particles[0].shape) if mask.ndim == 1 else mask
+    orig = particles[0].copy()
+    ro = particles.row_offset
+    if not isinstance(bm, (list, tuple)):
+        for _ in range(nsteps):                                  # :1052-1064
+            v = samplevisible(bm, particles[1], rng, 0, particles.clock, 1.0, ro, mu_inv_max=mu_inv_max)
+            particles.clock += 1
+            v[full] = orig[full]
+            particles[0] = v
+            particles[1] = samplehidden(bm, v, rng, 1, particles.clock, 1.0, ro)
+            particles.clock += 1
+        return particles
+    L = len(particles)
+    for _ in range(nsteps):                                      # :1066-1104
+        t = particles.clock
+        new = [None] * L
+        new[0] = samplevisible(bm[0], particles[1], rng, 0, t, 1.0, ro, mu_inv_max=mu_inv_max)
+        new[0][full] = orig[full]
+        for i in range(1, L - 1):
+            p = sigm(dbm_layer_input(bm, particles, i))
+            new[i] = sp.bernoulli(p, rng.uniforms(p.shape[0], p.shape[1], px.stream_id(i), t, ro))
+        new[L - 1] = samplehidden(bm[-1], particles[L - 2], rng, L - 1, t, 1.0, ro)
+        particles[:] = new
+        particles.clock += 1
+    return particles
+
+
+# ------------------------------------------------------------- zero-inflation dropout
+def estimatedropout(x):
+    """`estimatedropout!` (src/rbmtraining.jl:271-287): binomial GLM (logit link) of the per-gene zero
+    proportion on log1p(per-gene mean); returns (intercept, slope) = (dropoutmid, dropoutshape).
+    GLM.jl's `fit(GeneralizedLinearModel, ..., Binomial())` is IRLS; restated here."""
+    logcounts = np.log1p(x.mean(axis=0))
+    y = (x == 0).mean(axis=0)
+    X = np.stack([np.ones_like(logcounts), logcounts], axis=1)
+    beta = np.zeros(2)
+    for _ in range(100):
+        eta = X @ beta
+        mu = sigm(eta)
+        w = np.maximum(mu * (1 - mu), 1e-12)
+        z = eta + (y - mu) / w
+        new = np.linalg.solve(X.T @ (w[:, None] * X), X.T @ (w * z))
+        if np.max(np.abs(new - beta)) < 1e-12:
+            beta = new
+            break
+        beta = new
+    return float(beta[0]), float(beta[1])
+
+
+def sampledropout(x, mid, shape, rng, tick, log1p_form=False, row_offset=0):
+    """`sampledropout` (src/rbmtraining.jl:289-311): 1 - bernoulli(logistic(k (x' - x0))).  RBM form: x' = x
+    and scalar (mid, shape) (:289-299); DBM form: x' = log1p(x) and per-gene parameters (:301-311)."""
+    xt = np.log1p(x) if log1p_form else x
+    mid = np.broadcast_to(np.asarray(mid, float).reshape(1, -1), (1, x.shape[1]))
+    shape = np.broadcast_to(np.asarray(shape, float).reshape(1, -1), (1, x.shape[1]))
+    p = 1.0 / (1.0 + np.exp(-shape * (xt - mid)))
+    u = rng.uniforms(x.shape[0], x.shape[1], px.stream_id(0, px.P_DROPOUT), tick, row_offset)
+    return 1.0 - sp.bernoulli(p, u)
+
+
+# ------------------------------------------------------------- NB dispersion (Fisher scoring)
+def mle_for_theta(y, mu, lam, maxiter=20, convtol=1e-6):
+    """`mle_for_θ` (src/rbmtraining.jl:675-719), unit weights: penalised Fisher scoring for the NB
+    inverse dispersion of one gene.  `y`, `mu`: (n,) or (n, V) (vectorised over genes)."""
+    from scipy.special import digamma, polygamma
+    y = np.asarray(y, float)
+    mu = np.asarray(mu, float)
+    n = y.shape[0]
+    theta = n / np.sum((y / mu - 1.0) ** 2, axis=0)
+    theta = np.atleast_1d(np.asarray(theta, float)).copy()
+    y2 = y.reshape(n, -1)
+    mu2 = mu.reshape(n, -1)
+    active = np.ones(theta.shape, dtype=bool)
+    for _ in range(maxiter):
+        theta[active] = np.maximum(theta[active], 0.01)
+        th = theta[None, :]
+        score = np.sum(-((y2 + th) / (mu2 + th) + np.log(mu2 + th) - 1 - np.log(th) - digamma(th + y2) + digamma(th)), axis=0)
+        fisher = np.sum(-(y2 + th) / (mu2 + th) ** 2 + 2 / (mu2 + th) - 1 / th - polygamma(1, th + y2) + polygamma(1, th), axis=0)
+        delta = (score + lam * 2 / theta ** 3) / (fisher + lam * 6 / theta ** 4)
+        done = np.abs(delta) <= convtol
+        step = active & ~done
+        theta[step] = theta[step] + delta[step]
+        active &= ~done
+        if not active.any():
+            break
+    return theta if y.ndim > 1 else float(theta[0])
+
+
+def fitrbm_nb(x, rng, nhidden, epochs=10, learningrate=0.005, pcd=True, cdsteps=1, batchsize=1,
+              inversedispersion=None, fisherscoring=1, lam=100.0, zeroinflation=True, upfactor=1.0, downfactor=1.0,
+              mu_inv_max=sp.MU_INV_MAX):
+    """`fitrbm(...; rbmtype = NegativeBinomialBernoulliRBM)` with the reference's NB defaults
+    (src/rbmtraining.jl:89-223): every 5th epoch the per-gene inverse dispersion is re-estimated by
+    `mle_for_θ(x[:,g], estimatedmean[:,g])` (:172-183, estimatedispersion = "gene"), where `estimatedmean`
+    is the epoch's model means in minibatch order (quirk B3: not re-aligned with the rows of x)."""
+    rbm = initrbm(x, nhidden, rng, "nb", inversedispersion)
+    trainer = RBMTrainer(rbm, batchsize, rng, pcd)
+    n = x.shape[0]
+    for epoch in range(1, epochs + 1):
+        masks = randombatchmasks(n, batchsize, rng, trainer.clock)
+        trainer.clock += 1
+        est = []
+        for mask in masks:
+            trainrbm(rbm, x, trainer, learningrate, cdsteps, upfactor, downfactor, batchmasks=[mask], mu_inv_max=mu_inv_max)
+            est.append(trainer.last_vmodel)
+        if fisherscoring != 0 and epoch % 5 == 0:
+            estimatedmean = np.vstack(est)[:n]
+            rbm.inversedispersion = mle_for_theta(x, estimatedmean, lam, maxiter=20)
+    if zeroinflation:
+        mid, shape = estimatedropout(x)
+        rbm.dropoutmid, rbm.dropoutshape = np.array([mid]), np.array([shape])
+    return rbm

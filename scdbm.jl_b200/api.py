@@ -437,6 +437,93 @@ def gibbssamplenegativebinomial_(particles, rbm, nsteps=5, upfactor=1.0, downfac
     return particles
 
 
+def gibbssamplecond_(particles, bm, fixedvars, nsteps=5, ctx=None):
+    """`gibbssamplecond!` / `gibbssamplenegativebinomial_cond!` / `gibbssamplecondrow!`
+    (src/gibbssampling.jl:1042-1237).  `fixedvars`: indices of clamped visible units, a boolean vector over
+    the visible units, or a boolean (nparticles x nvisible) matrix."""
+    m = _model(bm, ctx)
+    host = not isinstance(particles, DeviceParticles)
+    p = DeviceParticles(m, particles[0].shape[0]).upload(particles) if host else particles
+    if host:
+        p.clock = getattr(particles, "clock", 1)
+    V = m.units[0]
+    fv = np.asarray(fixedvars)
+    if fv.dtype != bool:
+        mask = np.zeros(V, dtype=bool)
+        mask[fv.astype(np.int64)] = True
+    else:
+        mask = fv
+    if mask.ndim == 1:
+        if mask.shape != (V,):
+            raise ValueError("mask must have one entry per visible unit")
+        mm = np.ascontiguousarray(mask, dtype=np.uint8)
+        check(lib().scdbm_gibbs_cond(m.h, p.h, mm.ctypes.data_as(C.POINTER(C.c_uint8)), 0, 0, nsteps))
+    else:
+        if mask.shape != (p.n, V):
+            raise ValueError("mask must have the shape of the visible particles")
+        mm = np.asfortranarray(mask, dtype=np.uint8)
+        check(lib().scdbm_gibbs_cond(m.h, p.h, mm.ctypes.data_as(C.POINTER(C.c_uint8)), p.n, p.n, nsteps))
+    if host:
+        for i, x in enumerate(p.to_host()):
+            particles[i] = x
+        if hasattr(particles, "clock"):
+            particles.clock = p.clock
+        return particles
+    return p
+
+
+gibbssamplenegativebinomial_cond_ = gibbssamplecond_
+gibbssamplecondrow_ = gibbssamplecond_
+
+
+def estimatedropout(x, ctx=None):
+    """`estimatedropout!` (src/rbmtraining.jl:271-287): binomial GLM of the per-gene zero fraction on
+    log1p(per-gene mean); the per-gene statistics come from the device, the 2-parameter IRLS runs on the
+    host.  Returns (dropoutmid, dropoutshape) = (intercept, slope)."""
+    ctx = ctx or default_context()
+    xm = x if isinstance(x, Mat) else Mat.from_host(ctx, x, L.MAT_COUNT)
+    mean, _, zf = xm.column_stats()
+    lc = np.log1p(mean)
+    X = np.stack([np.ones_like(lc), lc], axis=1)
+    beta = np.zeros(2)
+    for _ in range(100):
+        eta = X @ beta
+        mu = 1.0 / (1.0 + np.exp(-eta))
+        w = np.maximum(mu * (1 - mu), 1e-12)
+        z = eta + (zf - mu) / w
+        new = np.linalg.solve(X.T @ (w[:, None] * X), X.T @ (w * z))
+        done = np.max(np.abs(new - beta)) < 1e-12
+        beta = new
+        if done:
+            break
+    return float(beta[0]), float(beta[1])
+
+
+def sampledropout_(v, x, dropoutmid, dropoutshape, log1p_form=False, tick=0, row_offset=0, ctx=None):
+    """Applies `sampledropout` (src/rbmtraining.jl:289-311) to the visible states in place:
+    v .*= 1 - bernoulli(logistic(shape (x' - mid))) (src/gibbssampling.jl:103-107,144-148)."""
+    ctx = ctx or (v.ctx if isinstance(v, Mat) else default_context())
+    vm = v if isinstance(v, Mat) else Mat.from_host(ctx, v, L.MAT_COUNT)
+    xm = x if isinstance(x, Mat) else Mat.from_host(ctx, x, L.MAT_COUNT)
+    mid = np.atleast_1d(np.asarray(dropoutmid, dtype=np.float64))
+    shp = np.atleast_1d(np.asarray(dropoutshape, dtype=np.float64))
+    if mid.shape != shp.shape:
+        raise ValueError("dropoutmid and dropoutshape must have the same length")
+    check(lib().scdbm_sample_dropout(vm.h, xm.h, _ptr(mid), _ptr(shp), len(mid), int(log1p_form), int(tick) & 0xFFFFFFFF,
+                                     C.c_uint64(row_offset)))
+    return vm if isinstance(v, Mat) else vm.to_host()
+
+
+def mle_for_theta(x, mu, lam=100.0, maxiter=20, convtol=1e-6, ctx=None):
+    """`mle_for_θ` for every gene (src/rbmtraining.jl:675-719)."""
+    ctx = ctx or (x.ctx if isinstance(x, Mat) else default_context())
+    xm = x if isinstance(x, Mat) else Mat.from_host(ctx, x, L.MAT_COUNT)
+    mm = mu if isinstance(mu, Mat) else Mat.from_host(ctx, mu, L.MAT_REAL)
+    theta = np.zeros(xm.cols)
+    check(lib().scdbm_mle_theta(xm.h, mm.h, float(lam), int(maxiter), float(convtol), _ptr(theta)))
+    return theta
+
+
 def sampleparticles(bm, nparticles, burnin=10, row_offset=0, device=False, ctx=None):
     """src/gibbssampling.jl:646-650"""
     m = _model(bm, ctx)
@@ -587,6 +674,14 @@ class RBMTrainer:
         check(lib().scdbm_trainer_chainstate(self.h, C.byref(h)))
         return Mat.borrowed(self.model.ctx, h)
 
+    def track_mean(self, enable=True):
+        check(lib().scdbm_trainer_track_mean(self.h, int(enable)))
+
+    def estimated_mean(self):
+        h = C.c_void_p()
+        check(lib().scdbm_trainer_estimated_mean(self.h, C.byref(h)))
+        return Mat.borrowed(self.model.ctx, h)
+
     def close(self):
         if self.h:
             lib().scdbm_trainer_destroy(self.h)
@@ -625,16 +720,22 @@ def trainrbm_(model, x, trainer, learningrate=0.005, cdsteps=1, upfactor=1.0, do
 
 def fitrbm(x, nhidden=None, epochs=10, upfactor=1.0, downfactor=1.0, learningrate=0.005, learningrates=None,
            pcd=True, cdsteps=1, batchsize=1, rbmtype=BernoulliRBM, inversedispersion=None, startrbm=None,
-           monitoring=None, fisherscoring=0, zeroinflation=False, sampler=None, seed=None, device=False, ctx=None):
-    """`fitrbm` (src/rbmtraining.jl:89-223).  Dispersion re-estimation
-    (`fisherscoring`) and zero-inflation are "next" rows: any non-default value
-    raises rather than being silently ignored."""
-    if fisherscoring != 0 or zeroinflation:
-        raise NotImplementedError("fisherscoring / zeroinflation are outside the accelerated hot path (DESIGN.md)")
+           monitoring=None, fisherscoring=0, zeroinflation=False, estimatedispersion="gene", lam=100.0,
+           sampler=None, seed=None, device=False, ctx=None):
+    """`fitrbm` (src/rbmtraining.jl:89-223).  For NB RBMs `fisherscoring != 0` re-estimates the per-gene
+    inverse dispersion every 5th epoch by penalised Fisher scoring on the device (`mle_for_θ`, :172-183,
+    estimatedispersion = "gene"; the reference's other two branches are broken -- SURVEY B4 -- and raise
+    here), and `zeroinflation` fits the dropout logistic (`estimatedropout!`, :531-534).  Note that the
+    reference's own defaults are fisherscoring = 1, zeroinflation = true; they are off by default here
+    because the reference applies `mle_for_θ` to every RBM type and errors for non-NB ones."""
     ctx = ctx or default_context()
     if seed is not None:
         ctx.set("seed", seed)
     nb = rbmtype is NegativeBinomialBernoulliRBM or rbmtype == "nb"
+    if fisherscoring != 0 and estimatedispersion != "gene":
+        raise NotImplementedError('estimatedispersion must be "gene" (the other branches of the reference do not run)')
+    if (fisherscoring != 0 or zeroinflation) and not nb:
+        raise NotImplementedError("fisherscoring / zeroinflation apply to NegativeBinomialBernoulliRBM only")
     xm = x if isinstance(x, Mat) else Mat.from_host(ctx, x, L.MAT_COUNT if nb else L.MAT_REAL)
     nhidden = xm.cols if nhidden is None else nhidden
     if learningrates is None:
@@ -649,12 +750,23 @@ def fitrbm(x, nhidden=None, epochs=10, upfactor=1.0, downfactor=1.0, learningrat
         m = DeviceModel(ctx, [xm.cols, nhidden], L.VIS_NEGBIN if nb else L.VIS_BERNOULLI)
         m.init_layer(0, xm, inversedispersion, seed=int(ctx.get("seed")))
     trainer = RBMTrainer(m, batchsize, pcd)
-    for epoch in range(epochs):
-        trainrbm_(m, xm, trainer, learningrates[epoch], cdsteps, upfactor, downfactor, sampler=sampler)
+    if fisherscoring != 0:
+        trainer.track_mean(True)
+    for epoch in range(1, epochs + 1):
+        trainrbm_(m, xm, trainer, learningrates[epoch - 1], cdsteps, upfactor, downfactor, sampler=sampler)
         if monitoring is not None:
-            monitoring(m.to_host(), epoch + 1)
+            monitoring(m.to_host(), epoch)
+        if fisherscoring != 0 and epoch % 5 == 0:
+            theta = mle_for_theta(xm, trainer.estimated_mean(), lam, maxiter=20)
+            check(lib().scdbm_model_set_layer(m.h, 0, None, 0, None, None, _ptr(theta)))
     trainer.close()
-    return m if device else m.to_host()
+    if device:
+        return m
+    rbm = m.to_host()
+    if zeroinflation:
+        mid, shape = estimatedropout(xm)
+        rbm.dropoutmid, rbm.dropoutshape = np.array([mid]), np.array([shape])
+    return rbm
 
 
 @dataclass

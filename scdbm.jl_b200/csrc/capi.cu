@@ -143,6 +143,8 @@ struct scdbm_trainer {
     scdbm_opt* opt = nullptr;
     int32_t* d_perm = nullptr;
     int64_t perm_cap = 0;
+    bool track_mean = false;      // record `estimatedmean` (model means in minibatch order) each epoch
+    scdbm_mat* est = nullptr;
 };
 
 // ------------------------------------------------------------------ helpers
@@ -1394,6 +1396,7 @@ int32_t scdbm_trainer_destroy(scdbm_trainer* t) {
     if (!t) return SCDBM_OK;
     cudaStreamSynchronize(t->model->ctx->stream);
     mat_free(t->chain); mat_free(t->v); mat_free(t->h); mat_free(t->hm); mat_free(t->hs); mat_free(t->vm); mat_free(t->vs);
+    mat_free(t->est);
     scdbm_opt_destroy(t->opt);
     cudaFree(t->d_perm);
     scdbm_model* tm = t->model;
@@ -1438,6 +1441,11 @@ int32_t scdbm_rbm_train_epoch(scdbm_trainer* t, const scdbm_mat* x, const int32_
         t->perm_cap = n;
     }
     CK(cudaMemcpyAsync(t->d_perm, perm, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    if (t->track_mean && (!t->est || t->est->v.rows != n)) {
+        mat_free(t->est);
+        t->est = nullptr;
+        t->est = mat_new(c, n, L.V, MAT_REAL);
+    }
     const float up = (float)upfactor, down = (float)downfactor;
     for (int64_t s = 0; s < n; s += B) {
         const int64_t thisb = std::min<int64_t>(B, n - s);
@@ -1465,6 +1473,14 @@ int32_t scdbm_rbm_train_epoch(scdbm_trainer* t, const scdbm_mat* x, const int32_
         }
         MatView vm = rows_view(t->vm->v, mrows);
         op_visible(m, t->l, hs, vm, down, SCDBM_OUT_POTENTIAL, d);                     // :573
+        if (t->track_mean) {                                                           // :575-576 (first n rows are used)
+            const int64_t cnt = std::min<int64_t>(mrows, n - s);
+            MatView dstv = t->est->v;
+            dstv.p0 += s * dstv.ld; dstv.p1 += s * dstv.ld; dstv.f += s * dstv.ld;
+            dstv.rows = cnt;
+            k_copy_rows<<<(unsigned)cnt, 128, 0, c->stream>>>(vm, dstv, cnt);
+            c->launches++;
+        }
         MatView hm = t->pcd ? t->chain->v : rows_view(t->hm->v, mrows);
         op_hidden(m, t->l, vm, hm, up, SCDBM_OUT_POTENTIAL, d);                        // :578
         gradient_layer(t->opt, t->l, v, rows_view(vm, thisb), h, rows_view(hm, thisb), 1.0f / (float)thisb, 1.0f / (float)thisb);
@@ -1490,6 +1506,136 @@ int32_t scdbm_dbm_pcd_step(scdbm_model* m, const scdbm_mat* x, scdbm_particles* 
         gradient_layer(o, l, v, p->cur[l]->v, mu->cur[l + 1]->v, p->cur[l + 1]->v, ps, ns);
     }
     for (int l = 0; l < (int)m->L.size(); ++l) update_layer(m, o, l, (float)lr);  // :294
+    API_END
+}
+
+int32_t scdbm_trainer_track_mean(scdbm_trainer* t, int32_t enable) {
+    API_BEGIN
+    REQUIRE(t, "trainer is NULL");
+    t->track_mean = enable != 0;
+    API_END
+}
+
+int32_t scdbm_trainer_estimated_mean(scdbm_trainer* t, scdbm_mat** borrowed) {
+    API_BEGIN
+    REQUIRE(t && borrowed, "NULL argument");
+    REQUIRE(t->est, "no epoch has been trained with scdbm_trainer_track_mean enabled");
+    *borrowed = t->est;
+    API_END
+}
+
+int32_t scdbm_mle_theta(const scdbm_mat* x, const scdbm_mat* mu, double lambda, int32_t maxiter, double convtol, double* theta) {
+    API_BEGIN
+    REQUIRE(x && mu && theta, "NULL argument");
+    REQUIRE(x->v.rows == mu->v.rows && x->v.cols == mu->v.cols, "x and mu must have the same shape");
+    REQUIRE(x->v.rows > 0 && x->v.cols > 0 && maxiter >= 0, "empty input");
+    scdbm_ctx* c = x->ctx;
+    double* d = nullptr;
+    CK(cudaMalloc(&d, x->v.cols * sizeof(double)));
+    k_mle_theta<<<(unsigned)x->v.cols, 256, 0, c->stream>>>(x->v, mu->v, lambda, maxiter, convtol, d);
+    c->launches++;
+    cudaError_t e = cudaMemcpyAsync(theta, d, x->v.cols * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    CK(e);
+    API_END
+}
+
+int32_t scdbm_sample_dropout(scdbm_mat* v, const scdbm_mat* x, const double* mid, const double* shape, int32_t nparams,
+                             int32_t log1p_form, uint32_t tick, uint64_t row_offset) {
+    API_BEGIN
+    REQUIRE(v && x && mid && shape, "NULL argument");
+    REQUIRE(v->v.rows == x->v.rows && v->v.cols == x->v.cols, "the data matrix must have the shape of the visible states");
+    REQUIRE(nparams == 1 || nparams == v->v.cols, "dropout parameters: one value or one per visible unit");
+    if (v->v.rows == 0) return SCDBM_OK;
+    scdbm_ctx* c = v->ctx;
+    std::vector<float> h(2 * nparams);
+    for (int i = 0; i < nparams; ++i) { h[i] = (float)mid[i]; h[nparams + i] = (float)shape[i]; }
+    float* d = nullptr;
+    CK(cudaMalloc(&d, h.size() * sizeof(float)));
+    CK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    DrawAddr da{(uint32_t)c->seed, (uint32_t)(c->seed >> 32), tick, stream_id(0, P_DROPOUT), (uint32_t)row_offset, nullptr, 0};
+    set_hiflags(c, v->v, true);
+    k_dropout<<<grid1d(v->v.rows * ((v->v.cols + 3) / 4)), 256, 0, c->stream>>>(v->v, x->v, d, d + nparams, nparams, log1p_form, da);
+    c->launches++;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    CK(e);
+    API_END
+}
+
+int32_t scdbm_gibbs_cond(scdbm_model* m, scdbm_particles* p, const uint8_t* mask, int64_t mask_rows, int64_t ldmask, int32_t nsteps) {
+    API_BEGIN
+    REQUIRE(m && p && mask, "NULL argument");
+    REQUIRE(p->model == m && !p->real_valued, "particles belong to a different model or hold mean-field values");
+    REQUIRE(mask_rows == 0 || (mask_rows == p->n && ldmask >= p->n), "mask must be a vector over the visible units or an (nparticles x nvisible) matrix");
+    REQUIRE(nsteps >= 0, "nsteps must be non-negative");
+    if (p->n == 0 || nsteps == 0) return SCDBM_OK;
+    scdbm_ctx* c = m->ctx;
+    const int V = m->L[0].V;
+    const int nl = m->nlayers();
+    // initial visible values (origvisibles = deepcopy(particles[1]))
+    scdbm_mat* orig = mat_new(c, p->n, V, p->cur[0]->v.kind);
+    int32_t* d_cols = nullptr;
+    uint8_t* d_mask = nullptr;
+    int ncols = 0;
+    try {
+        k_copy_rows<<<(unsigned)p->n, 128, 0, c->stream>>>(p->cur[0]->v, orig->v, p->n);
+        c->launches++;
+        if (mask_rows == 0) {
+            std::vector<int32_t> cols;
+            for (int j = 0; j < V; ++j) if (mask[j]) cols.push_back(j);
+            ncols = (int)cols.size();
+            if (ncols) {
+                CK(cudaMalloc(&d_cols, ncols * sizeof(int32_t)));
+                CK(cudaMemcpyAsync(d_cols, cols.data(), ncols * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+            }
+        } else {
+            std::vector<uint8_t> rm((size_t)p->n * V);
+            for (int j = 0; j < V; ++j)
+                for (int64_t i = 0; i < p->n; ++i) rm[(size_t)i * V + j] = mask[(size_t)j * ldmask + i] ? 1 : 0;
+            CK(cudaMalloc(&d_mask, rm.size()));
+            CK(cudaMemcpyAsync(d_mask, rm.data(), rm.size(), cudaMemcpyHostToDevice, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        }
+        auto restore = [&](const MatView& dst) {
+            if (d_mask) k_restore_mask<<<grid1d(p->n * V), 256, 0, c->stream>>>(dst, orig->v, d_mask);
+            else if (ncols) k_restore_cols<<<grid1d(p->n * ncols), 256, 0, c->stream>>>(dst, orig->v, d_cols, ncols);
+            c->launches++;
+        };
+        for (int step = 0; step < nsteps; ++step) {
+            DrawCfg d;
+            d.row_offset = (uint32_t)p->row_offset;
+            if (m->L.size() == 1) {                         // src/gibbssampling.jl:1052-1064
+                d.tick = (uint32_t)p->clock; d.stream = stream_id(0);
+                op_visible(m, 0, p->cur[1]->v, p->cur[0]->v, 1.0f, SCDBM_OUT_SAMPLE, d);
+                restore(p->cur[0]->v);
+                p->clock++;
+                d.tick = (uint32_t)p->clock; d.stream = stream_id(1);
+                op_hidden(m, 0, p->cur[0]->v, p->cur[1]->v, 1.0f, SCDBM_OUT_SAMPLE, d);
+                p->clock++;
+            } else {                                        // :1066-1104
+                d.tick = (uint32_t)p->clock;
+                d.stream = stream_id(0);
+                op_visible(m, 0, p->cur[1]->v, p->nxt[0]->v, 1.0f, SCDBM_OUT_SAMPLE, d);
+                restore(p->nxt[0]->v);
+                for (int i = 1; i < nl - 1; ++i) {
+                    d.stream = stream_id(i);
+                    op_dbm_layer(m, i, &p->cur[i - 1]->v, nullptr, 0, p->cur[i + 1]->v, p->nxt[i]->v, SCDBM_OUT_SAMPLE, d, nullptr, nullptr);
+                }
+                d.stream = stream_id(nl - 1);
+                op_hidden(m, nl - 2, p->cur[nl - 2]->v, p->nxt[nl - 1]->v, 1.0f, SCDBM_OUT_SAMPLE, d);
+                std::swap(p->cur, p->nxt);
+                p->clock++;
+            }
+        }
+        CK(cudaStreamSynchronize(c->stream));
+    } catch (...) {
+        mat_free(orig); cudaFree(d_cols); cudaFree(d_mask);
+        throw;
+    }
+    mat_free(orig); cudaFree(d_cols); cudaFree(d_mask);
     API_END
 }
 

@@ -253,4 +253,97 @@ __global__ void k_colstats(MatView m, double* __restrict__ sum, double* __restri
     }
 }
 
+// ---- conditional Gibbs: reset clamped visible entries to their initial values
+__global__ void k_restore_cols(MatView dst, MatView orig, const int32_t* __restrict__ cols, int ncols) {
+    const int64_t n = dst.rows * (int64_t)ncols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / ncols, c = cols[i % ncols], j = r * dst.ld + c;
+        dst.p0[j] = orig.p0[j];
+        if (dst.p1) dst.p1[j] = orig.p1[j];
+        if (dst.hiflag && dst.p1 && __bfloat162float(orig.p1[j]) != 0.0f) dst.hiflag[r / 128] = 1u;
+    }
+}
+__global__ void k_restore_mask(MatView dst, MatView orig, const uint8_t* __restrict__ mask) {   // mask row-major [rows x cols]
+    const int64_t n = dst.rows * dst.cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (!mask[i]) continue;
+        const int64_t r = i / dst.cols, j = r * dst.ld + i % dst.cols;
+        dst.p0[j] = orig.p0[j];
+        if (dst.p1) dst.p1[j] = orig.p1[j];
+        if (dst.hiflag && dst.p1 && __bfloat162float(orig.p1[j]) != 0.0f) dst.hiflag[r / 128] = 1u;
+    }
+}
+
+// ---- zero-inflation mask (K12): v *= 1 - bernoulli(logistic(shape * (x' - mid)))
+__global__ void k_dropout(MatView v, MatView x, const float* __restrict__ mid, const float* __restrict__ shape, int nparams,
+                          int log1p_form, DrawAddr d) {
+    const int64_t groups = (v.cols + 3) / 4;
+    const int64_t n = v.rows * groups;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / groups, gidx = i % groups, c0 = gidx * 4;
+        const int nvalid = (int)min((int64_t)4, v.cols - c0);
+        const uint4 w = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)r + d.row_offset, d.tick, d.stream), d.k0, d.k1);
+        const float u[4] = {u23(w.x), u23(w.y), u23(w.z), u23(w.w)};
+        float o[4] = {0, 0, 0, 0};
+        for (int j = 0; j < nvalid; ++j) {
+            const int pi = nparams == 1 ? 0 : (int)(c0 + j);
+            float xt = mat_load(x, r, c0 + j);
+            if (log1p_form) xt = log1pf(xt);
+            const float p = 1.0f / (1.0f + expf(-shape[pi] * (xt - mid[pi])));
+            o[j] = (u[j] < p) ? 0.0f : mat_load(v, r, c0 + j);
+        }
+        mat_store4(v, r, c0, o, nvalid);
+    }
+}
+
+// ---- NB inverse dispersion by penalised Fisher scoring (mle_for_theta), one block per gene, fp64
+__device__ inline double digamma_d(double x) {
+    double r = 0.0;
+    while (x < 6.0) { r -= 1.0 / x; x += 1.0; }
+    const double f = 1.0 / (x * x);
+    return r + log(x) - 0.5 / x - f * (1.0 / 12.0 - f * (1.0 / 120.0 - f * (1.0 / 252.0 - f * (1.0 / 240.0 - f * (1.0 / 132.0)))));
+}
+__device__ inline double trigamma_d(double x) {
+    double r = 0.0;
+    while (x < 6.0) { r += 1.0 / (x * x); x += 1.0; }
+    const double f = 1.0 / (x * x), ix = 1.0 / x;
+    return r + ix + 0.5 * f + ix * f * (1.0 / 6.0 - f * (1.0 / 30.0 - f * (1.0 / 42.0 - f * (1.0 / 30.0))));
+}
+__device__ inline double block_sum(double v, double* red) {
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    return t;
+}
+__global__ void __launch_bounds__(256) k_mle_theta(MatView x, MatView mu, double lam, int maxiter, double tol, double* __restrict__ theta) {
+    __shared__ double red[8];
+    const int64_t g = blockIdx.x, n = x.rows;
+    double s = 0.0;
+    for (int64_t r = threadIdx.x; r < n; r += blockDim.x) {
+        const double y = mat_load(x, r, g), m = mat_load(mu, r, g);
+        const double t = y / m - 1.0;
+        s += t * t;
+    }
+    double th = (double)n / block_sum(s, red);
+    for (int it = 0; it < maxiter; ++it) {
+        th = fmax(th, 0.01);
+        double score = 0.0, fisher = 0.0;
+        const double dg = digamma_d(th), tg = trigamma_d(th), lth = log(th);
+        for (int64_t r = threadIdx.x; r < n; r += blockDim.x) {
+            const double y = mat_load(x, r, g), m = mat_load(mu, r, g);
+            score += -((y + th) / (m + th) + log(m + th) - 1.0 - lth - digamma_d(th + y) + dg);
+            fisher += -(y + th) / ((m + th) * (m + th)) + 2.0 / (m + th) - 1.0 / th - trigamma_d(th + y) + tg;
+        }
+        score = block_sum(score, red);
+        fisher = block_sum(fisher, red);
+        const double delta = (score + lam * 2.0 / (th * th * th)) / (fisher + lam * 6.0 / (th * th * th * th));
+        if (fabs(delta) <= tol) break;     // block-uniform: every thread holds the same sums
+        th += delta;
+    }
+    if (threadIdx.x == 0) theta[g] = th;
+}
+
 }  // namespace scdbm

@@ -434,3 +434,73 @@ def test_free_running_statistics_vs_exact(pkg, ctx):
     assert np.all(np.abs(mean - emean) < 5 * se), (mean, emean)
     assert np.all(np.abs(zf - ezf) < 5 * np.sqrt(ezf * (1 - ezf) / n) + 1e-4)
     assert np.all(np.abs(var / evar - 1) < 0.12)          # heavy-tailed (r = 0.5): 4th-moment driven
+
+
+# ------------------------------------------------ "next" rows
+def test_conditional_gibbs(pkg, ctx):
+    """gibbssamplecond! / gibbssamplecondrow! (src/gibbssampling.jl:1042-1237)."""
+    dbm = small_dbm((130, 67, 33))
+    m = dm_of(pkg, ctx, dbm)
+    n = 64
+    mask = np.zeros(130, dtype=bool)
+    mask[[0, 5, 64, 129]] = True
+    p = pkg.initparticles(m, n, device=True)
+    ref = om.initparticles(dbm, n, px.Rng(SEED))
+    orig = p.layer(0).to_host()
+    pkg.gibbssamplecond_(p, m, np.flatnonzero(mask), 3)
+    om.gibbssamplecond(ref, dbm, px.Rng(SEED), mask, 3)
+    got = p.to_host()
+    assert np.array_equal(got[0][:, mask], orig[:, mask])          # clamped entries keep their initial values
+    for a, b in zip(got, ref):
+        assert np.mean(a != b) < 5e-3
+    # entry-wise mask (gibbssamplecondrow!) on an RBM
+    rbm = dbm[0]
+    mr = dm_of(pkg, ctx, rbm)
+    full = np.random.default_rng(3).random((n, 130)) < 0.3
+    p2 = pkg.initparticles(mr, n, device=True)
+    ref2 = om.initparticles(rbm, n, px.Rng(SEED))
+    o2 = p2.layer(0).to_host()
+    pkg.gibbssamplecond_(p2, mr, full, 2)
+    om.gibbssamplecond(ref2, rbm, px.Rng(SEED), full, 2)
+    g2 = p2.to_host()
+    assert np.array_equal(g2[0][full], o2[full])
+    for a, b in zip(g2, ref2):
+        assert np.mean(a != b) < 5e-3
+
+
+def test_zero_inflation_dropout(pkg, ctx):
+    """estimatedropout! and sampledropout (src/rbmtraining.jl:271-311)."""
+    x, _, _ = synth.counts(300, 50, seed=7)
+    x[0, :] += 1.0
+    mid, shape = pkg.estimatedropout(x, ctx=ctx)
+    rmid, rshape = om.estimatedropout(x)
+    assert abs(mid - rmid) < 1e-6 * max(1, abs(rmid)) and abs(shape - rshape) < 1e-6 * max(1, abs(rshape))
+    v = np.random.default_rng(1).poisson(3.0, x.shape).astype(float)
+    for log1p_form, pm, ps in [(False, 0.5, 1.0), (True, np.linspace(0.1, 1.0, 50), np.linspace(0.5, 2.0, 50))]:
+        got = pkg.sampledropout_(v, x, pm, ps, log1p_form=log1p_form, tick=11, ctx=ctx)
+        ref = v * om.sampledropout(x, pm, ps, px.Rng(SEED), 11, log1p_form=log1p_form)
+        assert np.mean(got != ref) < 1e-3
+        assert 0.05 < (got == 0).mean() < 0.95
+
+
+def test_fisher_scoring_dispersion(pkg, ctx):
+    """mle_for_θ on the device (fp64) vs the oracle (scipy digamma/trigamma), and fitrbm with the NB defaults."""
+    g = np.random.default_rng(5)
+    n, V = 400, 24
+    theta_true = g.uniform(0.3, 5.0, V)
+    mu = g.uniform(0.2, 6.0, (n, V))
+    y = g.poisson(g.gamma(theta_true[None, :], mu / theta_true[None, :])).astype(float)
+    for lam in (100.0, 0.0):
+        got = pkg.mle_for_theta(y, mu, lam, maxiter=20, ctx=ctx)
+        ref = om.mle_for_theta(y, mu, lam, maxiter=20)
+        assert np.max(np.abs(got - ref) / np.abs(ref)) < 1e-5       # mu passes through fp32 on the device
+    x, _, _ = synth.counts(60, 20, seed=9)
+    x[0, :] += 1.0
+    ctx.set("seed", 31)
+    rbm = pkg.fitrbm(x, nhidden=8, epochs=5, batchsize=12, learningrate=1e-3, rbmtype=pkg.NegativeBinomialBernoulliRBM,
+                     fisherscoring=1, zeroinflation=True, ctx=ctx)
+    ref = om.fitrbm_nb(x, px.Rng(31), 8, epochs=5, learningrate=1e-3, batchsize=12)
+    ctx.set("seed", SEED)
+    assert np.max(np.abs(rbm.inversedispersion - ref.inversedispersion) / ref.inversedispersion) < 2e-3
+    assert abs(rbm.dropoutmid[0] - ref.dropoutmid[0]) < 1e-6 and abs(rbm.dropoutshape[0] - ref.dropoutshape[0]) < 1e-6
+    assert np.max(np.abs(rbm.weights - ref.weights)) < 1e-3 * np.abs(ref.weights).max()

@@ -187,3 +187,30 @@ def test_golden_fixture_regression():
     mu, it, _ = om.meanfield(dbm, g["v"], eps=1e-6)
     assert it == int(g["mf_iters"]) and np.array_equal(mu[2], g["mf2"])
     assert np.array_equal(oais.aislogimpweights(dbm, rng, ntemperatures=10, nparticles=16), g["aisw"])
+
+
+def test_next_rows_oracle():
+    """Conditional Gibbs clamps, dropout GLM score equations, Fisher scoring recovers the dispersion."""
+    dbm = synth.random_dbm([20, 8, 4], 2, wscale=(0.02, 0.2))
+    p = om.initparticles(dbm, 10, px.Rng(1))
+    o = p[0].copy()
+    mask = np.zeros(20, bool)
+    mask[[1, 5, 7]] = True
+    om.gibbssamplecond(p, dbm, px.Rng(1), mask, 3)
+    assert np.array_equal(p[0][:, mask], o[:, mask]) and p.clock == 4
+    x, _, _ = synth.counts(300, 40, seed=3)
+    x[0, :] += 1
+    b0, b1 = om.estimatedropout(x)
+    lc, zf = np.log1p(x.mean(0)), (x == 0).mean(0)
+    mu = 1 / (1 + np.exp(-(b0 + b1 * lc)))
+    assert abs(np.sum(zf - mu)) < 1e-8 and abs(np.sum((zf - mu) * lc)) < 1e-8      # GLM score equations
+    assert b1 < 0                                                                    # more expression, fewer zeros
+    m = om.sampledropout(x, 0.5, 1.0, px.Rng(2), 7)
+    assert set(np.unique(m)) <= {0.0, 1.0}
+    g = np.random.default_rng(5)
+    n, theta_true = 4000, np.array([0.5, 2.0, 5.0])
+    mu = g.uniform(0.5, 6.0, (n, 3))
+    y = g.poisson(g.gamma(theta_true[None, :], mu / theta_true[None, :])).astype(float)
+    th = om.mle_for_theta(y, mu, lam=0.0, maxiter=50)
+    assert np.all(np.abs(th / theta_true - 1) < 0.15)
+    assert np.isclose(om.mle_for_theta(y[:, 0], mu[:, 0], 0.0, maxiter=50), th[0])
