@@ -322,9 +322,9 @@ static void upload_uniforms(scdbm_ctx* ctx, const double* u, int64_t ldu, int64_
     cudaFree(stage);
 }
 
-static void refresh_nbc(scdbm_ctx* ctx, Layer& L) {
+static void refresh_nbc(scdbm_ctx* ctx, Layer& L, unsigned int* invalid = nullptr) {
     if (!L.nbc) return;
-    k_refresh_nbc<<<(L.V + 127) / 128, 128, 0, ctx->stream>>>(L.a, L.r, L.W, L.V, L.H, ctx->mu_inv_max, L.nbc, L.nbL);
+    k_refresh_nbc<<<(L.V + 127) / 128, 128, 0, ctx->stream>>>(L.a, L.r, L.W, L.V, L.H, ctx->mu_inv_max, L.nbc, L.nbL, invalid);
     L.nbL_mu = ctx->mu_inv_max;
     ctx->launches++;
 }
@@ -608,7 +608,16 @@ int32_t scdbm_model_set_layer(scdbm_model* m, int32_t l, const double* W, int64_
         REQUIRE(L.kind == SCDBM_VIS_NEGBIN, "inversedispersion given for a non-NB layer");
         up(L.r, r, L.V, "inversedispersion", true, false);
     }
-    refresh_nbc(m->ctx, L);
+    if (L.kind == SCDBM_VIS_NEGBIN) {
+        // validity of the NB conditional (Appendix A of SURVEY.md): x_i = a_i + sum_j W_ij h_j < 0 for every binary h,
+        // i.e. a_i + sum_j max(W_ij, 0) < 0 (the reference keeps W <= 0, a <= -1e-10: src/optimizers.jl:482-483)
+        CK(cudaMemsetAsync(m->ctx->d_delta, 0, sizeof(unsigned int), st));
+        refresh_nbc(m->ctx, L, m->ctx->d_delta);
+        unsigned int bad = 0;
+        CK(cudaMemcpyAsync(&bad, m->ctx->d_delta, sizeof(bad), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (bad && W && a) throw Err(SCDBM_EINVAL, "invalid NB parameters: visbias[i] + sum_j max(weights[i,j], 0) must be negative for every gene");
+    }
     API_END
 }
 

@@ -134,7 +134,8 @@ __global__ void k_colsum_final(const float* __restrict__ partial, int nslabs, in
 // The shortcut only holds where the draw is the single-uniform inversion: a gene whose mean can exceed
 // mu_inv_max (gamma-Poisson branch, which does not consume u) gets L = 0.
 __global__ void k_refresh_nbc(const float* __restrict__ a, const float* __restrict__ r, const float* __restrict__ W, int V,
-                              int H, float mu_inv_max, float4* __restrict__ nbc, float* __restrict__ nbL) {
+                              int H, float mu_inv_max, float4* __restrict__ nbc, float* __restrict__ nbL,
+                              unsigned int* __restrict__ invalid) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V) return;
     const float rr = r[i], c = 1e-6f / rr;
@@ -142,6 +143,7 @@ __global__ void k_refresh_nbc(const float* __restrict__ a, const float* __restri
     float pos = 0.0f;
     for (int h = 0; h < H; ++h) pos += fmaxf(W[(int64_t)i * H + h], 0.0f);
     const float xmax = a[i] + pos;
+    if (!(xmax < 0.0f) && invalid) atomicOr(invalid, 1u);   // NB validity: x = a + W h must stay negative
     float L = 0.0f;
     if (xmax < 0.0f) {
         const float om = -expm1f(xmax);

@@ -52,6 +52,10 @@ def test_error_codes(pkg, ctx):
     bad[0].visbias = np.abs(bad[0].visbias)          # NB validity needs a < 0
     with pytest.raises(pkg.ScdbmError):
         pkg.DeviceModel.from_host(bad, ctx)
+    bad2 = to_pkg_model(pkg, dbm)
+    bad2[0].weights = np.abs(bad2[0].weights) * 50    # x = a + W h could become positive: not a valid NB conditional
+    with pytest.raises(pkg.ScdbmError, match="invalid NB parameters"):
+        pkg.DeviceModel.from_host(bad2, ctx)
     m = dm_of(pkg, ctx, dbm)
     with pytest.raises(pkg.ScdbmError):              # wrong width
         pkg.hiddenpotential(m, np.zeros((3, 41)), ctx=ctx)
