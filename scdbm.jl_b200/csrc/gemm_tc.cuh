@@ -138,8 +138,8 @@ __device__ __forceinline__ void mbar_wait_epi(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) break;
-        __nanosleep(100);
-        if (++spins > (1u << 25)) __trap();
+        __nanosleep(400);
+        if (++spins > (1u << 24)) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 }
                 __syncwarp();
             }
-            mbar_wait(smem_u32(&bar_tfull[astage]), aphase);
+            mbar_wait_epi(smem_u32(&bar_tfull[astage]), aphase);   // sleeps between polls: leaves the issue slots to the stragglers
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(astage * BN + slice * CW);
             const int64_t row = m0 + q * 32 + lane;
