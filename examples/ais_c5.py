@@ -32,6 +32,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = entry.load_package()
     layers = make_model(a.units)

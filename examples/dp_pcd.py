@@ -68,6 +68,7 @@ def main():
     world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    os.environ["NCCL_DEBUG"] = "WARN"
     dist.init_process_group("nccl", device_id=dev)
     pkg = entry.load_package()
     layers = make_model(a.units)
