@@ -158,3 +158,33 @@ def test_tc_traindbm_matches_oracle(pkg, tc):
         got = m.get_layer(l)
         dref = ref[l].weights - dbm[l].weights
         assert np.max(np.abs((got.weights - dbm[l].weights) - dref)) < 0.05 * np.abs(dref).max() + 1e-9
+
+
+def test_tc_bernoulli_visible_dbm(pkg, tc):
+    """BernoulliRBM first layer (src/bmtypes.jl:17-21) through the tensor-core engine: Gibbs, mean-field, PCD."""
+    import copy
+    g = np.random.default_rng(2)
+    units = [130, 67, 33]
+    dbm = [om.BernoulliRBM(g.normal(0, 0.3, (units[i], units[i + 1])), g.normal(0, .3, units[i]), g.normal(0, .3, units[i + 1]))
+           for i in range(2)]
+    m = pkg.DeviceModel.from_host(to_pkg_model(pkg, dbm), tc)
+    n = 200
+    p = pkg.initparticles(m, n, device=True)
+    ref = om.initparticles(dbm, n, px.Rng(SEED))
+    for a, b in zip(p.to_host(), ref):
+        assert np.array_equal(a, b)
+    pkg.gibbssample_(p, m, 4)
+    om.gibbssample_dbm(ref, dbm, px.Rng(SEED), 4)
+    for a, b in zip(p.to_host(), ref):
+        assert np.mean(a != b) < 5e-3
+    x = (g.random((150, units[0])) < 0.3).astype(float)
+    got = pkg.meanfield(m, x, eps=1e-6, ctx=tc)
+    mf, _, _ = om.meanfield(dbm, x, eps=1e-6)
+    for a, b in zip(got[1:], mf[1:]):
+        assert relerr(a, b) < RTOL
+    r2 = copy.deepcopy(dbm)
+    om.traindbm(r2, x, px.Rng(SEED), epochs=2, nparticles=64, learningrate=0.05)
+    pkg.traindbm_(m, x, epochs=2, nparticles=64, learningrate=0.05, ctx=tc)
+    for l in range(2):
+        dref = r2[l].weights - dbm[l].weights
+        assert np.max(np.abs((m.get_layer(l).weights - dbm[l].weights) - dref)) < 0.05 * np.abs(dref).max() + 1e-9
