@@ -329,11 +329,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     const int rl = (int)(pos & 31u), cl = (int)(pos >> 5);
                     const int64_t r2 = cur_m0 + q * 32 + rl;
                     const int64_t c2 = cur_n0 + slice * CW + cl;
-#ifdef DBG_NO_PASSB
-                    const float k = q_u[i] + q_acc[i] * 1e-30f; (void)r2;
-#else
                     const float k = nb_entry_draw(e, q_acc[i], q_u[i], (uint32_t)r2 + e.row_offset, (uint32_t)c2);
-#endif
                     const float hi = (k >= 256.0f) ? floorf(k * (1.0f / 256.0f)) * 256.0f : 0.0f;
                     s_lo[rl * CW + cl] = __float2bfloat16_rn(k - hi);
                     if (hi > 0.0f) {                                                     // rare: count >= 256
@@ -360,9 +356,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     const int rr = idx / (CW / 8), ch = idx % (CW / 8);
                     const int64_t r2 = m0 + q * 32 + rr, c2 = n0 + slice * CW + ch * 8;
                     reinterpret_cast<uint4*>(s_lo)[idx] = make_uint4(0u, 0u, 0u, 0u);
-#ifndef DBG_NO_STORES
                     if (r2 < p.M && c2 < o.ld) *reinterpret_cast<uint4*>(o.p1 + r2 * o.ld + c2) = make_uint4(0u, 0u, 0u, 0u);
-#endif
                 }
                 __syncwarp();
             }
@@ -389,22 +383,14 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     float u[4] = {0.f, 0.f, 0.f, 0.f};
                     float4 L = make_float4(1.f, 1.f, 1.f, 1.f);
                     if (live) {
-#ifdef DBG_NO_PHILOX
-                        const uint4 w = make_uint4((uint32_t)row * 2654435761u + (uint32_t)col0, (uint32_t)row * 40503u + (uint32_t)col0 * 7u, (uint32_t)(row + col0) * 2246822519u, (uint32_t)(row ^ col0) * 3266489917u);
-#else
                         const uint4 w = philox_group(e, (uint32_t)row, (uint32_t)(col0 >> 2));
-#endif
                         u[0] = u23(w.x); u[1] = u23(w.y); u[2] = u23(w.z); u[3] = u23(w.w);
                         L = __ldg(reinterpret_cast<const float4*>(e.nbL + col0));   // padded to a multiple of 4
                     }
                     const float Lj[4] = {L.x, L.y, L.z, L.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-#ifdef DBG_NO_ENQ
-                        const bool nz = live && j < nvalid && u[j] >= Lj[j] + 2.0f;
-#else
                         const bool nz = live && j < nvalid && u[j] >= Lj[j];
-#endif
                         const uint32_t mask = __ballot_sync(0xffffffffu, nz);
                         if (nz) {
                             const int slot = qn + __popc(mask & lt);
@@ -428,9 +414,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                         const int idx = i * 32 + lane;
                         const int rr = idx / (CW / 8), ch = idx % (CW / 8);
                         const int64_t r2 = m0 + q * 32 + rr, c2 = n0 + slice * CW + ch * 8;
-#ifndef DBG_NO_STORES
                         if (r2 < p.M && c2 < o.ld) *reinterpret_cast<uint4*>(o.p0 + r2 * o.ld + c2) = reinterpret_cast<const uint4*>(s_lo)[idx];
-#endif
                     }
                     __syncwarp();
                 }
@@ -540,9 +524,6 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
     for (int s = 0; s < nsrc; ++s) {
         const MatView& a = ops[s].a;
         p.kblocks[s] = (int)((ops[s].K + TC_BK - 1) / TC_BK);
-#ifdef DBG_ONE_KBLOCK
-        p.kblocks[s] = 1;
-#endif
         p.a_hiflag[s] = (a.kind == MAT_COUNT) ? a.hiflag : nullptr;
         p.nA[s] = a.p1 ? 2 : 1;
         // plane products: binary x (hi,lo); count (lo,hi) x (hi,lo); real (hi,lo) x (hi,lo) minus lo*lo
