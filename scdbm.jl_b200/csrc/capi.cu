@@ -84,6 +84,7 @@ struct Layer {
     float4* nbc = nullptr;  // NB layer: per-gene {a, r, 1e-6/r, r-1}
     float* nbL = nullptr;   // NB layer: per-gene lower bound on the zero probability
     float nbL_mu = -1.0f;   // mu_inv_max the bound was computed for
+    const float* scale = nullptr;   // model's device scalars {s, 1/s}: power-of-two scale of the fp16 weight planes
     int64_t ldh = 0, ldv = 0;
 };
 
@@ -92,6 +93,8 @@ struct scdbm_model {
     std::vector<Layer> L;
     int64_t live = 0;
     bool closed = false;
+    float* d_scale = nullptr;          // {s, 1/s}
+    unsigned int* d_wmax = nullptr;    // max |W| over all layers (float bits)
     int units(int layer) const { return layer == 0 ? L[0].V : L[layer - 1].H; }
     int nlayers() const { return (int)L.size() + 1; }
 };
@@ -102,6 +105,8 @@ static void model_free(scdbm_model* m) {
         cudaFree(L.W); cudaFree(L.a); cudaFree(L.b); cudaFree(L.r);
         cudaFree(L.w0); cudaFree(L.w1); cudaFree(L.t0); cudaFree(L.t1); cudaFree(L.nbc); cudaFree(L.nbL);
     }
+    cudaFree(m->d_scale);
+    cudaFree(m->d_wmax);
     scdbm_ctx* c = m->ctx;
     delete m;
     ctx_release(c);
@@ -291,12 +296,13 @@ static void run_sweep(scdbm_ctx* ctx, const SweepSrc* srcs, int nsrc, int64_t M,
         REQUIRE(a.cols == K, "state width does not match the weight matrix");
         REQUIRE(a.rows >= M, "state has fewer rows than requested");
         REQUIRE((srcs[s].up ? L.H : L.V) == N, "output width does not match the weight matrix");
-        g.src[s].a = a.f ? Operand{nullptr, nullptr, a.f, a.ld, 1} : Operand{a.p0, a.p1, nullptr, a.ld, 1};
-        g.src[s].b = srcs[s].up ? Operand{nullptr, nullptr, L.W, 1, (int64_t)L.H} : Operand{nullptr, nullptr, L.W, (int64_t)L.H, 1};
+        g.src[s].a = a.f ? Operand{nullptr, nullptr, a.f, a.ld, 1, a.kind} : Operand{a.p0, a.p1, nullptr, a.ld, 1, a.kind};
+        g.src[s].b = srcs[s].up ? Operand{nullptr, nullptr, L.W, 1, (int64_t)L.H, MAT_REAL} : Operand{nullptr, nullptr, L.W, (int64_t)L.H, 1, MAT_REAL};
         g.src[s].K = K;
         g.src[s].scale = 1.0f;
     }
     g.epi = epi;
+    if (nsrc > 0) g.epi.acc_scale = srcs[0].layer->scale + 1;   // used by the tensor-core engine only
     if (M == 0 || N == 0) return;
     run_gemm(ctx, g, srcs, nsrc);
 }
@@ -329,11 +335,23 @@ static void refresh_nbc(scdbm_ctx* ctx, Layer& L, unsigned int* invalid = nullpt
     ctx->launches++;
 }
 
-static void refresh_operands(scdbm_ctx* ctx, Layer& L) {
-    dim3 grid((L.V + 31) / 32, (L.H + 31) / 32), block(32, 8);
-    k_refresh_operands<<<grid, block, 0, ctx->stream>>>(L.W, L.V, L.H, L.w0, L.w1, L.ldh, L.t0, L.t1, L.ldv);
+// All weight planes of a model share one power-of-two scale (dual-source sweeps accumulate two layers' products
+// in one TMEM accumulator), kept on the device so that training never syncs for it: max |W| over all layers ->
+// scale -> fp16 hi/lo planes of every layer.  Called whenever any fp32 master weight changed.
+static void refresh_operands(scdbm_model* m) {
+    scdbm_ctx* ctx = m->ctx;
+    CK(cudaMemsetAsync(m->d_wmax, 0, sizeof(unsigned int), ctx->stream));
+    for (auto& L : m->L) {
+        const int64_t n = (int64_t)L.V * L.H;
+        k_absmax<<<grid1d(n), 256, 0, ctx->stream>>>(L.W, n, m->d_wmax);
+    }
+    k_weight_scale<<<1, 1, 0, ctx->stream>>>(m->d_wmax, m->d_scale);
+    for (auto& L : m->L) {
+        dim3 grid((L.V + 31) / 32, (L.H + 31) / 32), block(32, 8);
+        k_refresh_operands<<<grid, block, 0, ctx->stream>>>(L.W, L.V, L.H, m->d_scale, L.w0, L.w1, L.ldh, L.t0, L.t1, L.ldv);
+    }
     CK(cudaGetLastError());
-    ctx->launches++;
+    ctx->launches += 2 * (int64_t)m->L.size() + 1;
 }
 
 // ---- the three conditional operators, with explicit Philox stream/tick
@@ -530,6 +548,13 @@ int32_t scdbm_model_create(scdbm_ctx* c, int32_t nrbms, const int32_t* units, in
     for (int i = 0; i <= nrbms; ++i) REQUIRE(units[i] > 0, "layer sizes must be positive");
     auto* m = new scdbm_model{c, {}};
     ctx_retain(c);
+    CK(cudaMalloc(&m->d_scale, 2 * sizeof(float)));
+    CK(cudaMalloc(&m->d_wmax, sizeof(unsigned int)));
+    {
+        const float one[2] = {1.0f, 1.0f};
+        CK(cudaMemcpyAsync(m->d_scale, one, sizeof(one), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
     m->L.resize(nrbms);
     for (int l = 0; l < nrbms; ++l) {
         Layer& L = m->L[l];
@@ -538,6 +563,7 @@ int32_t scdbm_model_create(scdbm_ctx* c, int32_t nrbms, const int32_t* units, in
         L.kind = (l == 0) ? visible_kind : SCDBM_VIS_BERNOULLI;
         L.ldh = round_up(L.H, 64);
         L.ldv = round_up(L.V, 64);
+        L.scale = m->d_scale;
         CK(cudaMalloc(&L.W, (size_t)L.V * L.H * sizeof(float)));
         CK(cudaMalloc(&L.a, (size_t)L.V * sizeof(float)));
         CK(cudaMalloc(&L.b, (size_t)L.H * sizeof(float)));
@@ -588,7 +614,7 @@ int32_t scdbm_model_set_layer(scdbm_model* m, int32_t l, const double* W, int64_
             }
         CK(cudaMemcpyAsync(L.W, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, st));
         CK(cudaStreamSynchronize(st));
-        refresh_operands(m->ctx, L);
+        refresh_operands(m);
     }
     auto up = [&](float* dst, const double* src, int n, const char* what, bool need_pos, bool need_neg) {
         if (!src) return;
@@ -660,7 +686,7 @@ int32_t scdbm_model_copy_layer(scdbm_model* dst, int32_t dl, scdbm_model* src, i
     CK(cudaMemcpyAsync(D.a, S.a, (size_t)D.V * sizeof(float), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(D.b, S.b, (size_t)D.H * sizeof(float), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(D.r, S.r, (size_t)D.V * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    refresh_operands(dst->ctx, D);
+    refresh_operands(dst);
     refresh_nbc(dst->ctx, D);
     API_END
 }
@@ -695,7 +721,7 @@ int32_t scdbm_model_init_layer(scdbm_model* m, int32_t l, const scdbm_mat* x, co
                                                                                   (uint32_t)seed, (uint32_t)(seed >> 32));
     CK(cudaGetLastError());
     c->launches++;
-    refresh_operands(c, L);
+    refresh_operands(m);
     // column means -> visible bias on the host (V numbers)
     float* d_sum = nullptr;
     CK(cudaMalloc(&d_sum, L.V * sizeof(float)));
@@ -1241,7 +1267,7 @@ static void gradient_layer(scdbm_opt* o, int l, const MatView& v, const MatView&
     g.nsrc = 2;
     g.M = L.V;
     g.N = L.H;
-    auto opT = [](const MatView& x) { return x.f ? Operand{nullptr, nullptr, x.f, 1, x.ld} : Operand{x.p0, x.p1, nullptr, 1, x.ld}; };
+    auto opT = [](const MatView& x) { return x.f ? Operand{nullptr, nullptr, x.f, 1, x.ld, x.kind} : Operand{x.p0, x.p1, nullptr, 1, x.ld, x.kind}; };
     g.src[0].a = opT(v);
     g.src[0].b = opT(h);
     g.src[0].K = v.rows;
@@ -1328,8 +1354,7 @@ static void update_layer(scdbm_model* m, scdbm_opt* o, int l, float lr) {
     k_update<<<grid1d(L.H), 256, 0, c->stream>>>(L.b, o->buf + o->offB[l], L.H, lr, 0.0f, 0);
     CK(cudaGetLastError());
     c->launches += 3;
-    refresh_operands(c, L);
-    refresh_nbc(c, L);
+    refresh_nbc(c, L);   // (weight planes: refresh_operands(m) once after all layers are updated)
 }
 
 int32_t scdbm_update_parameters(scdbm_model* m, scdbm_opt* o, int32_t l, double lr) {
@@ -1339,6 +1364,7 @@ int32_t scdbm_update_parameters(scdbm_model* m, scdbm_opt* o, int32_t l, double 
     REQUIRE(l < (int)m->L.size(), "layer index out of range");
     if (l >= 0) update_layer(m, o, l, (float)lr);
     else for (int i = 0; i < (int)m->L.size(); ++i) update_layer(m, o, i, (float)lr);
+    refresh_operands(m);
     API_END
 }
 
@@ -1494,6 +1520,7 @@ int32_t scdbm_rbm_train_epoch(scdbm_trainer* t, const scdbm_mat* x, const int32_
         op_hidden(m, t->l, vm, hm, up, SCDBM_OUT_POTENTIAL, d);                        // :578
         gradient_layer(t->opt, t->l, v, rows_view(vm, thisb), h, rows_view(hm, thisb), 1.0f / (float)thisb, 1.0f / (float)thisb);
         update_layer(m, t->opt, t->l, (float)lr);                                      // :586-587
+        refresh_operands(m);
     }
     CK(cudaGetLastError());
     API_END
@@ -1515,6 +1542,7 @@ int32_t scdbm_dbm_pcd_step(scdbm_model* m, const scdbm_mat* x, scdbm_particles* 
         gradient_layer(o, l, v, p->cur[l]->v, mu->cur[l + 1]->v, p->cur[l + 1]->v, ps, ns);
     }
     for (int l = 0; l < (int)m->L.size(); ++l) update_layer(m, o, l, (float)lr);  // :294
+    refresh_operands(m);
     API_END
 }
 

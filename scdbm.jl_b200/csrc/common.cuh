@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -9,11 +10,13 @@
 namespace scdbm {
 
 // ---- device state matrix: [rows x cols], row = chain/cell, unit-contiguous.
-// Stored as one or two bf16 "planes" whose SUM is the value, so that every
-// state is directly a tcgen05 kind::f16 operand without conversion:
+// Stored as one or two FP16 "planes" whose SUM is the value, so that every state is directly a tcgen05
+// kind::f16 operand without conversion (A and B operands must share one 16-bit format; FP16 holds
+// integers to 2048 exactly, which keeps the second count plane empty for counts < 2048).  The plane
+// pointers are typed __nv_bfloat16 for historical reasons; the 16-bit words are IEEE fp16 everywhere.
 //   BINARY : p0 in {0,1}                                   (exact)
-//   COUNT  : p0 = v mod 256, p1 = v - p0  (multiple of 256) (exact to 65535)
-//   REAL   : p0 = bf16(v),   p1 = bf16(v - p0)             (16 significant bits)
+//   COUNT  : p0 = v mod 2048, p1 = v - p0 (multiple of 2048) -- exact to 65535, p1 != 0 only for counts >= 2048
+//   REAL   : p0 = fp16(v),   p1 = fp16(v - p0)             (22 significant bits in fp16's normal range)
 //            plus an fp32 master copy `f` (what downloads, mean-field deltas and the
 //            CUDA-core engine read; the planes are the tensor-core operands)
 enum MatKind : int32_t { MAT_BINARY = 0, MAT_COUNT = 1, MAT_REAL = 2 };
@@ -26,6 +29,8 @@ struct MatView {
     int64_t rows, cols, ld; // ld (elements) is a multiple of 64
     int32_t kind;
 };
+
+constexpr float COUNT_BASE = 2048.0f;   // COUNT planes: p0 = v mod 2048, p1 = v - p0
 
 __host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
@@ -48,6 +53,7 @@ struct EpiParams {
     int64_t ld_add;         //   (mean-field: the hoisted x*W1)
     float factor;           // multiplies (wscale*acc + biases): up/down factor
     float wscale;           // multiplies acc only: AIS temperature (weights-only annealing)
+    const float* acc_scale; // tensor-core engine: device scalar 1/s undoing the power-of-two scale s of the fp16 weight planes
     const float* r;         // NB inverse dispersion per column
     const float4* nbc;      // NB per-gene constants {a, r, 1e-6/r, r-1} (fast sampling epilogue)
     const float* nbL;       // NB per-gene lower bound on P(v = 0 | h) over all h in [0,1]^H (two-pass epilogue)
@@ -75,6 +81,7 @@ struct Operand {
     const __nv_bfloat16* p1;
     const float* f;
     int64_t s_mn, s_k;
+    int32_t kind;          // MatKind of the planes
 };
 struct GemmSource {
     Operand a, b;

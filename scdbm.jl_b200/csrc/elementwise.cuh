@@ -25,7 +25,7 @@ __global__ void k_upload_f64(const double* __restrict__ src, int64_t lds, MatVie
             dst.p0[r * dst.ld + c] = a;
             if (dst.p1) dst.p1[r * dst.ld + c] = b;
             if (dst.f) dst.f[r * dst.ld + c] = t[threadIdx.x][j];
-            if (dst.hiflag && __bfloat162float(b) != 0.0f) dst.hiflag[r / 128] = 1u;
+            if (dst.hiflag && (__bfloat16_as_ushort(b) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 1u;
         }
     }
 }
@@ -62,20 +62,37 @@ __global__ void k_upload_uniforms(const double* __restrict__ src, int64_t lds, f
     }
 }
 
-// ---- weights: fp32 master W[V x H] row-major -> bf16 hi/lo operand planes in
-// both orientations (W[V x ldH] for the down-sweep, Wt[H x ldV] for the up-sweep)
-__global__ void k_refresh_operands(const float* __restrict__ W, int V, int H, __nv_bfloat16* w0, __nv_bfloat16* w1,
-                                   int64_t ldh, __nv_bfloat16* t0, __nv_bfloat16* t1, int64_t ldv) {
+// ---- weights: fp32 master W[V x H] row-major -> fp16 hi/lo operand planes of s*W in both orientations
+// (W[V x ldH] for the down-sweep, Wt[H x ldV] for the up-sweep).  s = scale[0] is the model's power-of-two
+// weight scale (device scalar, see k_weight_scale): it keeps |s W| <= 1024 and small weights inside fp16's
+// normal range, so hi + lo carries ~22 bits; the tensor-core epilogue multiplies the accumulator by scale[1] = 1/s.
+__global__ void k_absmax(const float* __restrict__ W, int64_t n, unsigned int* __restrict__ out_bits) {
+    float m = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(W[i]));
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out_bits, __float_as_uint(m));
+}
+__global__ void k_weight_scale(const unsigned int* __restrict__ max_bits, float* __restrict__ scale) {
+    const float m = __uint_as_float(*max_bits);
+    int e = 0;
+    if (m > 0.0f && isfinite(m)) e = 10 - (int)ceilf(log2f(m));      // |s W| <= 2^10
+    e = max(-20, min(20, e));
+    scale[0] = exp2f((float)e);
+    scale[1] = exp2f((float)-e);
+}
+__global__ void k_refresh_operands(const float* __restrict__ W, int V, int H, const float* __restrict__ scale, __nv_bfloat16* w0,
+                                   __nv_bfloat16* w1, int64_t ldh, __nv_bfloat16* t0, __nv_bfloat16* t1, int64_t ldv) {
     __shared__ float t[32][33];
+    const float s = scale[0];
     const int v0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         const int v = v0 + j, h = h0 + threadIdx.x;
         float x = 0.0f;
         if (v < V && h < H) {
-            x = W[(int64_t)v * H + h];
-            const __nv_bfloat16 a = __float2bfloat16_rn(x);
+            x = s * W[(int64_t)v * H + h];
+            const __nv_bfloat16 a = plane_encode(x);
             w0[(int64_t)v * ldh + h] = a;
-            w1[(int64_t)v * ldh + h] = __float2bfloat16_rn(x - __bfloat162float(a));
+            w1[(int64_t)v * ldh + h] = plane_encode(x - plane_decode(a));
         }
         t[j][threadIdx.x] = x;
     }
@@ -84,9 +101,9 @@ __global__ void k_refresh_operands(const float* __restrict__ W, int V, int H, __
         const int h = h0 + j, v = v0 + threadIdx.x;
         if (v < V && h < H) {
             const float x = t[threadIdx.x][j];
-            const __nv_bfloat16 a = __float2bfloat16_rn(x);
+            const __nv_bfloat16 a = plane_encode(x);
             t0[(int64_t)h * ldv + v] = a;
-            t1[(int64_t)h * ldv + v] = __float2bfloat16_rn(x - __bfloat162float(a));
+            t1[(int64_t)h * ldv + v] = plane_encode(x - plane_decode(a));
         }
     }
 }
@@ -164,7 +181,7 @@ __global__ void k_gather_rows(MatView src, const int32_t* __restrict__ idx, MatV
     const int64_t s = idx[r];
     for (int64_t c = threadIdx.x; c < dst.ld; c += blockDim.x) {
         dst.p0[r * dst.ld + c] = src.p0[s * src.ld + c];
-        if (dst.p1) dst.p1[r * dst.ld + c] = src.p1 ? src.p1[s * src.ld + c] : __float2bfloat16_rn(0.0f);
+        if (dst.p1) dst.p1[r * dst.ld + c] = src.p1 ? src.p1[s * src.ld + c] : __ushort_as_bfloat16(0);
         if (dst.f) dst.f[r * dst.ld + c] = src.f ? src.f[s * src.ld + c] : (c < src.cols ? mat_load(src, s, c) : 0.0f);
     }
 }
@@ -174,7 +191,7 @@ __global__ void k_copy_rows(MatView src, MatView dst, int64_t rows) {
     if (r >= rows) return;
     for (int64_t c = threadIdx.x; c < dst.ld; c += blockDim.x) {
         dst.p0[r * dst.ld + c] = src.p0[r * src.ld + c];
-        if (dst.p1) dst.p1[r * dst.ld + c] = src.p1 ? src.p1[r * src.ld + c] : __float2bfloat16_rn(0.0f);
+        if (dst.p1) dst.p1[r * dst.ld + c] = src.p1 ? src.p1[r * src.ld + c] : __ushort_as_bfloat16(0);
         if (dst.f) dst.f[r * dst.ld + c] = src.f ? src.f[r * src.ld + c] : (c < src.cols ? mat_load(src, r, c) : 0.0f);
     }
 }
@@ -262,7 +279,7 @@ __global__ void k_restore_cols(MatView dst, MatView orig, const int32_t* __restr
         const int64_t r = i / ncols, c = cols[i % ncols], j = r * dst.ld + c;
         dst.p0[j] = orig.p0[j];
         if (dst.p1) dst.p1[j] = orig.p1[j];
-        if (dst.hiflag && dst.p1 && __bfloat162float(orig.p1[j]) != 0.0f) dst.hiflag[r / 128] = 1u;
+        if (dst.hiflag && dst.p1 && (__bfloat16_as_ushort(orig.p1[j]) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 1u;
     }
 }
 __global__ void k_restore_mask(MatView dst, MatView orig, const uint8_t* __restrict__ mask) {   // mask row-major [rows x cols]
@@ -272,7 +289,7 @@ __global__ void k_restore_mask(MatView dst, MatView orig, const uint8_t* __restr
         const int64_t r = i / dst.cols, j = r * dst.ld + i % dst.cols;
         dst.p0[j] = orig.p0[j];
         if (dst.p1) dst.p1[j] = orig.p1[j];
-        if (dst.hiflag && dst.p1 && __bfloat162float(orig.p1[j]) != 0.0f) dst.hiflag[r / 128] = 1u;
+        if (dst.hiflag && dst.p1 && (__bfloat16_as_ushort(orig.p1[j]) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 1u;
     }
 }
 

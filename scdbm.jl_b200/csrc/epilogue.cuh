@@ -7,22 +7,28 @@
 
 namespace scdbm {
 
+// 16-bit plane word <-> float (IEEE fp16, saturating so that no plane ever holds Inf)
+__device__ __forceinline__ float plane_decode(__nv_bfloat16 w) { return __half2float(__ushort_as_half(__bfloat16_as_ushort(w))); }
+__device__ __forceinline__ __nv_bfloat16 plane_encode(float v) {
+    return __ushort_as_bfloat16(__half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f))));
+}
+
 __device__ __forceinline__ float mat_load(const MatView& m, int64_t row, int64_t col) {
     const int64_t i = row * m.ld + col;
     if (m.f) return m.f[i];
-    float v = __bfloat162float(m.p0[i]);
-    if (m.p1) v += __bfloat162float(m.p1[i]);
+    float v = plane_decode(m.p0[i]);
+    if (m.p1) v += plane_decode(m.p1[i]);
     return v;
 }
 
 __device__ __forceinline__ void split_value(int kind, float v, __nv_bfloat16& a, __nv_bfloat16& b) {
     if (kind == MAT_COUNT) {
-        const float hi = floorf(v * (1.0f / 256.0f)) * 256.0f;
-        a = __float2bfloat16_rn(v - hi);
-        b = __float2bfloat16_rn(hi);
+        const float hi = floorf(v * (1.0f / COUNT_BASE)) * COUNT_BASE;
+        a = plane_encode(v - hi);
+        b = plane_encode(hi);
     } else {
-        a = __float2bfloat16_rn(v);
-        b = __float2bfloat16_rn(v - __bfloat162float(a));
+        a = plane_encode(v);
+        b = plane_encode(v - plane_decode(a));
     }
 }
 
@@ -125,70 +131,9 @@ __device__ __forceinline__ float epi_apply4(const EpiParams& e, int64_t row, int
 }
 
 // ---- specialised sampling epilogues (tensor-core engine, Philox-fed): 4 consecutive columns
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    const __half2 v = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&v);
-}
-
-__device__ __forceinline__ void epi_nb_draw4(const EpiParams& e, int64_t row, int64_t col0, const float (&acc)[4], int nvalid) {
-    const uint4 w = philox_group(e, (uint32_t)row, (uint32_t)(col0 >> 2));
-    float u[4] = {u23(w.x), u23(w.y), u23(w.z), u23(w.w)};
-    // phase 1 (straight-line, the 4 elements interleave): P0 = p^r, q, loop constants
-    float P[4], q[4], qr1[4], k[4];
-    unsigned slow = 0;
-    const float thr = e.mu_inv_max - 1e-6f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float4 c = __ldg(e.nbc + col0 + min(j, nvalid - 1));   // {a, r, 1e-6/r, r-1}
-        const float x = fmaf(e.wscale, acc[j], c.x);
-        const float E = fast_ex2(x * 1.4426950408889634f);
-        const float om = 1.0f - E;                                   // 1 - e^x
-        // mu = r E / om + 1e-6 > mu_inv_max  <=>  r E > (mu_inv_max - 1e-6) om ;  x -> 0-: cancellation
-        if (c.y * E > thr * om || x > -0.125f) slow |= 1u << j;
-        const float p = om * fast_rcp(fmaf(c.z, om, 1.0f)) - e.pshift;   // r/(mu+r) = om/(1 + (1e-6/r) om)
-        q[j] = 1.0f - p;
-        qr1[j] = q[j] * c.w;
-        P[j] = fast_ex2(c.y * fast_lg2(p));
-        k[j] = 0.0f;
-    }
-    // phase 2: chop-down inversion; P_{k+1} = P_k q (k+r)/(k+1) = P_k (q + q (r-1)/(k+1))
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (j < nvalid) {
-            if (slow & (1u << j)) {
-                const float4 c = __ldg(e.nbc + col0 + j);
-                const RngAddr g{e.k0, e.k1, (uint32_t)row + e.row_offset, (uint32_t)(col0 + j), e.tick, e.stream & 0xFFu};
-                k[j] = nb_draw_slow(fmaf(e.wscale, acc[j], c.x), c.y, u[j], e.pshift, e.mu_inv_max, g);
-            } else {
-                // 1/(k+1) for the next step is issued one iteration ahead, off the u/P dependency chain
-                float uu = u[j], PP = P[j], kk = 0.0f, rk = 1.0f;
-                while (uu >= PP && PP > PMIN_F) {
-                    uu -= PP;
-                    kk += 1.0f;
-                    const float ratio = fmaf(qr1[j], rk, q[j]);
-                    rk = fast_rcp(kk + 1.0f);
-                    PP *= ratio;
-                }
-                k[j] = kk;
-            }
-        }
-    }
-    float lo[4], hi[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        hi[j] = (k[j] >= 256.0f) ? floorf(k[j] * (1.0f / 256.0f)) * 256.0f : 0.0f;
-        lo[j] = k[j] - hi[j];
-    }
-    const int64_t i = row * e.out.ld + col0;
-    if (nvalid == 4) {
-        *reinterpret_cast<uint2*>(e.out.p0 + i) = make_uint2(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));
-        *reinterpret_cast<uint2*>(e.out.p1 + i) = make_uint2(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]));
-    } else {
-        for (int j = 0; j < nvalid; ++j) {
-            e.out.p0[i + j] = __float2bfloat16_rn(lo[j]);
-            e.out.p1[i + j] = __float2bfloat16_rn(hi[j]);
-        }
-    }
 }
 
 // ---- two-pass NB epilogue (tensor-core engine).  Pass B: one queued element per lane.
@@ -233,9 +178,9 @@ __device__ __forceinline__ void epi_bern4(const EpiParams& e, int64_t row, int64
     }
     const int64_t i = row * e.out.ld + col0;
     if (nvalid == 4) {
-        *reinterpret_cast<uint2*>(e.out.p0 + i) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+        *reinterpret_cast<uint2*>(e.out.p0 + i) = make_uint2(pack_f16x2(o[0], o[1]), pack_f16x2(o[2], o[3]));
     } else {
-        for (int j = 0; j < nvalid; ++j) e.out.p0[i + j] = __float2bfloat16_rn(o[j]);
+        for (int j = 0; j < nvalid; ++j) e.out.p0[i + j] = plane_encode(o[j]);
     }
 }
 

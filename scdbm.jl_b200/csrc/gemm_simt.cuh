@@ -12,8 +12,8 @@ constexpr int ST_M = 64, ST_N = 64, ST_K = 16, ST_THREADS = 256;
 __device__ __forceinline__ float operand_load(const Operand& o, int64_t mn, int64_t k) {
     const int64_t i = mn * o.s_mn + k * o.s_k;
     if (o.f) return o.f[i];
-    float v = __bfloat162float(o.p0[i]);
-    if (o.p1) v += __bfloat162float(o.p1[i]);
+    float v = plane_decode(o.p0[i]);
+    if (o.p1) v += plane_decode(o.p1[i]);
     return v;
 }
 

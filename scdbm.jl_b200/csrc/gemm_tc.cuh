@@ -2,7 +2,7 @@
 //
 //   out[M x N] = epi( sum_src sum_(pa,pb) A_src,pa[M x K] * B_src,pb[N x K]^T )
 //
-// A: state planes (bf16, K-major, row = chain), B: weight planes (bf16, K-major:
+// A: state planes (fp16, K-major, row = chain), B: weight planes (fp16 of s*W, K-major:
 // W[V x ldH] for the down-sweep, Wt[H x ldV] for the up-sweep).  The hi/lo
 // operand planes are extra MMA passes into the same fp32 TMEM accumulator.
 //
@@ -10,7 +10,7 @@
 //   warp 0      TMA producer      (cp.async.bulk.tensor -> 128B-swizzled smem ring)
 //   warp 1      MMA issuer        (tcgen05.mma kind::f16, M=128, N=BN, K=16 per instruction)
 //   warp 2      TMEM allocator
-//   warps 4-19  epilogue          (tcgen05.ld 32x32b -> bias/activation/Philox draw -> bf16 planes)
+//   warps 4-19  epilogue          (tcgen05.ld 32x32b -> bias/activation/Philox draw -> fp16 planes)
 // Two TMEM accumulator stages (2 x BN columns) let the MMAs of tile j+1 run
 // under the (sampler-bound) epilogue of tile j.
 #pragma once
@@ -50,7 +50,7 @@ constexpr int TC_MAX_STAGES = 8;
 // two-pass NB epilogue: queue entries per epilogue warp ({acc, u, pos} = 12 B each), sized to the shared
 // memory left beside the GEMM stages
 __host__ __device__ constexpr int tc_qcap(int epw) { return epw > 16 ? 256 : 384; }
-// per epilogue warp: queue (12 B per entry) + a 32 x CW bf16 staging tile of the lo count plane
+// per epilogue warp: queue (12 B per entry) + a 32 x CW fp16 staging tile of the lo count plane
 __host__ __device__ constexpr int tc_epi_smem(int epw, int cw) { return tc_qcap(epw) * 12 + 32 * cw * 2; }
 constexpr int TC_SMEM_BUDGET = 200 * 1024;
 
@@ -68,6 +68,8 @@ struct TcParams {
     int32_t m_tiles, n_tiles;
     int32_t stages, stage_bytes;
     int32_t a_tiles;      // A-plane tiles reserved per stage (1 or 2)
+    int32_t pair;         // 1: a work tile is 256 rows = two M=128 MMA tiles sharing every B (weight) tile load:
+                          //    a third less L2 -> shared-memory operand traffic (the up-sweep is L2-bandwidth-bound)
     const uint32_t* a_hiflag[2];   // per source: COUNT operand's per-row-tile "hi plane in use" flags (nullptr: always)
     int32_t sched;        // 1: a CTA owns whole m-tiles and walks all n-tiles (balanced over genes, A re-used
                           //    back-to-back); 0: flat round-robin over (m, n) tiles, n fastest (few m-tiles)
@@ -195,6 +197,14 @@ __device__ __forceinline__ int tc_tile(const TcParams& p, int it) {
     return t < p.m_tiles * p.n_tiles ? t : -1;
 }
 
+// hi count plane needed for work tile m_blk of source s?  (pair: either 128-row half flagged)
+__device__ __forceinline__ bool tc_use_hi(const TcParams& p, int s, int m_blk) {
+    if (!p.a_hiflag[s] || p.nA[s] != 2) return p.nA[s] == 2;
+    if (!p.pair) return p.a_hiflag[s][m_blk] != 0u;
+    const int64_t last = (p.M + TC_BM - 1) / TC_BM - 1;
+    return p.a_hiflag[s][2 * m_blk] != 0u || (2 * m_blk + 1 <= last && p.a_hiflag[s][2 * m_blk + 1] != 0u);
+}
+
 // ------------------------------------------------------------------ kernel
 // EK: epilogue class -- 0 generic (all modes, accurate math, explicit uniforms), 1 Philox-fed NB draw
 // (fast math), 2 Philox-fed Bernoulli draw (fast math).  Separate instantiations keep each kernel's
@@ -207,8 +217,8 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
     constexpr int CW = BN / NS;          // columns per epilogue warp per tile (16 or 32)
     constexpr int B_TILE = BN * TC_BK * 2;
     constexpr int ASTAGES = 2;    // TMEM accumulator stages (4 x 128 = all 512 columns; 4 x 64 = 256)
-    constexpr uint32_t TMEM_COLS = (ASTAGES * BN <= 128) ? 128 : (ASTAGES * BN <= 256) ? 256 : 512;
-    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    constexpr uint32_t TMEM_COLS = (EK == 1) ? ((ASTAGES * BN <= 256) ? 256 : 512) : ((2 * ASTAGES * BN <= 256) ? 256 : 512);
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // c = F32, a = b = F16, K-major
     static_assert(CW == 16 || CW == 32, "epilogue slice must be 16 or 32 columns");
     (void)tmem_ld16;
 
@@ -247,19 +257,21 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
             int stage = 0;
             uint32_t phase = 0;
             for (int it = 0, tile; (tile = tc_tile(p, it)) >= 0; ++it) {
-                const int m0 = (tile / p.n_tiles) * TC_BM, n0 = (tile % p.n_tiles) * BN;
+                const int rows = p.pair ? 2 * TC_BM : TC_BM;
+                const uint32_t a_bytes = (uint32_t)rows * TC_BK * 2;
+                const int m0 = (tile / p.n_tiles) * rows, n0 = (tile % p.n_tiles) * BN;
                 for (int s = 0; s < p.nsrc; ++s) {
                     // counts >= 256 are rare: skip the hi plane of a COUNT operand unless this row tile has one
-                    const int nA = (p.a_hiflag[s] && p.nA[s] == 2 && p.a_hiflag[s][m0 / TC_BM] == 0u) ? 1 : p.nA[s];
-                    const uint32_t tx = (uint32_t)(nA * TC_A_TILE + 2 * B_TILE);
+                    const int nA = tc_use_hi(p, s, tile / p.n_tiles) ? p.nA[s] : 1;
+                    const uint32_t tx = (uint32_t)nA * a_bytes + 2 * B_TILE;
                     for (int kb = 0; kb < p.kblocks[s]; ++kb) {
                         mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
                         const uint32_t full = smem_u32(&bar_full[stage]);
                         const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
                         mbar_expect_tx(full, tx);
-                        for (int pa = 0; pa < nA; ++pa) tma_load_2d(sa + pa * TC_A_TILE, &maps.a[s][pa], full, kb * TC_BK, m0);
+                        for (int pa = 0; pa < nA; ++pa) tma_load_2d(sa + pa * a_bytes, &maps.a[s][pa], full, kb * TC_BK, m0);
                         for (int pb = 0; pb < 2; ++pb)
-                            tma_load_2d(sa + (uint32_t)p.a_tiles * TC_A_TILE + pb * B_TILE, &maps.b[s][pb], full, kb * TC_BK, n0);
+                            tma_load_2d(sa + (uint32_t)p.a_tiles * a_bytes + pb * B_TILE, &maps.b[s][pb], full, kb * TC_BK, n0);
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -274,25 +286,29 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 const int m_blk = tile / p.n_tiles;
                 mbar_wait_backoff(smem_u32(&bar_tempty[astage]), aphase ^ 1u);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)astage * BN;
+                const int halves = p.pair ? 2 : 1;
+                const uint32_t a_bytes = (uint32_t)halves * TC_A_TILE;
+                const uint32_t tmem_d = tmem_base + (uint32_t)(astage * halves) * BN;
                 uint32_t accumulate = 0;
                 for (int s = 0; s < p.nsrc; ++s) {
-                    const uint32_t combos = (p.a_hiflag[s] && p.nA[s] == 2 && p.a_hiflag[s][m_blk] == 0u) ? (p.combos[s] & 0x3u) : p.combos[s];
+                    const uint32_t combos = tc_use_hi(p, s, m_blk) ? p.combos[s] : (p.combos[s] & 0x3u);
                     for (int kb = 0; kb < p.kblocks[s]; ++kb) {
                         mbar_wait(smem_u32(&bar_full[stage]), phase);
                         tc_fence_after();
                         const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
-                        const uint32_t sb = sa + (uint32_t)p.a_tiles * TC_A_TILE;
+                        const uint32_t sb = sa + (uint32_t)p.a_tiles * a_bytes;
+                        for (int h = 0; h < halves; ++h) {        // both row halves re-use the B tile in shared memory
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            if (!((combos >> c) & 1u)) continue;
-                            const uint32_t a0 = sa + (c >> 1) * TC_A_TILE, b0 = sb + (c & 1) * B_TILE;
+                            for (int c = 0; c < 4; ++c) {
+                                if (!((combos >> c) & 1u)) continue;
+                                const uint32_t a0 = sa + (c >> 1) * a_bytes + h * TC_A_TILE, b0 = sb + (c & 1) * B_TILE;
 #pragma unroll
-                            for (int k = 0; k < TC_BK / 16; ++k) {
-                                tc_mma_f16(tmem_d, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), IDESC, accumulate);
-                                accumulate = 1;
+                                for (int k = 0; k < TC_BK / 16; ++k)
+                                    tc_mma_f16(tmem_d + h * BN, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), IDESC,
+                                               (accumulate | (uint32_t)(c != __ffs(combos) - 1) | (uint32_t)k) ? 1u : 0u);
                             }
                         }
+                        accumulate = 1;
                         tc_commit(smem_u32(&bar_empty[stage]));   // smem slot is free once these MMAs retire
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
@@ -318,6 +334,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
         __nv_bfloat16* s_lo = reinterpret_cast<__nv_bfloat16*>(q_pos + tc_qcap(EPW));   // [32][CW] staging tile, 16 B aligned
         int64_t cur_m0 = 0, cur_n0 = 0;
         const uint32_t lt = (1u << lane) - 1u;
+        const float acc_scale = p.epi.acc_scale ? __ldg(p.epi.acc_scale) : 1.0f;   // 1/s of the fp16 weight planes
         int qn = 0;
         auto drain = [&]() {
             const EpiParams& e = p.epi;
@@ -330,10 +347,10 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     const int64_t r2 = cur_m0 + q * 32 + rl;
                     const int64_t c2 = cur_n0 + slice * CW + cl;
                     const float k = nb_entry_draw(e, q_acc[i], q_u[i], (uint32_t)r2 + e.row_offset, (uint32_t)c2);
-                    const float hi = (k >= 256.0f) ? floorf(k * (1.0f / 256.0f)) * 256.0f : 0.0f;
-                    s_lo[rl * CW + cl] = __float2bfloat16_rn(k - hi);
-                    if (hi > 0.0f) {                                                     // rare: count >= 256
-                        e.out.p1[r2 * e.out.ld + c2] = __float2bfloat16_rn(hi);
+                    const float hi = (k >= COUNT_BASE) ? floorf(k * (1.0f / COUNT_BASE)) * COUNT_BASE : 0.0f;
+                    s_lo[rl * CW + cl] = plane_encode(k - hi);
+                    if (hi > 0.0f) {                                                     // rare: count >= 2048
+                        e.out.p1[r2 * e.out.ld + c2] = plane_encode(hi);
                         if (e.out.hiflag) e.out.hiflag[r2 / TC_BM] = 1u;
                     }
                 }
@@ -342,7 +359,8 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
             qn = 0;
         };
         for (int it = 0, tile; (tile = tc_tile(p, it)) >= 0; ++it) {
-            const int64_t m0 = (int64_t)(tile / p.n_tiles) * TC_BM, n0 = (int64_t)(tile % p.n_tiles) * BN;
+            const int halves = (EK != 1 && p.pair) ? 2 : 1;
+            const int64_t m0 = (int64_t)(tile / p.n_tiles) * (TC_BM * halves), n0 = (int64_t)(tile % p.n_tiles) * BN;
             slice = (((warp - 4) >> 2) + it) % NS;
             if constexpr (EK == 1) {
                 // lo count plane: staged in the warp's shared-memory tile (zeroed here, patched by pass B, written
@@ -362,7 +380,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
             }
             mbar_wait_epi(smem_u32(&bar_tfull[astage]), aphase);   // sleeps between polls: leaves the issue slots to the stragglers
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(astage * BN + slice * CW);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(astage * halves * BN + slice * CW);
             const int64_t row = m0 + q * 32 + lane;
             float rowsum = 0.0f;
             if constexpr (EK == 1) {
@@ -394,7 +412,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                         const uint32_t mask = __ballot_sync(0xffffffffu, nz);
                         if (nz) {
                             const int slot = qn + __popc(mask & lt);
-                            q_acc[slot] = __uint_as_float(r[j]);
+                            q_acc[slot] = __uint_as_float(r[j]) * acc_scale;
                             q_u[slot] = u[j];
                             q_pos[slot] = ((uint32_t)(g * 4 + j) << 5) | (uint32_t)lane;
                         }
@@ -421,25 +439,31 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
             } else {
             // one 4-column group at a time straight out of TMEM: a single copy of the epilogue body
 #pragma unroll 1
-            for (int g = 0; g < CW / 4; ++g) {
+            for (int hg = 0; hg < halves * (CW / 4); ++hg) {
+                const int h = hg / (CW / 4), g = hg % (CW / 4);     // row half (pair mode), 4-column group
+                const int64_t rowh = row + h * TC_BM;
                 uint32_t r[4];
-                tmem_ld4(taddr + g * 4, r);          // warp-collective: outside any row/column predicate
+                tmem_ld4(taddr + h * BN + g * 4, r);   // warp-collective: outside any row/column predicate
                 tmem_wait_ld();
                 const int64_t col0 = n0 + slice * CW + g * 4;
                 const int nvalid = (int)max((int64_t)0, min((int64_t)4, p.N - col0));
-                if (row < p.M && nvalid > 0) {
-                    const float acc[4] = {__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3])};
-                    if constexpr (EK == 2) epi_bern4(p.epi, row, col0, acc, nvalid);
-                    else rowsum += epi_apply4(p.epi, row, col0, acc, nvalid, delta_local);
+                if (rowh < p.M && nvalid > 0) {
+                    const float acc[4] = {__uint_as_float(r[0]) * acc_scale, __uint_as_float(r[1]) * acc_scale, __uint_as_float(r[2]) * acc_scale,
+                                          __uint_as_float(r[3]) * acc_scale};
+                    if constexpr (EK == 2) epi_bern4(p.epi, rowh, col0, acc, nvalid);
+                    else rowsum += epi_apply4(p.epi, rowh, col0, acc, nvalid, delta_local);
+                }
+                if constexpr (EK == 0) {
+                    if (g == CW / 4 - 1) {                           // end of this row's slice: flush the AIS partial row sum
+                        if (p.epi.mode == EPI_AIS_RATIO && rowh < p.M) atomicAdd(&p.epi.logw[rowh], (double)rowsum);
+                        rowsum = 0.0f;
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[astage]));   // TMEM stage can be overwritten
             if (++astage == ASTAGES) { astage = 0; aphase ^= 1u; }
-            if constexpr (EK == 0) {
-                if (p.epi.mode == EPI_AIS_RATIO && row < p.M) atomicAdd(&p.epi.logw[row], (double)rowsum);
-            }
             }
         }
         if (p.epi.prev.p0 && p.epi.delta_bits) {
@@ -462,12 +486,12 @@ inline bool tc_make_map(TcContext& t, CUtensorMap* map, const void* ptr, int64_t
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
     const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    return t.encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    return t.encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// the tcgen05 kernel tiles any sweep whose operands exist as bf16 planes
+// the tcgen05 kernel tiles any sweep whose operands exist as fp16 planes
 inline bool tc_supported(const GemmArgs& g, int nsrc) {
     if (nsrc < 1 || nsrc > 2 || g.M < 1 || g.N < 1) return false;
     for (int s = 0; s < nsrc; ++s)
@@ -481,7 +505,7 @@ inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, i
     constexpr int B_TILE = BN * TC_BK * 2;
     const int qbytes = (EK == 1) ? EPW * tc_epi_smem(EPW, BN / (EPW / 4)) : 0;
     p.a_tiles = std::max(p.nA[0], p.nsrc > 1 ? p.nA[1] : 1);
-    p.stage_bytes = p.a_tiles * TC_A_TILE + 2 * B_TILE;
+    p.stage_bytes = p.a_tiles * (p.pair ? 2 : 1) * TC_A_TILE + 2 * B_TILE;
     p.stages = std::max(1, std::min(TC_MAX_STAGES, (TC_SMEM_BUDGET + 20 * 1024 - qbytes) / p.stage_bytes));
     const int smem = p.stages * p.stage_bytes + 1024 + qbytes;
     if (!t.attr_set[slot]) {
@@ -518,7 +542,11 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
     p.nsrc = nsrc;
     p.M = g.M;
     p.N = g.N;
-    p.m_tiles = (int)((g.M + TC_BM - 1) / TC_BM);
+    // pair mode: 256-row work tiles (two MMA row tiles per weight-tile load) when there is enough work to keep
+    // every SM busy with pairs; the NB sampling kernel keeps single tiles (its two 224-column stages fill TMEM)
+    p.pair = (ek != 1 && g.M >= (int64_t)2 * TC_BM * num_sms) ? 1 : 0;
+    const int rows_per_tile = p.pair ? 2 * TC_BM : TC_BM;
+    p.m_tiles = (int)((g.M + rows_per_tile - 1) / rows_per_tile);
     p.n_tiles = (int)((g.N + BN - 1) / BN);
     p.epi = g.epi;
     for (int s = 0; s < nsrc; ++s) {
@@ -528,8 +556,8 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
         p.nA[s] = a.p1 ? 2 : 1;
         // plane products: binary x (hi,lo); count (lo,hi) x (hi,lo); real (hi,lo) x (hi,lo) minus lo*lo
         p.combos[s] = a.p1 ? (a.kind == MAT_COUNT ? 0xFu : 0x7u) : 0x3u;
-        bool ok = tc_make_map(t, &maps.a[s][0], a.p0, g.M, ops[s].K, a.ld, TC_BM);
-        ok = ok && tc_make_map(t, &maps.a[s][1], a.p1 ? a.p1 : a.p0, g.M, ops[s].K, a.ld, TC_BM);
+        bool ok = tc_make_map(t, &maps.a[s][0], a.p0, g.M, ops[s].K, a.ld, rows_per_tile);
+        ok = ok && tc_make_map(t, &maps.a[s][1], a.p1 ? a.p1 : a.p0, g.M, ops[s].K, a.ld, rows_per_tile);
         ok = ok && tc_make_map(t, &maps.b[s][0], ops[s].b0, ops[s].N, ops[s].K, ops[s].ldb, BN);
         ok = ok && tc_make_map(t, &maps.b[s][1], ops[s].b1, ops[s].N, ops[s].K, ops[s].ldb, BN);
         if (!ok) return cudaErrorInvalidValue;
@@ -569,7 +597,7 @@ struct TcGradParams {
     int32_t m_tiles, n_tiles, splits, stages;
 };
 constexpr int TG_BN = 128, TG_THREADS = 32 * (4 + 16);
-constexpr int TG_PLANE = 128 * TC_BK * 2;           // 16 KB: [2 unit blocks][64 samples][64 units] bf16
+constexpr int TG_PLANE = 128 * TC_BK * 2;           // 16 KB: [2 unit blocks][64 samples][64 units] fp16
 constexpr int TG_STAGE = 4 * TG_PLANE;              // up to 2 A planes + 2 B planes
 
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
@@ -583,8 +611,8 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
 }
 
 __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant__ TcGradMaps maps, const __grid_constant__ TcGradParams p) {
-    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TG_BN >> 3) << 17) |
-                               ((uint32_t)(TC_BM >> 4) << 24);
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(TG_BN >> 3) << 17) |
+                               ((uint32_t)(TC_BM >> 4) << 24);   // c = F32, a = b = F16, both MN-major
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_tfull, bar_tempty;
     __shared__ uint32_t tmem_holder;
@@ -737,7 +765,7 @@ inline bool tc_make_map_mn(TcContext& t, CUtensorMap* map, const void* ptr, int6
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
     const cuuint32_t box[2] = {64, (cuuint32_t)TC_BK};
     const cuuint32_t estr[2] = {1, 1};
-    return t.encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    return t.encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }

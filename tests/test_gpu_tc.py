@@ -84,14 +84,14 @@ def test_tc_meanfield_and_ais(pkg, tc):
 
 
 def test_tc_large_counts_hi_plane_flags(pkg, tc, simt):
-    """Counts >= 256 are rare in scRNA data, so the up-sweep skips the hi count plane unless the row tile
-    is flagged by the sampling epilogue.  Here a few genes have means in the hundreds: the flags must be
+    """Counts >= 2048 are rare in scRNA data, so the up-sweep skips the hi count plane unless the row tile
+    is flagged by the sampling epilogue.  Here a few genes have means in the thousands: the flags must be
     set and the hi plane used -- the chain must still match the CUDA-core engine and the oracle."""
     units = [320, 128, 64]
     dbm = synth.random_dbm(units, 5, wscale=(0.002, 0.01))
     big = np.array([3, 77, 200, 319])
-    dbm[0].visbias[big] = np.log(np.array([300.0, 500.0, 800.0, 400.0]) / (np.array([300.0, 500.0, 800.0, 400.0]) + 0.5))
-    dbm[0].weights[big] = -1e-6                          # keep these genes' means in the hundreds for every h
+    dbm[0].visbias[big] = np.log(np.array([3000.0, 5000.0, 8000.0, 4000.0]) / (np.array([3000.0, 5000.0, 8000.0, 4000.0]) + 0.5))
+    dbm[0].weights[big] = -1e-6                          # keep these genes' means in the thousands for every h
     pm = to_pkg_model(pkg, dbm)
     mt, ms = pkg.DeviceModel.from_host(pm, tc), pkg.DeviceModel.from_host(pm, simt)
     n = 300
@@ -102,7 +102,7 @@ def test_tc_large_counts_hi_plane_flags(pkg, tc, simt):
     pkg.gibbssample_(ps, ms, 4)
     om.gibbssample_dbm(ref, dbm, px.Rng(SEED), 4)
     got = pt.to_host()
-    assert (got[0][:, big] >= 256).mean() > 0.1          # the hi plane is really in use
+    assert (got[0][:, big] >= 2048).mean() > 0.1         # the hi plane is really in use
     for a, b, c in zip(got, ps.to_host(), ref):
         assert np.mean(a != b) < 3e-3
         assert np.mean(a != c) < 6e-3
@@ -188,3 +188,26 @@ def test_tc_bernoulli_visible_dbm(pkg, tc):
     for l in range(2):
         dref = r2[l].weights - dbm[l].weights
         assert np.max(np.abs((m.get_layer(l).weights - dbm[l].weights) - dref)) < 0.05 * np.abs(dref).max() + 1e-9
+
+
+def test_tc_pair_mode_large_m(pkg, tc, simt):
+    """With >= 2*128*148 rows the deterministic / Bernoulli kernels process 256-row work tiles (two MMA row
+    tiles per weight-tile load).  Ragged row count, count operand with a flagged hi plane in one tile only."""
+    n = 2 * 128 * 148 + 77
+    units = (130, 67, 33)
+    dbm = synth.random_dbm(list(units), 3, wscale=(0.002, 0.02))
+    g = np.random.default_rng(1)
+    v = g.poisson(1.5, (n, units[0])).astype(float)
+    v[n - 5, 7] = 3000.0
+    h1 = (g.random((n, units[1])) < 0.5).astype(float)
+    h2 = (g.random((n, units[2])) < 0.5).astype(float)
+    m = pkg.DeviceModel.from_host(to_pkg_model(pkg, dbm), tc)
+    assert relerr(pkg.hiddenpotential(m, v, 2.0, ctx=tc), om.hiddenpotential(dbm[0], v, 2.0)) < RTOL
+    assert relerr(pkg.visiblepotential(m, h1, ctx=tc), om.visiblepotential(dbm[0], h1)) < RTOL
+    ref = osp.sigm(om.dbm_layer_input(dbm, [v, h1, h2], 1))
+    assert relerr(pkg.dbmlayer(m, 1, v, h2, ctx=tc), ref, 1e-7) < RTOL
+    got = pkg.samplehidden(m, v, tick=5, ctx=tc)                      # Philox-fed Bernoulli kernel, pair mode
+    assert np.mean(got != om.samplehidden(dbm[0], v, px.Rng(SEED), 1, 5)) < 5e-4
+    got2 = pkg.dbmlayer(m, 1, v, h2, what=pkg.OUT_SAMPLE, tick=6, ctx=tc)
+    ms = pkg.DeviceModel.from_host(to_pkg_model(pkg, dbm), simt)
+    assert np.mean(got2 != pkg.dbmlayer(ms, 1, v, h2, what=pkg.OUT_SAMPLE, tick=6, ctx=simt)) < 5e-4
