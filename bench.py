@@ -194,42 +194,47 @@ def run_ours(args):
     roofline["upsweep"] = {"kernel": "dual-source up-sweep GEMM (h1|v,h2: count x W hi/lo = 2 plane products + Bernoulli draw)",
                            "bound": "tensor", "launch_ms": u_ms, "achieved": uflops / (u_ms * 1e-3) / 1e12, "peak": pk["tflops_burst"],
                            "unit": "TFLOP/s", "frac": uflops / (u_ms * 1e-3) / 1e12 / pk["tflops_burst"],
-                           "note": "algorithmic FLOPs (2MNK), not multiplied by the 2 bf16 plane products issued"}
+                           "note": "algorithmic FLOPs (2MNK), not multiplied by the 2 fp16 plane products issued"}
     del vout, h1out
 
     # ---- end to end through the public API: host model in, host uint16 cells out
     e2e = None
     if rank == 0 or world > 1:
-        out = torch.empty((n, UNITS[0]), dtype=torch.uint16, pin_memory=True).numpy()
+        # two pinned result buffers: batch i travels to the host (copy engine) while batch i+1 is sampled
+        outs = [torch.empty((n, UNITS[0]), dtype=torch.uint16, pin_memory=True).numpy() for _ in range(2)]
         h2d = sum(a.nbytes for l in layers for a in l.values())
-        d2h = out.nbytes
+        d2h = outs[0].nbytes
 
-        def e2e_step():
+        def e2e_step(i):
             m = pkg.DeviceModel.from_host(host_model, ctx)          # H2D: parameters
             q = pkg.sampleparticles(m, n, burnin, row_offset, device=True)
-            q.layer(0).to_host_u16(out)                               # D2H: generated cells
+            q.layer(0).to_host_u16(outs[i % 2], wait=False)           # D2H: generated cells (all of them, every step)
             q.close()
             m.close()
 
-        e2e_step()
+        e2e_step(0)
+        ctx.wait_downloads()
         barrier()
         t0 = time.perf_counter()
-        ksteps = max(1, min(args.steps, 3))
-        for _ in range(ksteps):
-            e2e_step()
+        ksteps = max(1, args.steps)
+        for i in range(ksteps):
+            e2e_step(i)
+        ctx.wait_downloads()                                          # the last batch's copy is inside the timed region
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * n * burnin * ksteps / float(dt.item()), "unit": "sweeps*chains/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": ksteps,
+               "overlap": "the device->host copy of batch i (copy engine, own stream) overlaps the sampling of batch i+1; "
+                          "two pinned result buffers; the last copy completes inside the timed region",
                "cells_per_sec": world * n * ksteps / float(dt.item())}
 
     line = {
         "metric": "Gibbs sweeps x chains / sec (synthetic-cell generation, 2-layer scDBM)",
         "value": value, "unit": "sweeps*chains/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16x2-split operands, fp32 accumulate/epilogue", "data": "synthetic (random valid parameters, seed 3)",
+        "dtype": "fp16x2-split operands (value = hi + lo plane), fp32 accumulate/epilogue", "data": "synthetic (random valid parameters, seed 3)",
         "config": {"workload": f"C3: samples(dbm {UNITS[0]}->{UNITS[1]}->{UNITS[2]}, {n} chains per GPU, burnin={burnin}); "
                                "chains sharded over GPUs, no collective",
                    "chains_per_gpu": n, "burnin": burnin, "units": UNITS,

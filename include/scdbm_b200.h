@@ -107,6 +107,12 @@ int32_t scdbm_mat_shape(const scdbm_mat* m, int64_t* rows, int64_t* cols, int32_
 int32_t scdbm_mat_upload(scdbm_mat* m, const double* x, int64_t ld);        /* column-major fp64 in   */
 int32_t scdbm_mat_download(const scdbm_mat* m, double* x, int64_t ld);      /* column-major fp64 out  */
 int32_t scdbm_mat_download_u16(const scdbm_mat* m, uint16_t* x_rowmajor);   /* compact counts, row = sample */
+/* Asynchronous form for generation pipelines (src/gibbssampling.jl:663-730 called in a loop): a uint16 snapshot of
+ * the matrix is taken in stream order and drained to `x_rowmajor` (pinned host memory) by the copy engine on a
+ * separate stream, so the next batch of chains runs while the previous one travels.  The host buffer is valid
+ * after scdbm_wait_downloads(); one download is in flight per context, a second one queues behind it. */
+int32_t scdbm_mat_download_u16_async(const scdbm_mat* m, uint16_t* x_rowmajor);
+int32_t scdbm_wait_downloads(scdbm_ctx* ctx);
 int32_t scdbm_mat_copy(scdbm_mat* dst, const scdbm_mat* src);
 /* per-column mean, variance (n-1 denominator, as Julia `var`) and zero fraction
  * (src/NegativeBinomialRBMPlots.jl:148-182,428-462,500-515) */

@@ -41,6 +41,8 @@ PROTOTYPES = {
     "scdbm_mat_upload": [P, D, I64],
     "scdbm_mat_download": [P, D, I64],
     "scdbm_mat_download_u16": [P, C.POINTER(C.c_uint16)],
+    "scdbm_mat_download_u16_async": [P, C.POINTER(C.c_uint16)],
+    "scdbm_wait_downloads": [P],
     "scdbm_mat_copy": [P, P],
     "scdbm_mat_column_stats": [P, D, D, D],
     "scdbm_hidden": [P, I32, P, P, F64, I32, U32, D, I64],

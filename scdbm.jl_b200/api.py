@@ -47,6 +47,10 @@ class Context:
     def sync(self):
         check(lib().scdbm_sync(self.h))
 
+    def wait_downloads(self):
+        """Blocks until the host buffers of `Mat.to_host_u16(out, wait=False)` calls are filled."""
+        check(lib().scdbm_wait_downloads(self.h))
+
     def timer_start(self):
         check(lib().scdbm_timer_start(self.h))
 
@@ -233,10 +237,15 @@ class Mat:
         check(lib().scdbm_mat_download(self.h, _ptr(out), max(self.rows, 1)))
         return out
 
-    def to_host_u16(self, out=None):
+    def to_host_u16(self, out=None, wait=True):
+        """Compact row-major uint16 counts.  `wait=False` (with a pinned `out`) snapshots the matrix in stream
+        order and lets the copy engine drain it while later work runs; `Context.wait_downloads()` completes it."""
         if out is None:
             out = np.zeros((self.rows, self.cols), dtype=np.uint16)
-        check(lib().scdbm_mat_download_u16(self.h, out.ctypes.data_as(C.POINTER(C.c_uint16))))
+        if out.shape != (self.rows, self.cols) or out.dtype != np.uint16 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous uint16 array of the matrix' shape")
+        f = lib().scdbm_mat_download_u16 if wait else lib().scdbm_mat_download_u16_async
+        check(f(self.h, out.ctypes.data_as(C.POINTER(C.c_uint16))))
         return out
 
     def column_stats(self):

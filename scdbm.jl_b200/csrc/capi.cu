@@ -60,11 +60,24 @@ struct scdbm_ctx {
     TcContext tc;
     float* scratch = nullptr;   // reduction workspace (column-sum partials)
     int64_t scratch_cap = 0;
+    // asynchronous downloads: dense uint16 snapshot in HBM, drained to the host by the copy engine on its own stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_conv = nullptr, ev_copy = nullptr;
+    uint16_t* stage16 = nullptr;
+    size_t stage16_cap = 0;
+    bool copy_pending = false;
     int64_t live = 0;      // child handles still alive
     bool closed = false;   // scdbm_ctx_destroy was called; freed when `live` drops to 0
 };
 static void ctx_free(scdbm_ctx* c) {
     cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamDestroy(c->copy_stream);
+        cudaEventDestroy(c->ev_conv);
+        cudaEventDestroy(c->ev_copy);
+    }
+    cudaFree(c->stage16);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaFree(c->d_delta);
@@ -885,6 +898,50 @@ int32_t scdbm_mat_download_u16(const scdbm_mat* m, uint16_t* x) {
         throw;
     }
     cleanup();
+    API_END
+}
+
+int32_t scdbm_mat_download_u16_async(const scdbm_mat* m, uint16_t* x) {
+    API_BEGIN
+    REQUIRE(m && x, "NULL argument");
+    const int64_t n = m->v.rows * m->v.cols;
+    if (n == 0) return SCDBM_OK;
+    scdbm_ctx* c = m->ctx;
+    if (!c->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_conv, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+    }
+    if (c->copy_pending) CK(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));   // the snapshot buffer is still being drained
+    const size_t bytes = (size_t)n * sizeof(uint16_t);
+    if (c->stage16_cap < bytes) {
+        CK(cudaStreamSynchronize(c->copy_stream));
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(c->stage16);
+        c->stage16 = nullptr;
+        c->stage16_cap = 0;
+        if (cudaMalloc(&c->stage16, bytes) != cudaSuccess) throw Err(SCDBM_ENOMEM, "download snapshot buffer");
+        c->stage16_cap = bytes;
+    }
+    // the snapshot is taken in stream order, so the caller may overwrite the matrix (next batch of chains) right away
+    k_download_u16<<<grid1d(n), 256, 0, c->stream>>>(m->v, c->stage16);
+    CK(cudaGetLastError());
+    c->launches++;
+    CK(cudaEventRecord(c->ev_conv, c->stream));
+    CK(cudaStreamWaitEvent(c->copy_stream, c->ev_conv, 0));
+    CK(cudaMemcpyAsync(x, c->stage16, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    CK(cudaEventRecord(c->ev_copy, c->copy_stream));
+    c->copy_pending = true;
+    API_END
+}
+
+int32_t scdbm_wait_downloads(scdbm_ctx* ctx) {
+    API_BEGIN
+    REQUIRE(ctx, "ctx is NULL");
+    if (ctx->copy_pending) {
+        CK(cudaStreamSynchronize(ctx->copy_stream));
+        ctx->copy_pending = false;
+    }
     API_END
 }
 

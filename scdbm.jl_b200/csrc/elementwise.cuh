@@ -238,9 +238,23 @@ __global__ void k_init(MatView dst, int mode, const float* __restrict__ bias, co
         if (mode == 3) {
             const uint4 w2 = philox4x32_10(make_uint4((uint32_t)gidx, (uint32_t)row + row_offset, 0u, stream_id(layer, P_INIT2)), k0, k1);
             const float u2[4] = {u23(w2.x), u23(w2.y), u23(w2.z), u23(w2.w)};
+            const uint32_t wj[4] = {w.x, w.y, w.z, w.w};
             for (int j = 0; j < nvalid; ++j) {
-                const float v0 = nb_inversion(1.0f, 1.0f, u[j], 0.0f);
-                o[j] = nb_inversion(v0, r[c0 + j], u2[j], 1e-6f);
+                // stage 1, NB(1, 1/2) by inversion: P(k) = 2^-(k+1), every chop-down subtraction is exact on the
+                // 24-bit uniform (m + 1/2) 2^-23, so k = number of leading one bits of m (24 if all 23 are set)
+                const uint32_t t = ~(wj[j] >> 9) & 0x7FFFFFu;
+                const float v0 = t ? (float)(__clz((int)t) - 9) : 24.0f;
+                // stage 2, NB(r, p = r/(v0 + r) - 1e-6) by inversion (same recurrence as nb_inversion, MUFU math)
+                const float rr = r[c0 + j];
+                const float p = rr * fast_rcp(v0 + rr) - 1e-6f, q = 1.0f - p, qr1 = q * (rr - 1.0f);
+                float P = fast_ex2(rr * fast_lg2(p)), uu = u2[j], k = 0.0f, rk = 1.0f;
+                while (uu >= P && P > PMIN_F) {
+                    uu -= P;
+                    k += 1.0f;
+                    P *= fmaf(qr1, rk, q);
+                    rk = fast_rcp(k + 1.0f);
+                }
+                o[j] = k;
             }
         } else {
             for (int j = 0; j < nvalid; ++j) {

@@ -39,6 +39,28 @@ def test_upload_download_roundtrip(pkg, ctx):
         assert relerr(pkg.Mat.from_host(ctx, r, pkg.MAT_REAL).to_host(), r) < 2e-5
 
 
+def test_async_u16_download_snapshots_in_stream_order(pkg, ctx):
+    """scdbm_mat_download_u16_async: the snapshot is taken in stream order, so the matrix may be overwritten
+    right after the call; a second download queues behind the first; buffers are valid after wait_downloads."""
+    import torch
+    g = np.random.default_rng(1)
+    x1 = g.poisson(2.0, (3000, 700)).astype(float)
+    x2 = g.poisson(40.0, (3000, 700)).astype(float)
+    x2[5, 5] = 4097
+    m = pkg.Mat.from_host(ctx, x1, pkg.MAT_COUNT)
+    o1 = torch.empty((3000, 700), dtype=torch.uint16, pin_memory=True).numpy()
+    o2 = torch.empty((3000, 700), dtype=torch.uint16, pin_memory=True).numpy()
+    m.to_host_u16(o1, wait=False)
+    m.upload(x2)                                   # overwrites the planes while the first copy may still be in flight
+    m.to_host_u16(o2, wait=False)
+    ctx.wait_downloads()
+    assert np.array_equal(o1, x1.astype(np.uint16))
+    assert np.array_equal(o2, x2.astype(np.uint16))
+    ctx.wait_downloads()                           # idempotent
+    with pytest.raises(ValueError):
+        m.to_host_u16(np.zeros((3, 3), dtype=np.uint16))
+
+
 def test_error_codes(pkg, ctx):
     with pytest.raises(pkg.ScdbmError) as e:
         pkg.Mat.from_host(ctx, np.array([[np.nan]]), pkg.MAT_REAL)
