@@ -95,7 +95,7 @@ struct Layer {
     float *W = nullptr, *a = nullptr, *b = nullptr, *r = nullptr;
     __nv_bfloat16 *w0 = nullptr, *w1 = nullptr, *t0 = nullptr, *t1 = nullptr;  // W[V x ldh], Wt[H x ldv] hi/lo
     float4* nbc = nullptr;  // NB layer: per-gene {a, r, 1e-6/r, r-1}
-    float* nbL = nullptr;   // NB layer: per-gene lower bound on the zero probability
+    uint32_t* nbT = nullptr;   // NB layer: per-gene Philox-word threshold of the zero shortcut, padded with 0xFFFFFFFF
     float nbL_mu = -1.0f;   // mu_inv_max the bound was computed for
     const float* scale = nullptr;   // model's device scalars {s, 1/s}: power-of-two scale of the fp16 weight planes
     int64_t ldh = 0, ldv = 0;
@@ -116,7 +116,7 @@ static void model_free(scdbm_model* m) {
     cudaStreamSynchronize(m->ctx->stream);
     for (auto& L : m->L) {
         cudaFree(L.W); cudaFree(L.a); cudaFree(L.b); cudaFree(L.r);
-        cudaFree(L.w0); cudaFree(L.w1); cudaFree(L.t0); cudaFree(L.t1); cudaFree(L.nbc); cudaFree(L.nbL);
+        cudaFree(L.w0); cudaFree(L.w1); cudaFree(L.t0); cudaFree(L.t1); cudaFree(L.nbc); cudaFree(L.nbT);
     }
     cudaFree(m->d_scale);
     cudaFree(m->d_wmax);
@@ -343,7 +343,7 @@ static void upload_uniforms(scdbm_ctx* ctx, const double* u, int64_t ldu, int64_
 
 static void refresh_nbc(scdbm_ctx* ctx, Layer& L, unsigned int* invalid = nullptr) {
     if (!L.nbc) return;
-    k_refresh_nbc<<<(L.V + 127) / 128, 128, 0, ctx->stream>>>(L.a, L.r, L.W, L.V, L.H, ctx->mu_inv_max, L.nbc, L.nbL, invalid);
+    k_refresh_nbc<<<(L.V + 127) / 128, 128, 0, ctx->stream>>>(L.a, L.r, L.W, L.V, L.H, ctx->mu_inv_max, L.nbc, L.nbT, invalid);
     L.nbL_mu = ctx->mu_inv_max;
     ctx->launches++;
 }
@@ -413,7 +413,7 @@ static void op_visible(scdbm_model* m, int l, const MatView& h, const MatView& o
     e.r = L.r;
     if (nb && L.nbL_mu != m->ctx->mu_inv_max) refresh_nbc(m->ctx, L);   // option changed since the last refresh
     e.nbc = L.nbc;
-    e.nbL = L.nbL;
+    e.nbT = L.nbT;
     if (d.pshift >= 0.0f) e.pshift = d.pshift;
     e.stream = d.stream; e.tick = d.tick; e.row_offset = d.row_offset;
     e.uniforms = d.uniforms; e.ldu = d.ldu;
@@ -583,8 +583,9 @@ int32_t scdbm_model_create(scdbm_ctx* c, int32_t nrbms, const int32_t* units, in
         CK(cudaMalloc(&L.r, (size_t)L.V * sizeof(float)));
         if (L.kind == SCDBM_VIS_NEGBIN) {
             CK(cudaMalloc(&L.nbc, (size_t)L.V * sizeof(float4)));
-            CK(cudaMalloc(&L.nbL, (size_t)round_up(L.V, 4) * sizeof(float)));
-            CK(cudaMemsetAsync(L.nbL, 0, (size_t)round_up(L.V, 4) * sizeof(float), c->stream));
+            // padded past the last column tile of any tile width: the padding never queues a draw
+            CK(cudaMalloc(&L.nbT, (size_t)(round_up(L.V, 256) + 256) * sizeof(uint32_t)));
+            CK(cudaMemsetAsync(L.nbT, 0xFF, (size_t)(round_up(L.V, 256) + 256) * sizeof(uint32_t), c->stream));
         }
         CK(cudaMemsetAsync(L.W, 0, (size_t)L.V * L.H * sizeof(float), c->stream));
         CK(cudaMemsetAsync(L.a, 0, (size_t)L.V * sizeof(float), c->stream));

@@ -56,7 +56,7 @@ struct EpiParams {
     const float* acc_scale; // tensor-core engine: device scalar 1/s undoing the power-of-two scale s of the fp16 weight planes
     const float* r;         // NB inverse dispersion per column
     const float4* nbc;      // NB per-gene constants {a, r, 1e-6/r, r-1} (fast sampling epilogue)
-    const float* nbL;       // NB per-gene lower bound on P(v = 0 | h) over all h in [0,1]^H (two-pass epilogue)
+    const uint32_t* nbT;    // NB per-gene threshold: Philox word < T  <=>  u < lower bound of P(v = 0 | h) over all h (two-pass epilogue)
     float pshift;           // 1e-6 for the gamma-Poisson form of the reference, else 0
     float mu_inv_max;       // inversion / gamma-Poisson switch
     uint32_t k0, k1;        // Philox key (seed)

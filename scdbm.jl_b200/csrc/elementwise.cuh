@@ -151,7 +151,7 @@ __global__ void k_colsum_final(const float* __restrict__ partial, int nslabs, in
 // The shortcut only holds where the draw is the single-uniform inversion: a gene whose mean can exceed
 // mu_inv_max (gamma-Poisson branch, which does not consume u) gets L = 0.
 __global__ void k_refresh_nbc(const float* __restrict__ a, const float* __restrict__ r, const float* __restrict__ W, int V,
-                              int H, float mu_inv_max, float4* __restrict__ nbc, float* __restrict__ nbL,
+                              int H, float mu_inv_max, float4* __restrict__ nbc, uint32_t* __restrict__ nbT,
                               unsigned int* __restrict__ invalid) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V) return;
@@ -168,7 +168,9 @@ __global__ void k_refresh_nbc(const float* __restrict__ a, const float* __restri
         const float mu_max = rr * expf(xmax) / om + 1e-6f;      // the mean is increasing in x
         if (p > 0.0f && mu_max < 0.99f * mu_inv_max) L = expf(rr * logf(p)) * (1.0f - 2e-5f);   // margin: fast-math P0 of pass B
     }
-    nbL[i] = L;
+    // u = (m + 1/2) 2^-23 with m = word >> 9 is exact in fp32, so  u < L  <=>  2m + 1 < L 2^24  <=>  m < ceil((L 2^24 - 1) / 2)
+    const double mt = ceil(((double)L * 16777216.0 - 1.0) * 0.5);
+    nbT[i] = mt >= 8388608.0 ? 0xFFFFFFFFu : (mt <= 0.0 ? 0u : ((uint32_t)mt << 9));
 }
 
 __global__ void k_fill_f32(float* p, int64_t n, float v) {

@@ -329,8 +329,8 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
         // two-pass NB epilogue state (EK == 1): per-warp queue in dynamic shared memory behind the GEMM stages
         float* q_acc = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (uint32_t)p.stages * (uint32_t)p.stage_bytes +
                                                 (uint32_t)(warp - 4) * (uint32_t)tc_epi_smem(EPW, CW));
-        float* q_u = q_acc + tc_qcap(EPW);
-        uint32_t* q_pos = reinterpret_cast<uint32_t*>(q_u + tc_qcap(EPW));
+        uint2* q_aw = reinterpret_cast<uint2*>(q_acc);                                  // {accumulator, Philox word} per queued entry
+        uint32_t* q_pos = reinterpret_cast<uint32_t*>(q_aw + tc_qcap(EPW));
         __nv_bfloat16* s_lo = reinterpret_cast<__nv_bfloat16*>(q_pos + tc_qcap(EPW));   // [32][CW] staging tile, 16 B aligned
         int64_t cur_m0 = 0, cur_n0 = 0;
         const uint32_t lt = (1u << lane) - 1u;
@@ -346,12 +346,15 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     const int rl = (int)(pos & 31u), cl = (int)(pos >> 5);
                     const int64_t r2 = cur_m0 + q * 32 + rl;
                     const int64_t c2 = cur_n0 + slice * CW + cl;
-                    const float k = nb_entry_draw(e, q_acc[i], q_u[i], (uint32_t)r2 + e.row_offset, (uint32_t)c2);
-                    const float hi = (k >= COUNT_BASE) ? floorf(k * (1.0f / COUNT_BASE)) * COUNT_BASE : 0.0f;
-                    s_lo[rl * CW + cl] = plane_encode(k - hi);
-                    if (hi > 0.0f) {                                                     // rare: count >= 2048
-                        e.out.p1[r2 * e.out.ld + c2] = plane_encode(hi);
-                        if (e.out.hiflag) e.out.hiflag[r2 / TC_BM] = 1u;
+                    if (r2 < p.M && c2 < p.N) {                                          // pass A also queues rows/columns of the tile padding
+                        const uint2 aw = q_aw[i];
+                        const float k = nb_entry_draw(e, __uint_as_float(aw.x), u23(aw.y), (uint32_t)r2 + e.row_offset, (uint32_t)c2);
+                        const float hi = (k >= COUNT_BASE) ? floorf(k * (1.0f / COUNT_BASE)) * COUNT_BASE : 0.0f;
+                        s_lo[rl * CW + cl] = plane_encode(k - hi);
+                        if (hi > 0.0f) {                                                 // rare: count >= 2048
+                            e.out.p1[r2 * e.out.ld + c2] = plane_encode(hi);
+                            if (e.out.hiflag) e.out.hiflag[r2 / TC_BM] = 1u;
+                        }
                     }
                 }
             }
@@ -386,34 +389,26 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
             if constexpr (EK == 1) {
                 // ---- two-pass NB draw.  Pass A (all elements): Philox uniform vs the per-gene lower bound L of
                 // the zero probability; u < L => 0 (placeholder zeros are stored for every element).  The
-                // other ~20 % are queued in shared memory and drawn densely, one per lane, in pass B.  The
-                // queue persists across tiles (entries carry the tile index), so a warp with expensive genes
-                // does not hold back the per-tile TMEM hand-over.
+                // other ~20 % are queued in shared memory and drawn densely, one per lane, in pass B.
                 const EpiParams& e = p.epi;
 #pragma unroll 2
                 for (int g = 0; g < CW / 4; ++g) {
                     uint32_t r[4];
                     tmem_ld4(taddr + g * 4, r);
                     tmem_wait_ld();
-                    const int64_t col0 = n0 + slice * CW + g * 4;
-                    const int nvalid = (int)max((int64_t)0, min((int64_t)4, p.N - col0));
-                    const bool live = row < p.M && nvalid > 0;
-                    float u[4] = {0.f, 0.f, 0.f, 0.f};
-                    float4 L = make_float4(1.f, 1.f, 1.f, 1.f);
-                    if (live) {
-                        const uint4 w = philox_group(e, (uint32_t)row, (uint32_t)(col0 >> 2));
-                        u[0] = u23(w.x); u[1] = u23(w.y); u[2] = u23(w.z); u[3] = u23(w.w);
-                        L = __ldg(reinterpret_cast<const float4*>(e.nbL + col0));   // padded to a multiple of 4
-                    }
-                    const float Lj[4] = {L.x, L.y, L.z, L.w};
+                    // u < L  <=>  Philox word < per-gene integer threshold T (exactly the fp32 comparison of the 23-bit
+                    // uniform; T is padded to whole tiles with 0xFFFFFFFF): no int->float conversion in pass A
+                    const uint32_t col0 = (uint32_t)n0 + (uint32_t)(slice * CW + g * 4);
+                    const uint4 w = philox_group(e, (uint32_t)row, col0 >> 2);
+                    const uint4 T = __ldg(reinterpret_cast<const uint4*>(e.nbT + col0));
+                    const uint32_t wj[4] = {w.x, w.y, w.z, w.w}, Tj[4] = {T.x, T.y, T.z, T.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const bool nz = live && j < nvalid && u[j] >= Lj[j];
+                        const bool nz = wj[j] >= Tj[j];
                         const uint32_t mask = __ballot_sync(0xffffffffu, nz);
                         if (nz) {
                             const int slot = qn + __popc(mask & lt);
-                            q_acc[slot] = __uint_as_float(r[j]) * acc_scale;
-                            q_u[slot] = u[j];
+                            q_aw[slot] = make_uint2(__float_as_uint(__uint_as_float(r[j]) * acc_scale), wj[j]);
                             q_pos[slot] = ((uint32_t)(g * 4 + j) << 5) | (uint32_t)lane;
                         }
                         qn += __popc(mask);
@@ -524,7 +519,7 @@ inline int tc_epilogue_class(const GemmArgs& g, const TcOperandPlanes* ops, int 
     const EpiParams& e = g.epi;
     int ek = 0;
     if (!e.uniforms && !e.addend && !e.prev.p0) {
-        if (e.mode == EPI_NB_DRAW && e.factor == 1.0f && e.nbc && e.nbL && !e.bias1 && e.out.p1 && !e.out.f && e.out.kind == MAT_COUNT &&
+        if (e.mode == EPI_NB_DRAW && e.factor == 1.0f && e.nbc && e.nbT && !e.bias1 && e.out.p1 && !e.out.f && e.out.kind == MAT_COUNT &&
             nsrc == 1 && ops[0].a.kind == MAT_BINARY && e.wscale >= 0.0f && e.wscale <= 1.0f) ek = 1;
         if (e.mode == EPI_SIGM_BERN && e.bias0 && !e.out.p1 && !e.out.f) ek = 2;
     }
