@@ -113,6 +113,21 @@ int32_t scdbm_mat_download_u16(const scdbm_mat* m, uint16_t* x_rowmajor);   /* c
  * after scdbm_wait_downloads(); one download is in flight per context, a second one queues behind it. */
 int32_t scdbm_mat_download_u16_async(const scdbm_mat* m, uint16_t* x_rowmajor);
 int32_t scdbm_wait_downloads(scdbm_ctx* ctx);
+
+/* Sparse data path (scRNA-seq counts are 80-92 % zeros).  The reference takes dense
+ * Matrix{Float64} data (src/rbmtraining.jl:89, src/dbmtraining.jl:108) and returns dense samples
+ * (src/gibbssampling.jl:663-730); these entry points carry the same matrices compressed.
+ *  upload_compressed: major = 0 CSR (ptr[rows+1], idx = column), 1 CSC (ptr[cols+1], idx = row: the arrays of a
+ *    Julia SparseMatrixCSC after the 1 -> 0 index shift).  Entries are validated like scdbm_mat_upload.
+ *  csr_prepare + download_csr: row-compressed download of a count / binary matrix; prepare returns nnz so the
+ *    caller can allocate indices[nnz] (uint16 or int32, index_bytes = 2 | 4) and values[nnz].
+ *  generate_counts: synthetic "10x-like" counts on the device, x_cg ~ NB(r_g, r_g/(s_c m_g + r_g)),
+ *    s_c = exp(sigma z_c); Philox-addressed by the global cell index row_offset + c (oracle/synth.py twin). */
+int32_t scdbm_mat_upload_compressed(scdbm_mat* m, int32_t major, const int64_t* ptr, const int32_t* idx, const float* val);
+int32_t scdbm_mat_csr_prepare(scdbm_mat* m, int64_t* nnz);
+int32_t scdbm_mat_download_csr(scdbm_mat* m, int64_t* indptr, void* indices, int32_t index_bytes, uint16_t* values);
+int32_t scdbm_mat_generate_counts(scdbm_mat* m, const double* gene_mean, const double* r, double sizefactor_sigma,
+                                  uint64_t seed, uint64_t row_offset);
 int32_t scdbm_mat_copy(scdbm_mat* dst, const scdbm_mat* src);
 /* per-column mean, variance (n-1 denominator, as Julia `var`) and zero fraction
  * (src/NegativeBinomialRBMPlots.jl:148-182,428-462,500-515) */

@@ -28,6 +28,8 @@ P_GAMMA = 3      # Marsaglia-Tsang gamma attempts (NB rejection branch)
 P_POIS = 4       # Poisson stage of the NB rejection branch
 P_DROPOUT = 5    # zero-inflation mask
 P_PERM = 6       # minibatch permutation
+P_DATA = 7       # synthetic count data: NB draw
+P_SIZE = 8       # synthetic count data: per-cell size factor
 
 
 def stream_id(layer, purpose=P_GIBBS, attempt=0):

@@ -43,6 +43,10 @@ PROTOTYPES = {
     "scdbm_mat_download_u16": [P, C.POINTER(C.c_uint16)],
     "scdbm_mat_download_u16_async": [P, C.POINTER(C.c_uint16)],
     "scdbm_wait_downloads": [P],
+    "scdbm_mat_upload_compressed": [P, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_float)],
+    "scdbm_mat_csr_prepare": [P, C.POINTER(C.c_int64)],
+    "scdbm_mat_download_csr": [P, C.POINTER(C.c_int64), C.c_void_p, C.c_int32, C.POINTER(C.c_uint16)],
+    "scdbm_mat_generate_counts": [P, D, D, C.c_double, C.c_uint64, C.c_uint64],
     "scdbm_mat_copy": [P, P],
     "scdbm_mat_column_stats": [P, D, D, D],
     "scdbm_hidden": [P, I32, P, P, F64, I32, U32, D, I64],

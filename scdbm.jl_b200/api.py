@@ -226,6 +226,59 @@ class Mat:
         m.upload(x)
         return m
 
+    @classmethod
+    def from_compressed(cls, ctx, shape, ptr, idx, val, kind=L.MAT_COUNT, major="csr"):
+        """Device matrix from CSR (`ptr` over rows, `idx` = columns) or CSC (`major="csc"`: `ptr` over columns,
+        `idx` = rows -- the 0-based arrays of a Julia `SparseMatrixCSC`) arrays; only the non-zeros cross PCIe."""
+        m = cls(ctx, shape[0], shape[1], kind)
+        m.upload_compressed(ptr, idx, val, major)
+        return m
+
+    @classmethod
+    def from_sparse(cls, ctx, x, kind=L.MAT_COUNT):
+        """`x`: any scipy.sparse matrix (samples x units)."""
+        if x.format == "csc":
+            return cls.from_compressed(ctx, x.shape, x.indptr, x.indices, x.data, kind, "csc")
+        x = x.tocsr()
+        return cls.from_compressed(ctx, x.shape, x.indptr, x.indices, x.data, kind, "csr")
+
+    def upload_compressed(self, ptr, idx, val, major="csr"):
+        if major not in ("csr", "csc"):
+            raise ValueError("major must be 'csr' or 'csc'")
+        ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        val = np.ascontiguousarray(val, dtype=np.float32)
+        nmajor = self.cols if major == "csc" else self.rows
+        if ptr.shape != (nmajor + 1,) or idx.shape != val.shape or idx.ndim != 1 or (len(ptr) and ptr[-1] != len(idx)):
+            raise ValueError("inconsistent compressed arrays")
+        check(lib().scdbm_mat_upload_compressed(self.h, 1 if major == "csc" else 0, ptr.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                idx.ctypes.data_as(C.POINTER(C.c_int32)), val.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def to_host_csr(self, index_dtype=None):
+        """(indptr int64[rows+1], indices, values uint16) of a count / binary matrix, columns ascending within a
+        row: the compact wire format for generated cells.  `index_dtype`: np.uint16 (default when it fits) or np.int32."""
+        if index_dtype is None:
+            index_dtype = np.uint16 if self.cols <= 65536 else np.int32
+        index_dtype = np.dtype(index_dtype)
+        if index_dtype not in (np.dtype(np.uint16), np.dtype(np.int32)):
+            raise ValueError("index_dtype must be uint16 or int32")
+        nnz = C.c_int64()
+        check(lib().scdbm_mat_csr_prepare(self.h, C.byref(nnz)))
+        indptr = np.zeros(self.rows + 1, dtype=np.int64)
+        indices = np.zeros(nnz.value, dtype=index_dtype)
+        values = np.zeros(nnz.value, dtype=np.uint16)
+        check(lib().scdbm_mat_download_csr(self.h, indptr.ctypes.data_as(C.POINTER(C.c_int64)), indices.ctypes.data_as(C.c_void_p),
+                                           index_dtype.itemsize, values.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return indptr, indices, values
+
+    def generate_counts(self, gene_mean, r, sizefactor_sigma=0.3, seed=0, row_offset=0):
+        """Fills a COUNT matrix with synthetic "10x-like" cells on the device: no host matrix exists."""
+        gm, rr = _f64(gene_mean), _f64(r)
+        if gm.shape != (self.cols,) or rr.shape != (self.cols,):
+            raise ValueError("gene_mean and r must have one entry per column")
+        check(lib().scdbm_mat_generate_counts(self.h, _ptr(gm), _ptr(rr), float(sizefactor_sigma), int(seed), int(row_offset)))
+        return self
+
     def upload(self, x):
         x = _f64(x)
         if x.shape != (self.rows, self.cols):
@@ -271,8 +324,14 @@ def _data_kind(model, layer=0):
     return L.MAT_BINARY
 
 
+def _is_sparse(x):
+    return hasattr(x, "tocsr") and hasattr(x, "format")
+
+
 def _as_mat(ctx, x, kind):
-    return x if isinstance(x, Mat) else Mat.from_host(ctx, x, kind)
+    if isinstance(x, Mat):
+        return x
+    return Mat.from_sparse(ctx, x, kind) if _is_sparse(x) else Mat.from_host(ctx, x, kind)
 
 
 def _state_kind(x, default):
@@ -490,7 +549,7 @@ def estimatedropout(x, ctx=None):
     log1p(per-gene mean); the per-gene statistics come from the device, the 2-parameter IRLS runs on the
     host.  Returns (dropoutmid, dropoutshape) = (intercept, slope)."""
     ctx = ctx or default_context()
-    xm = x if isinstance(x, Mat) else Mat.from_host(ctx, x, L.MAT_COUNT)
+    xm = _as_mat(ctx, x, L.MAT_COUNT)
     mean, _, zf = xm.column_stats()
     lc = np.log1p(mean)
     X = np.stack([np.ones_like(lc), lc], axis=1)
@@ -512,8 +571,8 @@ def sampledropout_(v, x, dropoutmid, dropoutshape, log1p_form=False, tick=0, row
     """Applies `sampledropout` (src/rbmtraining.jl:289-311) to the visible states in place:
     v .*= 1 - bernoulli(logistic(shape (x' - mid))) (src/gibbssampling.jl:103-107,144-148)."""
     ctx = ctx or (v.ctx if isinstance(v, Mat) else default_context())
-    vm = v if isinstance(v, Mat) else Mat.from_host(ctx, v, L.MAT_COUNT)
-    xm = x if isinstance(x, Mat) else Mat.from_host(ctx, x, L.MAT_COUNT)
+    vm = _as_mat(ctx, v, L.MAT_COUNT)
+    xm = _as_mat(ctx, x, L.MAT_COUNT)
     mid = np.atleast_1d(np.asarray(dropoutmid, dtype=np.float64))
     shp = np.atleast_1d(np.asarray(dropoutshape, dtype=np.float64))
     if mid.shape != shp.shape:
@@ -526,7 +585,7 @@ def sampledropout_(v, x, dropoutmid, dropoutshape, log1p_form=False, tick=0, row
 def mle_for_theta(x, mu, lam=100.0, maxiter=20, convtol=1e-6, ctx=None):
     """`mle_for_θ` for every gene (src/rbmtraining.jl:675-719)."""
     ctx = ctx or (x.ctx if isinstance(x, Mat) else default_context())
-    xm = x if isinstance(x, Mat) else Mat.from_host(ctx, x, L.MAT_COUNT)
+    xm = _as_mat(ctx, x, L.MAT_COUNT)
     mm = mu if isinstance(mu, Mat) else Mat.from_host(ctx, mu, L.MAT_REAL)
     theta = np.zeros(xm.cols)
     check(lib().scdbm_mle_theta(xm.h, mm.h, float(lam), int(maxiter), float(convtol), _ptr(theta)))
@@ -745,7 +804,7 @@ def fitrbm(x, nhidden=None, epochs=10, upfactor=1.0, downfactor=1.0, learningrat
         raise NotImplementedError('estimatedispersion must be "gene" (the other branches of the reference do not run)')
     if (fisherscoring != 0 or zeroinflation) and not nb:
         raise NotImplementedError("fisherscoring / zeroinflation apply to NegativeBinomialBernoulliRBM only")
-    xm = x if isinstance(x, Mat) else Mat.from_host(ctx, x, L.MAT_COUNT if nb else L.MAT_REAL)
+    xm = _as_mat(ctx, x, L.MAT_COUNT if nb else L.MAT_REAL)
     nhidden = xm.cols if nhidden is None else nhidden
     if learningrates is None:
         learningrates = [learningrate] * epochs
@@ -806,7 +865,7 @@ def stackrbms(x, nhiddens=None, epochs=10, predbm=False, learningrate=0.005, bat
             nhiddens = [ncol] * 2
         trainlayers = [TrainLayer(nhidden=n) for n in nhiddens]
     nb0 = trainlayers[0].rbmtype is NegativeBinomialBernoulliRBM
-    xm = x if isinstance(x, Mat) else Mat.from_host(ctx, x, L.MAT_COUNT if nb0 else L.MAT_REAL)
+    xm = _as_mat(ctx, x, L.MAT_COUNT if nb0 else L.MAT_REAL)
     layers = []
     upfactor, downfactor = (2.0 if predbm else 1.0), 1.0
     hiddenval = xm
@@ -881,7 +940,7 @@ def fitdbm(x, nhiddens=None, epochs=10, nparticles=100, learningrate=0.005, lear
     if seed is not None:
         ctx.set("seed", seed)
     nb0 = bool(pretraining) and pretraining[0].rbmtype is NegativeBinomialBernoulliRBM
-    xm = x if isinstance(x, Mat) else Mat.from_host(ctx, x, L.MAT_COUNT if nb0 else L.MAT_REAL)
+    xm = _as_mat(ctx, x, L.MAT_COUNT if nb0 else L.MAT_REAL)
     if not pretraining and not nhiddens:
         nhiddens = [xm.cols] * 2
     dbm = stackrbms(xm, nhiddens=nhiddens, epochs=epochs if epochspretraining is None else epochspretraining,

@@ -4,6 +4,7 @@
 #include "elementwise.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "sparse.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -133,6 +134,8 @@ struct scdbm_mat {
     scdbm_ctx* ctx;
     MatView v;
     bool owns;
+    int64_t* csr_indptr = nullptr;   // device row pointers of the pending CSR download (scdbm_mat_csr_prepare)
+    int64_t csr_nnz = -1;
 };
 
 struct scdbm_particles {
@@ -216,6 +219,7 @@ static scdbm_mat* mat_new(scdbm_ctx* ctx, int64_t rows, int64_t cols, int kind) 
 }
 static void mat_free(scdbm_mat* m) {
     if (!m) return;
+    if (m->csr_indptr) cudaFreeAsync(m->csr_indptr, m->ctx->stream);
     if (m->owns) {
         cudaStream_t st = m->ctx->stream;
         if (m->v.p0) cudaFreeAsync(m->v.p0, st);
@@ -943,6 +947,145 @@ int32_t scdbm_wait_downloads(scdbm_ctx* ctx) {
         CK(cudaStreamSynchronize(ctx->copy_stream));
         ctx->copy_pending = false;
     }
+    API_END
+}
+
+// ------------------------------------------------------------------ sparse data path
+int32_t scdbm_mat_upload_compressed(scdbm_mat* m, int32_t major, const int64_t* ptr, const int32_t* idx, const float* val) {
+    API_BEGIN
+    REQUIRE(m && ptr, "NULL argument");
+    REQUIRE(major == 0 || major == 1, "major must be 0 (CSR) or 1 (CSC)");
+    scdbm_ctx* c = m->ctx;
+    const int64_t nmajor = major ? m->v.cols : m->v.rows;
+    const int64_t nnz = ptr[nmajor];
+    REQUIRE(ptr[0] == 0 && nnz >= 0, "pointer array must start at 0 and end at nnz");
+    for (int64_t i = 0; i < nmajor; ++i) REQUIRE(ptr[i] <= ptr[i + 1], "pointer array must be non-decreasing");
+    REQUIRE(nnz == 0 || (idx && val), "NULL index/value array");
+    if (m->v.rows == 0 || m->v.cols == 0) return SCDBM_OK;
+    const size_t plane = (size_t)m->v.rows * m->v.ld * sizeof(__nv_bfloat16);
+    CK(cudaMemsetAsync(m->v.p0, 0, plane, c->stream));
+    if (m->v.p1) CK(cudaMemsetAsync(m->v.p1, 0, plane, c->stream));
+    if (m->v.f) CK(cudaMemsetAsync(m->v.f, 0, plane * 2, c->stream));
+    set_hiflags(c, m->v, false);
+    if (nnz == 0) return SCDBM_OK;
+    int64_t* d_ptr = nullptr;
+    int32_t* d_idx = nullptr;
+    float* d_val = nullptr;
+    unsigned int* d_err = nullptr;
+    auto cleanup = [&]() { cudaFree(d_ptr); cudaFree(d_idx); cudaFree(d_val); cudaFree(d_err); };
+    try {
+        CK(cudaMalloc(&d_ptr, (size_t)(nmajor + 1) * sizeof(int64_t)));
+        CK(cudaMalloc(&d_idx, (size_t)nnz * sizeof(int32_t)));
+        CK(cudaMalloc(&d_val, (size_t)nnz * sizeof(float)));
+        CK(cudaMalloc(&d_err, sizeof(unsigned int)));
+        CK(cudaMemsetAsync(d_err, 0, sizeof(unsigned int), c->stream));
+        CK(cudaMemcpyAsync(d_ptr, ptr, (size_t)(nmajor + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(d_idx, idx, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(d_val, val, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        k_scatter_compressed<<<grid1d(nmajor * 32), 256, 0, c->stream>>>(d_ptr, d_idx, d_val, nmajor, major, m->v, d_err);
+        CK(cudaGetLastError());
+        c->launches++;
+        unsigned int err = 0;
+        CK(cudaMemcpyAsync(&err, d_err, sizeof(err), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (err & 1u) throw Err(SCDBM_EINVAL, "compressed matrix holds an index outside the matrix");
+        if (err & 2u) throw Err(SCDBM_EINVAL, m->v.kind == MAT_COUNT ? "count matrix entries must be integers in [0, 65535]"
+                                              : m->v.kind == MAT_BINARY ? "binary matrix entries must be 0 or 1" : "matrix contains NaN/Inf");
+    } catch (...) {
+        cleanup();
+        throw;
+    }
+    cleanup();
+    API_END
+}
+
+int32_t scdbm_mat_csr_prepare(scdbm_mat* m, int64_t* nnz) {
+    API_BEGIN
+    REQUIRE(m && nnz, "NULL argument");
+    REQUIRE(m->v.kind != MAT_REAL, "CSR download is for count / binary matrices");
+    scdbm_ctx* c = m->ctx;
+    const int64_t R = m->v.rows;
+    if (m->csr_indptr) { CK(cudaFreeAsync(m->csr_indptr, c->stream)); m->csr_indptr = nullptr; }
+    m->csr_nnz = -1;
+    CK(cudaMallocAsync(&m->csr_indptr, (size_t)(R + 1) * sizeof(int64_t), c->stream));
+    const int64_t nblocks = std::max<int64_t>(1, (R + 1023) / 1024);
+    int64_t *d_cnt = nullptr, *d_tot = nullptr;
+    CK(cudaMallocAsync(&d_cnt, (size_t)std::max<int64_t>(R, 1) * sizeof(int64_t), c->stream));
+    CK(cudaMallocAsync(&d_tot, (size_t)(nblocks + 1) * sizeof(int64_t), c->stream));
+    if (R > 0 && m->v.cols > 0) k_row_nnz<<<grid1d(R * 32), 256, 0, c->stream>>>(m->v, d_cnt);
+    else if (R > 0) CK(cudaMemsetAsync(d_cnt, 0, (size_t)R * sizeof(int64_t), c->stream));
+    k_scan_block<<<(unsigned)nblocks, 1024, 0, c->stream>>>(d_cnt, R, m->csr_indptr, d_tot);
+    k_scan_totals<<<1, 1024, 0, c->stream>>>(d_tot, nblocks, d_tot + nblocks);
+    k_scan_add<<<(unsigned)nblocks, 1024, 0, c->stream>>>(m->csr_indptr, R, d_tot, d_tot + nblocks);
+    CK(cudaGetLastError());
+    c->launches += 4;
+    int64_t total = 0;
+    CK(cudaMemcpyAsync(&total, d_tot + nblocks, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaFreeAsync(d_cnt, c->stream));
+    CK(cudaFreeAsync(d_tot, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    m->csr_nnz = total;
+    *nnz = total;
+    API_END
+}
+
+int32_t scdbm_mat_download_csr(scdbm_mat* m, int64_t* indptr, void* indices, int32_t index_bytes, uint16_t* values) {
+    API_BEGIN
+    REQUIRE(m && indptr, "NULL argument");
+    REQUIRE(m->csr_indptr && m->csr_nnz >= 0, "call scdbm_mat_csr_prepare first");
+    REQUIRE(index_bytes == 2 || index_bytes == 4, "index_bytes must be 2 or 4");
+    REQUIRE(index_bytes == 4 || m->v.cols <= 65536, "16-bit column indices need at most 65536 columns");
+    const int64_t nnz = m->csr_nnz, R = m->v.rows;
+    REQUIRE(nnz == 0 || (indices && values), "NULL index/value array");
+    scdbm_ctx* c = m->ctx;
+    void* d_idx = nullptr;
+    uint16_t* d_val = nullptr;
+    if (nnz > 0) {
+        CK(cudaMallocAsync(&d_idx, (size_t)nnz * index_bytes, c->stream));
+        CK(cudaMallocAsync(&d_val, (size_t)nnz * sizeof(uint16_t), c->stream));
+        if (index_bytes == 2) k_csr_fill<uint16_t><<<grid1d(R * 32), 256, 0, c->stream>>>(m->v, m->csr_indptr, (uint16_t*)d_idx, d_val);
+        else k_csr_fill<int32_t><<<grid1d(R * 32), 256, 0, c->stream>>>(m->v, m->csr_indptr, (int32_t*)d_idx, d_val);
+        CK(cudaGetLastError());
+        c->launches++;
+        CK(cudaMemcpyAsync(indices, d_idx, (size_t)nnz * index_bytes, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(values, d_val, (size_t)nnz * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaMemcpyAsync(indptr, m->csr_indptr, (size_t)(R + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    if (d_idx) CK(cudaFreeAsync(d_idx, c->stream));
+    if (d_val) CK(cudaFreeAsync(d_val, c->stream));
+    CK(cudaFreeAsync(m->csr_indptr, c->stream));
+    m->csr_indptr = nullptr;
+    m->csr_nnz = -1;
+    CK(cudaStreamSynchronize(c->stream));
+    API_END
+}
+
+int32_t scdbm_mat_generate_counts(scdbm_mat* m, const double* gene_mean, const double* r, double sizefactor_sigma, uint64_t seed,
+                                  uint64_t row_offset) {
+    API_BEGIN
+    REQUIRE(m && gene_mean && r, "NULL argument");
+    REQUIRE(m->v.kind == MAT_COUNT, "synthetic counts need a COUNT matrix");
+    REQUIRE(sizefactor_sigma >= 0.0, "size-factor sigma must be non-negative");
+    const int64_t V = m->v.cols;
+    if (m->v.rows == 0 || V == 0) return SCDBM_OK;
+    scdbm_ctx* c = m->ctx;
+    std::vector<float> h(2 * (size_t)V);
+    for (int64_t j = 0; j < V; ++j) {
+        REQUIRE(std::isfinite(gene_mean[j]) && gene_mean[j] >= 0.0, "gene means must be finite and non-negative");
+        REQUIRE(std::isfinite(r[j]) && r[j] > 0.0, "inverse dispersions must be positive");
+        h[j] = (float)gene_mean[j];
+        h[V + j] = (float)r[j];
+    }
+    float* d = nullptr;
+    CK(cudaMallocAsync(&d, h.size() * sizeof(float), c->stream));
+    CK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    set_hiflags(c, m->v, false);
+    k_generate_counts<<<grid1d(m->v.rows * ((V + 3) / 4)), 256, 0, c->stream>>>(m->v, d, d + V, (float)sizefactor_sigma, c->mu_inv_max,
+                                                                                 (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)row_offset);
+    CK(cudaGetLastError());
+    c->launches++;
+    CK(cudaFreeAsync(d, c->stream));
+    CK(cudaStreamSynchronize(c->stream));   // h goes out of scope
     API_END
 }
 

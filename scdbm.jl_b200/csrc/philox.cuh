@@ -5,7 +5,7 @@
 
 namespace scdbm {
 
-enum Purpose : uint32_t { P_GIBBS = 0, P_INIT = 1, P_INIT2 = 2, P_GAMMA = 3, P_POIS = 4, P_DROPOUT = 5, P_PERM = 6 };
+enum Purpose : uint32_t { P_GIBBS = 0, P_INIT = 1, P_INIT2 = 2, P_GAMMA = 3, P_POIS = 4, P_DROPOUT = 5, P_PERM = 6, P_DATA = 7, P_SIZE = 8 };
 
 __host__ __device__ inline uint32_t stream_id(uint32_t layer, uint32_t purpose = P_GIBBS, uint32_t attempt = 0) {
     return (layer & 0xFFu) | ((purpose & 0xFFu) << 8) | ((attempt & 0xFFFFu) << 16);

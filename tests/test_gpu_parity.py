@@ -61,6 +61,85 @@ def test_async_u16_download_snapshots_in_stream_order(pkg, ctx):
         m.to_host_u16(np.zeros((3, 3), dtype=np.uint16))
 
 
+# ------------------------------------------------------------ sparse data path
+def test_compressed_upload_and_csr_download(pkg, ctx):
+    g = np.random.default_rng(5)
+    for rows, cols in [(1, 1), (7, 5), (130, 257), (1500, 700)]:
+        x = g.poisson(0.3, (rows, cols)).astype(float)
+        x[0, 0] = 65535
+        x[rows - 1, cols - 1] = 2048                     # hi count plane
+        if rows > 3:
+            x[2, :] = 0                                    # empty row
+        ptr, idx, val = synth.to_csr(x)
+        assert np.array_equal(synth.from_compressed(x.shape, ptr, idx, val), x)
+        m = pkg.Mat.from_compressed(ctx, x.shape, ptr, idx, val)
+        assert np.array_equal(m.to_host(), x)
+        cptr, cidx, cval = synth.to_csr(x.T)               # CSC of x = CSR of its transpose
+        assert np.array_equal(pkg.Mat.from_compressed(ctx, x.shape, cptr, cidx, cval, major="csc").to_host(), x)
+        for dt in (np.uint16, np.int32):
+            p2, i2, v2 = m.to_host_csr(index_dtype=dt)
+            assert np.array_equal(p2, ptr) and np.array_equal(i2, idx) and np.array_equal(v2, val.astype(np.uint16))
+            assert i2.dtype == dt and v2.dtype == np.uint16 and p2.dtype == np.int64
+    z = pkg.Mat(ctx, 9, 4, pkg.MAT_COUNT)                  # all-zero matrix
+    p2, i2, v2 = z.to_host_csr()
+    assert np.array_equal(p2, np.zeros(10)) and len(i2) == 0 and len(v2) == 0
+    b = (g.random((40, 33)) < 0.2).astype(float)           # binary states compress the same way
+    pb, ib, vb = pkg.Mat.from_host(ctx, b, pkg.MAT_BINARY).to_host_csr()
+    assert np.array_equal(synth.from_compressed(b.shape, pb, ib, vb), b)
+
+
+def test_compressed_upload_validation(pkg, ctx):
+    m = pkg.Mat(ctx, 4, 5, pkg.MAT_COUNT)
+    ptr = np.array([0, 1, 1, 2, 2])
+    for idx, val in [([9, 0], [1.0, 2.0]), ([1, 0], [1.5, 2.0]), ([1, 0], [-1.0, 2.0]), ([1, 0], [70000.0, 2.0])]:
+        with pytest.raises(pkg.ScdbmError) as e:
+            m.upload_compressed(ptr, idx, val)
+        assert e.value.code == -1
+    with pytest.raises(pkg.ScdbmError):
+        m.upload_compressed(np.array([0, 2, 1, 2, 2]), [1, 0], [1.0, 2.0])
+    with pytest.raises(ValueError):
+        m.upload_compressed(ptr[:-1], [1, 0], [1.0, 2.0])
+    m.upload_compressed(ptr, [1, 0], [3.0, 2.0])
+    want = np.zeros((4, 5)); want[0, 1] = 3; want[2, 0] = 2
+    assert np.array_equal(m.to_host(), want)
+
+
+def test_sparse_input_trains_like_dense(pkg):
+    sps = pytest.importorskip("scipy.sparse")
+    ctx = pkg.Context(0, 11)                               # fitrbm(seed=...) re-seeds its context
+    x, _, _ = synth.counts(60, 24, 4)
+    a = pkg.fitrbm(x, rbmtype=pkg.NegativeBinomialBernoulliRBM, nhidden=6, epochs=2, batchsize=20, learningrate=1e-4,
+                   fisherscoring=0, zeroinflation=False, seed=11, ctx=ctx)
+    for fmt in (sps.csr_matrix, sps.csc_matrix):
+        b = pkg.fitrbm(fmt(x), rbmtype=pkg.NegativeBinomialBernoulliRBM, nhidden=6, epochs=2, batchsize=20, learningrate=1e-4,
+                       fisherscoring=0, zeroinflation=False, seed=11, ctx=ctx)
+        assert np.array_equal(a.weights, b.weights) and np.array_equal(a.visbias, b.visbias)
+
+
+def test_generated_counts_match_oracle(pkg, ctx):
+    g = np.random.default_rng(8)
+    V, n, off = 70, 500, 1000
+    gm = np.clip(np.exp(g.normal(-1.5, 1.5, V)), 1e-3, 50.0)
+    gm[:3] = [20.0, 45.0, 0.0]                             # gamma-Poisson branch and an unexpressed gene
+    r = g.uniform(0.2, 2.0, V)
+    got = pkg.Mat(ctx, n, V, pkg.MAT_COUNT).generate_counts(gm, r, 0.3, seed=77, row_offset=off).to_host()
+    want, s = synth.philox_counts(n, gm, r, 0.3, px.Rng(77), row_offset=off)
+    inv = (s[:, None] * gm[None, :]) <= 0.98 * 8.0         # single-uniform inversion: same draw except at CDF steps
+    assert np.mean(got[inv] != want[inv]) < 2e-3
+    assert np.all(got[:, 2] == 0)
+    # gamma-Poisson branch: fp32 vs fp64 rejection samplers agree in distribution
+    big = ~inv
+    assert abs(got[big].mean() / want[big].mean() - 1) < 0.15
+    # any shard of cells can be generated independently
+    part = pkg.Mat(ctx, 100, V, pkg.MAT_COUNT).generate_counts(gm, r, 0.3, seed=77, row_offset=off + 200).to_host()
+    assert np.array_equal(part, got[200:300])
+    # statistics of a larger sample: mean s_c m_g (E[s] = exp(sigma^2/2)), zero fraction 80-92 %-like
+    big_m = pkg.Mat(ctx, 20000, V, pkg.MAT_COUNT).generate_counts(gm, r, 0.3, seed=5)
+    mean, var, zf = big_m.column_stats()
+    sel = gm > 0.05
+    assert np.allclose(mean[sel], gm[sel] * np.exp(0.045), rtol=0.25)
+
+
 def test_error_codes(pkg, ctx):
     with pytest.raises(pkg.ScdbmError) as e:
         pkg.Mat.from_host(ctx, np.array([[np.nan]]), pkg.MAT_REAL)

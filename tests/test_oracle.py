@@ -214,3 +214,27 @@ def test_next_rows_oracle():
     th = om.mle_for_theta(y, mu, lam=0.0, maxiter=50)
     assert np.all(np.abs(th / theta_true - 1) < 0.15)
     assert np.isclose(om.mle_for_theta(y[:, 0], mu[:, 0], 0.0, maxiter=50), th[0])
+
+
+def test_philox_counts_generator_statistics_and_sharding():
+    """oracle/synth.philox_counts (twin of scdbm_mat_generate_counts): NB(r, r/(s m + r)) moments, shard invariance."""
+    from oracle import synth
+    g = np.random.default_rng(2)
+    V, n = 12, 40000
+    gm = np.array([0.05, 0.2, 1.0, 3.0, 7.0, 20.0, 0.0, 0.5, 2.0, 0.1, 12.0, 0.8])
+    r = g.uniform(0.3, 2.0, V)
+    x, s = synth.philox_counts(n, gm, r, 0.3, px.Rng(9))
+    assert abs(s.mean() - np.exp(0.045)) < 0.01 and abs(np.log(s).std() - 0.3) < 0.01
+    assert np.all(x[:, 6] == 0)
+    sel = gm > 0
+    assert np.allclose(x.mean(axis=0)[sel], gm[sel] * np.exp(0.045), rtol=0.08)
+    # variance of the NB-lognormal mixture: E[mu] + E[mu^2] (1 + 1/r) - E[mu]^2
+    e1, e2 = gm * np.exp(0.045), gm ** 2 * np.exp(0.18)
+    want_var = e1 + e2 * (1 + 1 / r) - e1 ** 2
+    assert np.allclose(x.var(axis=0)[sel], want_var[sel], rtol=0.25)
+    part, _ = synth.philox_counts(50, gm, r, 0.3, px.Rng(9), row_offset=100)
+    assert np.array_equal(part, x[100:150])
+    ptr, idx, val = synth.to_csr(x[:200])
+    assert np.array_equal(synth.from_compressed((200, V), ptr, idx, val), x[:200])
+    cptr, cidx, cval = synth.to_csr(x[:200].T)
+    assert np.array_equal(synth.from_compressed((200, V), cptr, cidx, cval, major="csc"), x[:200])
