@@ -230,6 +230,36 @@ def run_ours(args):
                           "two pinned result buffers; the last copy completes inside the timed region",
                "cells_per_sec": world * n * ksteps / float(dt.item())}
 
+        # the same step with the row-compressed wire format (uint16 column indices + uint16 counts, ~20 % dense)
+        del outs
+        cap = int(0.3 * n * UNITS[0])
+        ib = torch.empty(cap, dtype=torch.uint16, pin_memory=True).numpy()
+        vb = torch.empty(cap, dtype=torch.uint16, pin_memory=True).numpy()
+        csr_bytes = [0]
+
+        def csr_step():
+            m = pkg.DeviceModel.from_host(host_model, ctx)
+            q = pkg.sampleparticles(m, n, burnin, row_offset, device=True)
+            ptr, idx, val = q.layer(0).to_host_csr(buffers=(ib, vb))
+            csr_bytes[0] = ptr.nbytes + idx.nbytes + val.nbytes
+            q.close()
+            m.close()
+
+        csr_step()
+        barrier()
+        t0 = time.perf_counter()
+        csteps = max(1, min(args.steps, 2))
+        for _ in range(csteps):
+            csr_step()
+        barrier()
+        dtc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dtc, op=dist.ReduceOp.MAX)
+        e2e["csr"] = {"value": world * n * burnin * csteps / float(dtc.item()), "unit": "sweeps*chains/s", "steps": csteps,
+                      "d2h_bytes_per_step": int(csr_bytes[0]),
+                      "note": "scdbm_mat_csr_prepare + scdbm_mat_download_csr into pinned buffers, synchronous (not overlapped)"}
+        del ib, vb
+
     line = {
         "metric": "Gibbs sweeps x chains / sec (synthetic-cell generation, 2-layer scDBM)",
         "value": value, "unit": "sweeps*chains/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

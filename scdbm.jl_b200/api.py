@@ -254,9 +254,11 @@ class Mat:
         check(lib().scdbm_mat_upload_compressed(self.h, 1 if major == "csc" else 0, ptr.ctypes.data_as(C.POINTER(C.c_int64)),
                                                 idx.ctypes.data_as(C.POINTER(C.c_int32)), val.ctypes.data_as(C.POINTER(C.c_float))))
 
-    def to_host_csr(self, index_dtype=None):
+    def to_host_csr(self, index_dtype=None, buffers=None):
         """(indptr int64[rows+1], indices, values uint16) of a count / binary matrix, columns ascending within a
-        row: the compact wire format for generated cells.  `index_dtype`: np.uint16 (default when it fits) or np.int32."""
+        row: the compact wire format for generated cells.  `index_dtype`: np.uint16 (default when it fits) or np.int32.
+        `buffers=(indices_buf, values_buf)`: preallocated (pinned) 1-d arrays of sufficient capacity to fill instead
+        of fresh pageable arrays; views of their first nnz entries are returned."""
         if index_dtype is None:
             index_dtype = np.uint16 if self.cols <= 65536 else np.int32
         index_dtype = np.dtype(index_dtype)
@@ -265,8 +267,14 @@ class Mat:
         nnz = C.c_int64()
         check(lib().scdbm_mat_csr_prepare(self.h, C.byref(nnz)))
         indptr = np.zeros(self.rows + 1, dtype=np.int64)
-        indices = np.zeros(nnz.value, dtype=index_dtype)
-        values = np.zeros(nnz.value, dtype=np.uint16)
+        if buffers is None:
+            indices = np.zeros(nnz.value, dtype=index_dtype)
+            values = np.zeros(nnz.value, dtype=np.uint16)
+        else:
+            ib, vb = buffers
+            if ib.dtype != index_dtype or vb.dtype != np.uint16 or ib.ndim != 1 or vb.ndim != 1 or min(len(ib), len(vb)) < nnz.value:
+                raise ValueError(f"buffers too small or of the wrong dtype for {nnz.value} non-zeros")
+            indices, values = ib[:nnz.value], vb[:nnz.value]
         check(lib().scdbm_mat_download_csr(self.h, indptr.ctypes.data_as(C.POINTER(C.c_int64)), indices.ctypes.data_as(C.c_void_p),
                                            index_dtype.itemsize, values.ctypes.data_as(C.POINTER(C.c_uint16))))
         return indptr, indices, values

@@ -55,6 +55,7 @@ struct scdbm_ctx {
     int engine = SCDBM_ENGINE_AUTO;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned int* d_delta = nullptr;
+    unsigned int *h_flag = nullptr, *d_flag = nullptr;   // zero-copy status word (mapped pinned host memory): no copy-engine read-back
     int64_t launches = 0;
     int64_t tc_launches = 0;
     int num_sms = 148;
@@ -82,6 +83,7 @@ static void ctx_free(scdbm_ctx* c) {
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaFree(c->d_delta);
+    if (c->h_flag) cudaFreeHost(c->h_flag);
     cudaFree(c->scratch);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -114,13 +116,18 @@ struct scdbm_model {
 };
 
 static void model_free(scdbm_model* m) {
-    cudaStreamSynchronize(m->ctx->stream);
+    // stream-ordered frees: destroying a model never waits for the copy stream (an asynchronous download in flight)
+    cudaStream_t st = m->ctx->stream;
     for (auto& L : m->L) {
-        cudaFree(L.W); cudaFree(L.a); cudaFree(L.b); cudaFree(L.r);
-        cudaFree(L.w0); cudaFree(L.w1); cudaFree(L.t0); cudaFree(L.t1); cudaFree(L.nbc); cudaFree(L.nbT);
+        float* f[] = {L.W, L.a, L.b, L.r};
+        for (float* p : f) if (p) cudaFreeAsync(p, st);
+        __nv_bfloat16* h[] = {L.w0, L.w1, L.t0, L.t1};
+        for (__nv_bfloat16* p : h) if (p) cudaFreeAsync(p, st);
+        if (L.nbc) cudaFreeAsync(L.nbc, st);
+        if (L.nbT) cudaFreeAsync(L.nbT, st);
     }
-    cudaFree(m->d_scale);
-    cudaFree(m->d_wmax);
+    if (m->d_scale) cudaFreeAsync(m->d_scale, st);
+    if (m->d_wmax) cudaFreeAsync(m->d_wmax, st);
     scdbm_ctx* c = m->ctx;
     delete m;
     ctx_release(c);
@@ -481,6 +488,9 @@ int32_t scdbm_ctx_create(int32_t device, uint64_t seed, void* stream, scdbm_ctx*
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     CK(cudaMalloc(&c->d_delta, sizeof(unsigned int)));
+    CK(cudaHostAlloc(&c->h_flag, sizeof(unsigned int), cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer(&c->d_flag, c->h_flag, 0));
+    *c->h_flag = 0u;
     {   // keep freed state matrices in the device's default memory pool instead of returning them to the driver
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -565,8 +575,8 @@ int32_t scdbm_model_create(scdbm_ctx* c, int32_t nrbms, const int32_t* units, in
     for (int i = 0; i <= nrbms; ++i) REQUIRE(units[i] > 0, "layer sizes must be positive");
     auto* m = new scdbm_model{c, {}};
     ctx_retain(c);
-    CK(cudaMalloc(&m->d_scale, 2 * sizeof(float)));
-    CK(cudaMalloc(&m->d_wmax, sizeof(unsigned int)));
+    CK(cudaMallocAsync(&m->d_scale, 2 * sizeof(float), c->stream));
+    CK(cudaMallocAsync(&m->d_wmax, sizeof(unsigned int), c->stream));
     {
         const float one[2] = {1.0f, 1.0f};
         CK(cudaMemcpyAsync(m->d_scale, one, sizeof(one), cudaMemcpyHostToDevice, c->stream));
@@ -581,14 +591,14 @@ int32_t scdbm_model_create(scdbm_ctx* c, int32_t nrbms, const int32_t* units, in
         L.ldh = round_up(L.H, 64);
         L.ldv = round_up(L.V, 64);
         L.scale = m->d_scale;
-        CK(cudaMalloc(&L.W, (size_t)L.V * L.H * sizeof(float)));
-        CK(cudaMalloc(&L.a, (size_t)L.V * sizeof(float)));
-        CK(cudaMalloc(&L.b, (size_t)L.H * sizeof(float)));
-        CK(cudaMalloc(&L.r, (size_t)L.V * sizeof(float)));
+        CK(cudaMallocAsync(&L.W, (size_t)L.V * L.H * sizeof(float), c->stream));
+        CK(cudaMallocAsync(&L.a, (size_t)L.V * sizeof(float), c->stream));
+        CK(cudaMallocAsync(&L.b, (size_t)L.H * sizeof(float), c->stream));
+        CK(cudaMallocAsync(&L.r, (size_t)L.V * sizeof(float), c->stream));
         if (L.kind == SCDBM_VIS_NEGBIN) {
-            CK(cudaMalloc(&L.nbc, (size_t)L.V * sizeof(float4)));
+            CK(cudaMallocAsync(&L.nbc, (size_t)L.V * sizeof(float4), c->stream));
             // padded past the last column tile of any tile width: the padding never queues a draw
-            CK(cudaMalloc(&L.nbT, (size_t)(round_up(L.V, 256) + 256) * sizeof(uint32_t)));
+            CK(cudaMallocAsync(&L.nbT, (size_t)(round_up(L.V, 256) + 256) * sizeof(uint32_t), c->stream));
             CK(cudaMemsetAsync(L.nbT, 0xFF, (size_t)(round_up(L.V, 256) + 256) * sizeof(uint32_t), c->stream));
         }
         CK(cudaMemsetAsync(L.W, 0, (size_t)L.V * L.H * sizeof(float), c->stream));
@@ -596,8 +606,8 @@ int32_t scdbm_model_create(scdbm_ctx* c, int32_t nrbms, const int32_t* units, in
         CK(cudaMemsetAsync(L.b, 0, (size_t)L.H * sizeof(float), c->stream));
         k_fill_f32<<<grid1d(L.V), 256, 0, c->stream>>>(L.r, L.V, 1.0f);
         const size_t wb = (size_t)L.V * L.ldh * sizeof(__nv_bfloat16), tb = (size_t)L.H * L.ldv * sizeof(__nv_bfloat16);
-        CK(cudaMalloc(&L.w0, wb)); CK(cudaMalloc(&L.w1, wb));
-        CK(cudaMalloc(&L.t0, tb)); CK(cudaMalloc(&L.t1, tb));
+        CK(cudaMallocAsync(&L.w0, wb, c->stream)); CK(cudaMallocAsync(&L.w1, wb, c->stream));
+        CK(cudaMallocAsync(&L.t0, tb, c->stream)); CK(cudaMallocAsync(&L.t1, tb, c->stream));
         CK(cudaMemsetAsync(L.w0, 0, wb, c->stream)); CK(cudaMemsetAsync(L.w1, 0, wb, c->stream));
         CK(cudaMemsetAsync(L.t0, 0, tb, c->stream)); CK(cudaMemsetAsync(L.t1, 0, tb, c->stream));
         refresh_nbc(c, L);
@@ -655,11 +665,13 @@ int32_t scdbm_model_set_layer(scdbm_model* m, int32_t l, const double* W, int64_
     if (L.kind == SCDBM_VIS_NEGBIN) {
         // validity of the NB conditional (Appendix A of SURVEY.md): x_i = a_i + sum_j W_ij h_j < 0 for every binary h,
         // i.e. a_i + sum_j max(W_ij, 0) < 0 (the reference keeps W <= 0, a <= -1e-10: src/optimizers.jl:482-483)
-        CK(cudaMemsetAsync(m->ctx->d_delta, 0, sizeof(unsigned int), st));
-        refresh_nbc(m->ctx, L, m->ctx->d_delta);
-        unsigned int bad = 0;
-        CK(cudaMemcpyAsync(&bad, m->ctx->d_delta, sizeof(bad), cudaMemcpyDeviceToHost, st));
+        // the status word lives in mapped host memory: a device->host copy would queue behind an asynchronous
+        // download in flight on the copy engine
         CK(cudaStreamSynchronize(st));
+        *m->ctx->h_flag = 0u;
+        refresh_nbc(m->ctx, L, m->ctx->d_flag);
+        CK(cudaStreamSynchronize(st));
+        const unsigned int bad = *m->ctx->h_flag;
         if (bad && W && a) throw Err(SCDBM_EINVAL, "invalid NB parameters: visbias[i] + sum_j max(weights[i,j], 0) must be negative for every gene");
     }
     API_END
@@ -864,7 +876,8 @@ int32_t scdbm_mat_download_u16(const scdbm_mat* m, uint16_t* x) {
     scdbm_ctx* c = m->ctx;
     // chunked and double-buffered: the plane -> uint16 conversion of chunk i+1 (context stream) overlaps the
     // device -> host copy of chunk i (copy stream).  Pinned host memory gives full PCIe bandwidth.
-    const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(m->v.rows, (int64_t)(64ll << 20) / std::max<int64_t>(2 * m->v.cols, 1)));
+    // whole 128-row tiles per chunk: the hi-plane flags are per row tile
+    const int64_t chunk_rows = std::max<int64_t>(128, (int64_t)(64ll << 20) / std::max<int64_t>(2 * m->v.cols, 1) / 128 * 128);
     uint16_t* stage[2] = {nullptr, nullptr};
     cudaStream_t cs = nullptr;
     cudaEvent_t ek[2] = {nullptr, nullptr}, ec[2] = {nullptr, nullptr};
@@ -886,9 +899,10 @@ int32_t scdbm_mat_download_u16(const scdbm_mat* m, uint16_t* x) {
             sub.p0 += r0 * sub.ld;
             if (sub.p1) sub.p1 += r0 * sub.ld;
             if (sub.f) sub.f += r0 * sub.ld;
+            if (sub.hiflag) sub.hiflag += r0 / 128;
             sub.rows = nr;
             if (r0 >= 2 * chunk_rows) CK(cudaStreamWaitEvent(c->stream, ec[b], 0));   // staging buffer free again
-            k_download_u16<<<grid1d(nr * m->v.cols), 256, 0, c->stream>>>(sub, stage[b]);
+            k_download_u16<<<(unsigned)((nr + 7) / 8), dim3(32, 8), 0, c->stream>>>(sub, stage[b]);
             CK(cudaGetLastError());
             c->launches++;
             CK(cudaEventRecord(ek[b], c->stream));
@@ -929,12 +943,16 @@ int32_t scdbm_mat_download_u16_async(const scdbm_mat* m, uint16_t* x) {
         c->stage16_cap = bytes;
     }
     // the snapshot is taken in stream order, so the caller may overwrite the matrix (next batch of chains) right away
-    k_download_u16<<<grid1d(n), 256, 0, c->stream>>>(m->v, c->stage16);
+    k_download_u16<<<(unsigned)((m->v.rows + 7) / 8), dim3(32, 8), 0, c->stream>>>(m->v, c->stage16);
     CK(cudaGetLastError());
     c->launches++;
     CK(cudaEventRecord(c->ev_conv, c->stream));
     CK(cudaStreamWaitEvent(c->copy_stream, c->ev_conv, 0));
-    CK(cudaMemcpyAsync(x, c->stage16, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    // 32 MB pieces: small device->host read-backs of later calls (status flags, scalars) share the copy engine
+    // and would otherwise queue behind the whole transfer
+    for (size_t off = 0; off < bytes; off += (size_t)32 << 20)
+        CK(cudaMemcpyAsync(reinterpret_cast<char*>(x) + off, reinterpret_cast<const char*>(c->stage16) + off,
+                           std::min<size_t>((size_t)32 << 20, bytes - off), cudaMemcpyDeviceToHost, c->copy_stream));
     CK(cudaEventRecord(c->ev_copy, c->copy_stream));
     c->copy_pending = true;
     API_END
