@@ -5,6 +5,7 @@
 # build image, so this file has NOT been executed there; it is a mechanical mirror of the Python
 # facade scdbm.jl_b200/api.py, which drives the same entry points in tests and benches.
 module scDBM
+using SparseArrays
 
 export BernoulliRBM, NegativeBinomialBernoulliRBM, MultimodalDBM, Particles, TrainLayer,
        fitrbm, stackrbms, fitdbm, traindbm!, trainrbm!, gibbssample!, gibbssamplenegativebinomial!,
@@ -94,6 +95,23 @@ function upload(ctx::Context, x::Matrix{Float64}, kind::Int32)
    m = Mat(ctx, size(x, 1), size(x, 2), kind)
    GC.@preserve x check(ccall((:scdbm_mat_upload, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64), m.h, x, max(size(x, 1), 1)))
    m
+end
+# sparse data (cells x genes SparseMatrixCSC): only the non-zeros cross PCIe
+function upload(ctx::Context, x::SparseMatrixCSC{Float64,<:Integer}, kind::Int32)
+   m = Mat(ctx, size(x, 1), size(x, 2), kind)
+   ptr = Int64.(x.colptr .- 1); idx = Int32.(x.rowval .- 1); val = Float32.(x.nzval)
+   GC.@preserve ptr idx val check(ccall((:scdbm_mat_upload_compressed, LIB), Int32,
+      (Ptr{Cvoid}, Int32, Ptr{Int64}, Ptr{Int32}, Ptr{Float32}), m.h, Int32(1), ptr, idx, val))
+   m
+end
+# generated cells as a genes x cells SparseMatrixCSC{UInt16} (= the row-compressed cells x genes matrix)
+function downloadsparse(m::Mat)
+   nnz = Ref{Int64}(0)
+   check(ccall((:scdbm_mat_csr_prepare, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), m.h, nnz))
+   ptr = Vector{Int64}(undef, m.rows + 1); idx = Vector{Int32}(undef, nnz[]); val = Vector{UInt16}(undef, nnz[])
+   GC.@preserve ptr idx val check(ccall((:scdbm_mat_download_csr, LIB), Int32,
+      (Ptr{Cvoid}, Ptr{Int64}, Ptr{Cvoid}, Int32, Ptr{UInt16}), m.h, ptr, idx, Int32(4), val))
+   SparseMatrixCSC(m.cols, m.rows, ptr .+ 1, idx .+ Int32(1), val)
 end
 function download!(x::Matrix{Float64}, m::Mat)
    GC.@preserve x check(ccall((:scdbm_mat_download, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64), m.h, x, max(size(x, 1), 1)))

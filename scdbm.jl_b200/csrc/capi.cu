@@ -246,12 +246,12 @@ static MatView rows_view(const MatView& v, int64_t rows) {
     return r;
 }
 
-// hi-plane flags of a COUNT matrix: `all` = true after any writer that does not maintain them
-// (upload, gather, copies, generic epilogues); the two-pass NB epilogue starts from all-clear
+// hi-plane flags of a COUNT matrix (see MatView): `all` = true after any writer that does not maintain them
+// (gather, copies, generic epilogues); false before a writer that rewrites both planes and raises the flags itself
 static void set_hiflags(scdbm_ctx* ctx, const MatView& v, bool all) {
     if (!v.hiflag) return;
     const size_t fb = (size_t)((std::max<int64_t>(v.rows, 1) + 127) / 128) * sizeof(uint32_t);
-    cudaMemsetAsync(v.hiflag, all ? 0x01 : 0x00, fb, ctx->stream);
+    cudaMemsetAsync(v.hiflag, all ? 0x03 : 0x00, fb, ctx->stream);   // 3 = in use + may hold stale entries; 0 = all zero
 }
 
 static EpiParams epi_base(scdbm_ctx* ctx) {
@@ -295,9 +295,16 @@ static void run_gemm(scdbm_ctx* ctx, GemmArgs& g, const SweepSrc* srcs, int nsrc
             ops[s].N = srcs[s].up ? L.H : L.V;
             ops[s].K = srcs[s].up ? L.V : L.H;
         }
-        // the Philox-fed tensor-core NB epilogue maintains the hi-plane flags itself (from all-clear); every
+        // the Philox-fed tensor-core NB epilogue maintains the hi-plane flags itself: row tiles whose hi plane was in
+        // use are marked for zero-filling, all others are known to be all zero and are not written at all.  Every
         // other writer of a COUNT matrix marks all row tiles as "hi plane possibly in use"
-        set_hiflags(ctx, g.epi.out, tc_epilogue_class(g, ops, nsrc) != 1);
+        if (tc_epilogue_class(g, ops, nsrc) == 1 && g.epi.out.hiflag) {
+            const int64_t nt = (std::max<int64_t>(g.epi.out.rows, 1) + 127) / 128;
+            k_flags_advance<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(g.epi.out.hiflag, nt);
+            ctx->launches++;
+        } else {
+            set_hiflags(ctx, g.epi.out, true);
+        }
         CK(launch_gemm_tc(ctx->tc, ops, nsrc, g, ctx->num_sms, ctx->stream));
         ctx->tc_launches++;
     } else {

@@ -25,7 +25,8 @@ struct MatView {
     __nv_bfloat16* p0;
     __nv_bfloat16* p1;     // nullptr for BINARY
     float* f;              // fp32 master copy, REAL only (else nullptr)
-    uint32_t* hiflag;      // COUNT only: per 128-row tile, non-zero if the p1 plane may hold a non-zero entry
+    uint32_t* hiflag;      // COUNT only, per 128-row tile: bit 0 = the p1 (hi) plane may hold a non-zero entry (consumers read it),
+                           // bit 1 = it may hold stale non-zeros (the NB sampling kernel zero-fills it before patching); 0 = all zero
     int64_t rows, cols, ld; // ld (elements) is a multiple of 64
     int32_t kind;
 };

@@ -25,7 +25,7 @@ __global__ void k_upload_f64(const double* __restrict__ src, int64_t lds, MatVie
             dst.p0[r * dst.ld + c] = a;
             if (dst.p1) dst.p1[r * dst.ld + c] = b;
             if (dst.f) dst.f[r * dst.ld + c] = t[threadIdx.x][j];
-            if (dst.hiflag && (__bfloat16_as_ushort(b) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 1u;
+            if (dst.hiflag && (__bfloat16_as_ushort(b) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 3u;
         }
     }
 }
@@ -49,7 +49,7 @@ __global__ void k_download_f64(MatView src, double* __restrict__ dst, int64_t ld
 __global__ void k_download_u16(MatView src, uint16_t* __restrict__ dst) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
     if (r >= src.rows) return;
-    const bool use_hi = src.p1 && (!src.hiflag || src.hiflag[r / 128] != 0u);
+    const bool use_hi = src.p1 && (!src.hiflag || (src.hiflag[r / 128] & 1u));
     const bool vec_out = (src.cols & 7) == 0;
     for (int64_t c0 = (int64_t)threadIdx.x * 8; c0 < src.cols; c0 += 32 * 8) {
         float v[8];
@@ -205,6 +205,13 @@ __global__ void k_refresh_nbc(const float* __restrict__ a, const float* __restri
     nbT[i] = mt >= 8388608.0 ? 0xFFFFFFFFu : (mt <= 0.0 ? 0u : ((uint32_t)mt << 9));
 }
 
+// before an NB sampling launch into `flags`' matrix: tiles whose hi plane was in use (or marked) must be zero-filled
+// by this launch (-> 2); tiles that were zero-filled by the previous launch and got no new entry are clean (-> 0)
+__global__ void k_flags_advance(uint32_t* __restrict__ flags, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = (flags[i] & 1u) ? 2u : 0u;
+}
+
 __global__ void k_fill_f32(float* p, int64_t n, float v) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -327,7 +334,7 @@ __global__ void k_restore_cols(MatView dst, MatView orig, const int32_t* __restr
         const int64_t r = i / ncols, c = cols[i % ncols], j = r * dst.ld + c;
         dst.p0[j] = orig.p0[j];
         if (dst.p1) dst.p1[j] = orig.p1[j];
-        if (dst.hiflag && dst.p1 && (__bfloat16_as_ushort(orig.p1[j]) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 1u;
+        if (dst.hiflag && dst.p1 && (__bfloat16_as_ushort(orig.p1[j]) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 3u;
     }
 }
 __global__ void k_restore_mask(MatView dst, MatView orig, const uint8_t* __restrict__ mask) {   // mask row-major [rows x cols]
@@ -337,7 +344,7 @@ __global__ void k_restore_mask(MatView dst, MatView orig, const uint8_t* __restr
         const int64_t r = i / dst.cols, j = r * dst.ld + i % dst.cols;
         dst.p0[j] = orig.p0[j];
         if (dst.p1) dst.p1[j] = orig.p1[j];
-        if (dst.hiflag && dst.p1 && (__bfloat16_as_ushort(orig.p1[j]) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 1u;
+        if (dst.hiflag && dst.p1 && (__bfloat16_as_ushort(orig.p1[j]) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 3u;
     }
 }
 

@@ -200,9 +200,9 @@ __device__ __forceinline__ int tc_tile(const TcParams& p, int it) {
 // hi count plane needed for work tile m_blk of source s?  (pair: either 128-row half flagged)
 __device__ __forceinline__ bool tc_use_hi(const TcParams& p, int s, int m_blk) {
     if (!p.a_hiflag[s] || p.nA[s] != 2) return p.nA[s] == 2;
-    if (!p.pair) return p.a_hiflag[s][m_blk] != 0u;
+    if (!p.pair) return (p.a_hiflag[s][m_blk] & 1u) != 0u;
     const int64_t last = (p.M + TC_BM - 1) / TC_BM - 1;
-    return p.a_hiflag[s][2 * m_blk] != 0u || (2 * m_blk + 1 <= last && p.a_hiflag[s][2 * m_blk + 1] != 0u);
+    return (p.a_hiflag[s][2 * m_blk] & 1u) != 0u || (2 * m_blk + 1 <= last && (p.a_hiflag[s][2 * m_blk + 1] & 1u) != 0u);
 }
 
 // ------------------------------------------------------------------ kernel
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                         s_lo[rl * CW + cl] = plane_encode(k - hi);
                         if (hi > 0.0f) {                                                 // rare: count >= 2048
                             e.out.p1[r2 * e.out.ld + c2] = plane_encode(hi);
-                            if (e.out.hiflag) e.out.hiflag[r2 / TC_BM] = 1u;
+                            if (e.out.hiflag) e.out.hiflag[r2 / TC_BM] = 3u;
                         }
                     }
                 }
@@ -367,17 +367,20 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
             slice = (((warp - 4) >> 2) + it) % NS;
             if constexpr (EK == 1) {
                 // lo count plane: staged in the warp's shared-memory tile (zeroed here, patched by pass B, written
-                // out coalesced at the end of the tile).  hi plane (counts >= 256, rare): coalesced zero-fill now
-                // (full 32 B sectors: 4 lanes x 16 B per row, 8 rows per store), scattered patches from pass B.
+                // out coalesced at the end of the tile).  hi plane (counts >= 2048, rare): coalesced zero-fill now where
+                // the row tile is marked (full 32 B sectors: 4 lanes x 16 B per row, 8 rows per store), scattered patches from pass B.
                 cur_m0 = m0; cur_n0 = n0;
                 const MatView& o = p.epi.out;
+                // the hi plane of a row tile is all zero unless its flag says otherwise (bit 1: stale entries of an
+                // earlier sweep, or of an earlier column tile of this launch -- re-zeroing those is harmless)
+                const bool dirty = !o.hiflag || (*reinterpret_cast<const volatile uint32_t*>(o.hiflag + m0 / TC_BM) & 2u) != 0u;
 #pragma unroll
                 for (int i = 0; i < (32 * CW * 2) / (32 * 16); ++i) {
                     const int idx = i * 32 + lane;                   // 16-byte chunk index within the region
                     const int rr = idx / (CW / 8), ch = idx % (CW / 8);
                     const int64_t r2 = m0 + q * 32 + rr, c2 = n0 + slice * CW + ch * 8;
                     reinterpret_cast<uint4*>(s_lo)[idx] = make_uint4(0u, 0u, 0u, 0u);
-                    if (r2 < p.M && c2 < o.ld) *reinterpret_cast<uint4*>(o.p1 + r2 * o.ld + c2) = make_uint4(0u, 0u, 0u, 0u);
+                    if (dirty && r2 < p.M && c2 < o.ld) *reinterpret_cast<uint4*>(o.p1 + r2 * o.ld + c2) = make_uint4(0u, 0u, 0u, 0u);
                 }
                 __syncwarp();
             }
@@ -647,7 +650,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
                     int lo, hi;
                     kb_range(s, sp, lo, hi);
                     for (int kb = lo; kb < hi; ++kb) {
-                        const int nA = (p.a_hiflag[s] && p.nA[s] == 2 && p.a_hiflag[s][kb / 2] == 0u) ? 1 : p.nA[s];
+                        const int nA = (p.a_hiflag[s] && p.nA[s] == 2 && (p.a_hiflag[s][kb / 2] & 1u) == 0u) ? 1 : p.nA[s];
                         mbar_wait_backoff(smem_u32(&bar_empty[stage]), phase ^ 1u);
                         const uint32_t full = smem_u32(&bar_full[stage]);
                         const uint32_t sa = smem_base + (uint32_t)stage * TG_STAGE, sb = sa + 2 * TG_PLANE;
@@ -677,7 +680,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
                     int lo, hi;
                     kb_range(s, sp, lo, hi);
                     for (int kb = lo; kb < hi; ++kb) {
-                        const uint32_t combos = (p.a_hiflag[s] && p.nA[s] == 2 && p.a_hiflag[s][kb / 2] == 0u) ? (p.combos[s] & 0x3u) : p.combos[s];
+                        const uint32_t combos = (p.a_hiflag[s] && p.nA[s] == 2 && (p.a_hiflag[s][kb / 2] & 1u) == 0u) ? (p.combos[s] & 0x3u) : p.combos[s];
                         mbar_wait_backoff(smem_u32(&bar_full[stage]), phase);
                         tc_fence_after();
                         const uint32_t sa = smem_base + (uint32_t)stage * TG_STAGE, sb = sa + 2 * TG_PLANE;

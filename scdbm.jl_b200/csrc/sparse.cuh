@@ -31,7 +31,7 @@ __global__ void k_scatter_compressed(const int64_t* __restrict__ ptr, const int3
             dst.p0[j] = a;
             if (dst.p1) dst.p1[j] = hb;
             if (dst.f) dst.f[j] = v;
-            if (dst.hiflag && (__bfloat16_as_ushort(hb) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 1u;
+            if (dst.hiflag && (__bfloat16_as_ushort(hb) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 3u;
         }
     }
 }
@@ -160,7 +160,7 @@ __global__ void k_generate_counts(MatView dst, const float* __restrict__ gene_me
             big = big || o[j] >= COUNT_BASE;
         }
         mat_store4(dst, row, c0, o, nvalid);
-        if (big && dst.hiflag) dst.hiflag[row / 128] = 1u;
+        if (big && dst.hiflag) dst.hiflag[row / 128] = 3u;
     }
 }
 

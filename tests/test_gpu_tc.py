@@ -116,6 +116,14 @@ def test_tc_large_counts_hi_plane_flags(pkg, tc, simt):
     pkg.gibbssample_(p2s, m2s, 3)
     for a, b in zip(p2t.to_host(), p2s.to_host()):
         assert np.mean(a != b) < 3e-3
+    # one more sweep lands in the other particle buffer: its hi plane (in use two sweeps ago) must have been
+    # zero-filled lazily -- the Float64 download reads both planes regardless of the flags
+    pkg.gibbssample_(p2t, m2t, 1)
+    pkg.gibbssample_(p2s, m2s, 1)
+    for a, b in zip(p2t.to_host(), p2s.to_host()):
+        assert np.mean(a != b) < 3e-3
+    assert p2t.to_host()[0].max() < 2048
+    assert np.array_equal(p2t.layer(0).to_host_u16().astype(float), p2t.to_host()[0])
 
 
 @pytest.mark.parametrize("V,H,npos,nneg", [(130, 67, 50, 37), (256, 128, 700, 64), (2000, 256, 1500, 100)])
