@@ -30,7 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 UNITS = [2000, 256, 64]
-NB_DRAM_BYTES_PER_CHAIN = 8829.0   # measured: (0.5845 + 8.2441) GB per NB down-sweep launch over 1e6 chains (ncu, round 1)
+NB_DRAM_BYTES_PER_CHAIN = 4630.0   # measured: (0.5274 + 4.1025) GB per NB down-sweep launch over 1e6 chains (ncu capture prof_r01g)
 MODEL_SEED = 3
 SEED = 20261019
 
@@ -175,9 +175,10 @@ def run_ours(args):
     roofline = {"kernel": "fused NB down-sweep GEMM (v|h1: tcgen05/SIMT GEMM + NB-mean + Philox NB draw)",
                 "bound": "tensor", "achieved": achieved, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tflops_burst"],
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel: 8.829e9 B per launch at 1,000,000 chains
-                # (ncu --set full capture, profiles/r01_ncu_summary.md); both count planes are written once per sweep
-                "traffic": NB_DRAM_BYTES_PER_CHAIN * n, "traffic_source": "ncu capture r01f scaled by chains",
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel: 4.63e9 B per launch at 1,000,000 chains
+                # (ncu --set full capture, profiles/r01_ncu_summary.md); the lo count plane is written once per sweep
+                "traffic": NB_DRAM_BYTES_PER_CHAIN * n, "traffic_source": "ncu --set full capture prof_r01g (profiles/r01_ncu_summary.md) scaled by chains",
+                "issue_active_pct_ncu": 72.7, "pipes_pct_ncu": {"alu": 43.8, "fma_heavy": 38.7, "xu": 33.7, "tensor": 12.5},
                 "peak_source": pk["source"] + ", burst (kernel timed alone)",
                 "launch_ms": k_ms, "flops_per_launch": flops, "nb_draws_per_sec": n * UNITS[0] / (k_ms * 1e-3),
                 "note": "sampled sweeps are bound by the draw epilogue (issue/MUFU), not by the tensor pipe; see DESIGN.md"}

@@ -1249,7 +1249,7 @@ int32_t scdbm_particles_init(scdbm_particles* p, int32_t biased) {
             if (m->L[0].kind == SCDBM_VIS_NEGBIN) { mode = 3; r = m->L[0].r; }
             else { mode = biased ? 1 : 0; bias = m->L[0].a; }
         } else { mode = biased ? 1 : 0; bias = m->L[i - 1].b; }
-        set_hiflags(c, v, true);
+        set_hiflags(c, v, false);   // k_init rewrites both planes and raises the flag of a row tile that gets a count >= 2048
         k_init<<<grid1d(v.rows * ((v.cols + 3) / 4)), 256, 0, c->stream>>>(v, mode, bias, r, k0, k1, (uint32_t)i,
                                                                             (uint32_t)p->row_offset);
         CK(cudaGetLastError());

@@ -296,6 +296,7 @@ __global__ void k_init(MatView dst, int mode, const float* __restrict__ bias, co
                     rk = fast_rcp(k + 1.0f);
                 }
                 o[j] = k;
+                if (k >= COUNT_BASE && dst.hiflag) dst.hiflag[row / 128] = 3u;
             }
         } else {
             for (int j = 0; j < nvalid; ++j) {
