@@ -68,6 +68,8 @@ struct TcParams {
     int32_t m_tiles, n_tiles;
     int32_t stages, stage_bytes;
     int32_t a_tiles;      // A-plane tiles reserved per stage (1 or 2)
+    int32_t split_hi[2];  // 1: COUNT source -- the (rarely used) hi plane is contracted in a second k-pass through the
+                          //    same single A slot instead of occupying a second A tile in every stage
     int32_t pair;         // 1: a work tile is 256 rows = two M=128 MMA tiles sharing every B (weight) tile load:
                           //    a third less L2 -> shared-memory operand traffic (the up-sweep is L2-bandwidth-bound)
     const uint32_t* a_hiflag[2];   // per source: COUNT operand's per-row-tile "hi plane in use" flags (nullptr: always)
@@ -261,19 +263,22 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 const uint32_t a_bytes = (uint32_t)rows * TC_BK * 2;
                 const int m0 = (tile / p.n_tiles) * rows, n0 = (tile % p.n_tiles) * BN;
                 for (int s = 0; s < p.nsrc; ++s) {
-                    // counts >= 256 are rare: skip the hi plane of a COUNT operand unless this row tile has one
-                    const int nA = tc_use_hi(p, s, tile / p.n_tiles) ? p.nA[s] : 1;
+                    // counts >= 2048 are rare: the hi plane of a COUNT operand is contracted only where this row tile has one
+                    const bool hi = tc_use_hi(p, s, tile / p.n_tiles);
+                    const int npass = p.split_hi[s] ? (hi ? 2 : 1) : 1;
+                    const int nA = p.split_hi[s] ? 1 : (hi ? p.nA[s] : 1);
                     const uint32_t tx = (uint32_t)nA * a_bytes + 2 * B_TILE;
-                    for (int kb = 0; kb < p.kblocks[s]; ++kb) {
-                        mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-                        const uint32_t full = smem_u32(&bar_full[stage]);
-                        const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
-                        mbar_expect_tx(full, tx);
-                        for (int pa = 0; pa < nA; ++pa) tma_load_2d(sa + pa * a_bytes, &maps.a[s][pa], full, kb * TC_BK, m0);
-                        for (int pb = 0; pb < 2; ++pb)
-                            tma_load_2d(sa + (uint32_t)p.a_tiles * a_bytes + pb * B_TILE, &maps.b[s][pb], full, kb * TC_BK, n0);
-                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-                    }
+                    for (int pass = 0; pass < npass; ++pass)
+                        for (int kb = 0; kb < p.kblocks[s]; ++kb) {
+                            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+                            const uint32_t full = smem_u32(&bar_full[stage]);
+                            const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
+                            mbar_expect_tx(full, tx);
+                            for (int pa = 0; pa < nA; ++pa) tma_load_2d(sa + pa * a_bytes, &maps.a[s][pa + pass], full, kb * TC_BK, m0);
+                            for (int pb = 0; pb < 2; ++pb)
+                                tma_load_2d(sa + (uint32_t)p.a_tiles * a_bytes + pb * B_TILE, &maps.b[s][pb], full, kb * TC_BK, n0);
+                            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                        }
                 }
             }
         }
@@ -291,8 +296,10 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 const uint32_t tmem_d = tmem_base + (uint32_t)(astage * halves) * BN;
                 uint32_t accumulate = 0;
                 for (int s = 0; s < p.nsrc; ++s) {
-                    const uint32_t combos = tc_use_hi(p, s, m_blk) ? p.combos[s] : (p.combos[s] & 0x3u);
-                    for (int kb = 0; kb < p.kblocks[s]; ++kb) {
+                    const bool hi = tc_use_hi(p, s, m_blk);
+                    const uint32_t combos = (p.split_hi[s] || !hi) ? (p.combos[s] & 0x3u) : p.combos[s];
+                    const int nkb = p.kblocks[s] * ((p.split_hi[s] && hi) ? 2 : 1);    // second pass: the hi count plane in the same A slot
+                    for (int kb = 0; kb < nkb; ++kb) {
                         mbar_wait(smem_u32(&bar_full[stage]), phase);
                         tc_fence_after();
                         const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
@@ -502,7 +509,7 @@ inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, i
     const int slot = (BN == 64 ? 0 : BN == 128 ? 3 : 6) + EK;   // BN 192/224: slot 7
     constexpr int B_TILE = BN * TC_BK * 2;
     const int qbytes = (EK == 1) ? EPW * tc_epi_smem(EPW, BN / (EPW / 4)) : 0;
-    p.a_tiles = std::max(p.nA[0], p.nsrc > 1 ? p.nA[1] : 1);
+    p.a_tiles = std::max(p.split_hi[0] ? 1 : p.nA[0], p.nsrc > 1 ? (p.split_hi[1] ? 1 : p.nA[1]) : 1);
     p.stage_bytes = p.a_tiles * (p.pair ? 2 : 1) * TC_A_TILE + 2 * B_TILE;
     p.stages = std::max(1, std::min(TC_MAX_STAGES, (TC_SMEM_BUDGET + 20 * 1024 - qbytes) / p.stage_bytes));
     const int smem = p.stages * p.stage_bytes + 1024 + qbytes;
@@ -554,6 +561,7 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
         p.nA[s] = a.p1 ? 2 : 1;
         // plane products: binary x (hi,lo); count (lo,hi) x (hi,lo); real (hi,lo) x (hi,lo) minus lo*lo
         p.combos[s] = a.p1 ? (a.kind == MAT_COUNT ? 0xFu : 0x7u) : 0x3u;
+        p.split_hi[s] = (a.p1 && a.kind == MAT_COUNT) ? 1 : 0;
         bool ok = tc_make_map(t, &maps.a[s][0], a.p0, g.M, ops[s].K, a.ld, rows_per_tile);
         ok = ok && tc_make_map(t, &maps.a[s][1], a.p1 ? a.p1 : a.p0, g.M, ops[s].K, a.ld, rows_per_tile);
         ok = ok && tc_make_map(t, &maps.b[s][0], ops[s].b0, ops[s].N, ops[s].K, ops[s].ldb, BN);
