@@ -231,8 +231,9 @@ def run_ours(args):
                           "two pinned result buffers; the last copy completes inside the timed region",
                "cells_per_sec": world * n * ksteps / float(dt.item())}
 
-        # the same step with the row-compressed wire format (uint16 column indices + uint16 counts, ~20 % dense)
         del outs
+    if e2e is not None and world == 1:
+        # the same step with the row-compressed wire format (uint16 column indices + uint16 counts, ~20 % dense)
         cap = int(0.3 * n * UNITS[0])
         ib = torch.empty(cap, dtype=torch.uint16, pin_memory=True).numpy()
         vb = torch.empty(cap, dtype=torch.uint16, pin_memory=True).numpy()
