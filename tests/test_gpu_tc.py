@@ -219,3 +219,53 @@ def test_tc_pair_mode_large_m(pkg, tc, simt):
     got2 = pkg.dbmlayer(m, 1, v, h2, what=pkg.OUT_SAMPLE, tick=6, ctx=tc)
     ms = pkg.DeviceModel.from_host(to_pkg_model(pkg, dbm), simt)
     assert np.mean(got2 != pkg.dbmlayer(ms, 1, v, h2, what=pkg.OUT_SAMPLE, tick=6, ctx=simt)) < 5e-4
+
+
+def test_full_size_generation_properties(pkg, tc):
+    """BASELINE configuration C3 at (nearly) full size -- the oracle cannot follow here, so size-independent
+    properties: (1) any shard of chains generated on its own (global row offset) equals the same rows of the
+    big run bit for bit and equals the oracle on a slice it can afford; (2) the run is reproducible;
+    (3) dense uint16, Float64 and row-compressed downloads describe the same matrix (checksums);
+    (4) two disjoint halves of the chains agree in per-gene mean and zero fraction within sampling error."""
+    import bench
+    n, burnin, V = 400_000, 6, bench.UNITS[0]
+    L = bench.make_model()
+    host = [pkg.NegativeBinomialBernoulliRBM(**L[0]), pkg.BernoulliRBM(**L[1])]
+    m = pkg.DeviceModel.from_host(host, tc)
+    p = pkg.sampleparticles(m, n, burnin, row_offset=0, device=True)
+    big = p.layer(0).to_host_u16()
+    # (1) shards: last rows of the run (ragged start inside a 128-row tile) on the device and on the oracle
+    lo, cnt = n - 1000 - 37, 1000
+    shard = pkg.sampleparticles(m, cnt, burnin, row_offset=lo, device=True).layer(0).to_host_u16()
+    assert np.array_equal(shard, big[lo:lo + cnt])
+    dbm = [om.NegativeBinomialBernoulliRBM(L[0]["weights"], L[0]["visbias"], L[0]["hidbias"], L[0]["inversedispersion"]),
+           om.BernoulliRBM(L[1]["weights"], L[1]["visbias"], L[1]["hidbias"])]
+    rng = px.Rng(SEED)
+    ref = om.initparticles(dbm, 64, rng, row_offset=lo)
+    om.gibbssample_dbm(ref, dbm, rng, burnin)
+    assert np.mean(ref[0] != big[lo:lo + 64]) < 6e-3
+    # (2) reproducible
+    p2 = pkg.sampleparticles(m, n, burnin, row_offset=0, device=True)
+    s1, s2 = p.layer(0).column_stats(), p2.layer(0).column_stats()
+    assert all(np.array_equal(a, b) for a, b in zip(s1, s2))
+    # (3) one matrix, three wire formats
+    ptr, idx, val = p.layer(0).to_host_csr()
+    assert ptr[-1] == np.count_nonzero(big) and int(val.sum(dtype=np.int64)) == int(big.sum(dtype=np.int64))
+    assert np.array_equal(np.diff(ptr), np.count_nonzero(big, axis=1))
+    r = 123_456
+    row = np.zeros(V, dtype=np.uint16)
+    row[idx[ptr[r]:ptr[r + 1]]] = val[ptr[r]:ptr[r + 1]]
+    assert np.array_equal(row, big[r])
+    mean, var, zf = s1
+    assert np.allclose(mean, big.mean(axis=0, dtype=np.float64), rtol=1e-9, atol=1e-12)
+    assert np.allclose(zf, (big == 0).mean(axis=0), rtol=1e-9, atol=1e-12)
+    # (4) halves agree: |mean_a - mean_b| <= 6 SE, zero fractions likewise (statistics reduced on the device)
+    h = n // 2
+    ma, va, za = pkg.sampleparticles(m, h, burnin, row_offset=0, device=True).layer(0).column_stats()
+    mb, vb, zb = pkg.sampleparticles(m, h, burnin, row_offset=h, device=True).layer(0).column_stats()
+    assert np.allclose(0.5 * (ma + mb), mean, rtol=1e-9, atol=1e-12)          # the halves are the big run's rows
+    se = np.sqrt(va / h + vb / h) + 1e-9
+    assert np.all(np.abs(ma - mb) <= 6 * se)
+    sz = np.sqrt(za * (1 - za) / h + zb * (1 - zb) / h) + 1e-9
+    assert np.all(np.abs(za - zb) <= 6 * sz)
+    assert 0.7 < (big == 0).mean() < 0.95                  # 10x-like sparsity
