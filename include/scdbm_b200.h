@@ -10,7 +10,13 @@
  * Conventions
  *  - every function returns int32 status: 0 ok, <0 error class (below);
  *    scdbm_last_error() returns a thread-local message.
- *  - opaque handles are library-owned and released by *_destroy.
+ *  - opaque handles are library-owned and released by *_destroy.  Handles are
+ *    reference-counted: a child keeps its parent alive (matrices, models ->
+ *    context; particles, optimizers, trainers -> model), and every scdbm_mat*
+ *    handed out by scdbm_particles_layer / scdbm_trainer_chainstate /
+ *    scdbm_trainer_estimated_mean is a SHARED handle (one more reference on
+ *    the same matrix) that the caller releases with scdbm_mat_destroy -- it
+ *    stays valid after the particles / trainer object is destroyed.
  *  - host matrices are COLUMN-MAJOR Float64 with explicit leading dimension
  *    (a Julia Matrix{Float64} or a NumPy order='F' array passes its pointer
  *    unchanged); host buffers are never retained after return.
@@ -159,7 +165,9 @@ int32_t scdbm_particles_create(scdbm_model* m, int64_t nparticles, uint64_t row_
                                scdbm_particles** out);
 int32_t scdbm_particles_destroy(scdbm_particles* p);
 int32_t scdbm_particles_init(scdbm_particles* p, int32_t biased);
-int32_t scdbm_particles_layer(scdbm_particles* p, int32_t layer, scdbm_mat** borrowed);
+/* shared handle of the matrix that holds layer `layer` NOW (release with scdbm_mat_destroy); a later
+ * scdbm_gibbs may move the layer to the particles' second buffer -- fetch the handle again after sampling. */
+int32_t scdbm_particles_layer(scdbm_particles* p, int32_t layer, scdbm_mat** shared);
 int32_t scdbm_particles_clock(scdbm_particles* p, int64_t* clock, int64_t set_to /* <0: keep */);
 /* gibbssample!(particles, dbm, nsteps) (src/gibbssampling.jl:153-182): synchronous
  * update of all layers; temperature scales all weight matrices (copyannealed!,
@@ -198,12 +206,15 @@ int32_t scdbm_meanfield(scdbm_model* m, const scdbm_mat* x, double eps, int32_t 
  * (src/optimizers.jl:34-39,57-70,103). */
 int32_t scdbm_opt_create(scdbm_model* m, scdbm_opt** out);
 int32_t scdbm_opt_destroy(scdbm_opt* o);
-/* computegradient!(opt, v, vmodel, h, hmodel, rbm) (src/optimizers.jl:207-214,263-310).
- * npos/nneg <= 0: use the row counts.  normalize == 0 leaves the un-normalised
- * partial sums (data-parallel mode: allreduce, then scdbm_opt_scale). */
+/* computegradient!(opt, v, vmodel, h, hmodel, rbm) (src/optimizers.jl:207-214,263-310):
+ * dW = v'h / rows(v) - vmodel'hmodel / nneg, da, db likewise from column means.
+ * nrows_used > 0: only the first nrows_used rows of vmodel/hmodel enter (short last
+ * minibatch of PCD, src/rbmtraining.jl:580-585); <= 0: all rows. */
 int32_t scdbm_compute_gradient(scdbm_opt* o, scdbm_model* m, int32_t l, const scdbm_mat* v, const scdbm_mat* vmodel,
                                const scdbm_mat* h, const scdbm_mat* hmodel, int64_t nrows_used);
-/* computegradient!(StackedOptimizer, mu, particles, dbm) (src/optimizers.jl:431-442) */
+/* computegradient!(StackedOptimizer, mu, particles, dbm) (src/optimizers.jl:431-442).
+ * pos_scale / neg_scale > 0 replace 1/rows(mu), 1/nparticles: a data-parallel rank passes the
+ * GLOBAL 1/n+, 1/n- so that the allreduce(sum) of the per-rank blocks is the full-batch gradient. */
 int32_t scdbm_compute_gradient_dbm(scdbm_opt* o, scdbm_model* m, scdbm_particles* mu, scdbm_particles* particles,
                                    double pos_scale, double neg_scale);
 /* updateparameters!(bm, opt) (src/optimizers.jl:450-454,478-485,505-520); l < 0: all layers */
@@ -218,11 +229,11 @@ int32_t scdbm_opt_buffer(scdbm_opt* o, void** device_ptr, int64_t* nfloats);
 int32_t scdbm_trainer_create(scdbm_model* m, int32_t l, int32_t batchsize, int32_t pcd, scdbm_trainer** out);
 int32_t scdbm_trainer_destroy(scdbm_trainer* t);
 int32_t scdbm_trainer_clock(scdbm_trainer* t, int64_t* clock, int64_t set_to);
-int32_t scdbm_trainer_chainstate(scdbm_trainer* t, scdbm_mat** borrowed);
+int32_t scdbm_trainer_chainstate(scdbm_trainer* t, scdbm_mat** shared);   /* release with scdbm_mat_destroy */
 /* `estimatedmean` of trainrbm! (src/rbmtraining.jl:536,575-576): when enabled, each epoch records the model
  * means of its minibatches, in minibatch order, as a (nsamples x nvisible) matrix. */
 int32_t scdbm_trainer_track_mean(scdbm_trainer* t, int32_t enable);
-int32_t scdbm_trainer_estimated_mean(scdbm_trainer* t, scdbm_mat** borrowed);
+int32_t scdbm_trainer_estimated_mean(scdbm_trainer* t, scdbm_mat** shared);   /* release with scdbm_mat_destroy */
 /* mle_for_θ (src/rbmtraining.jl:675-719), all genes at once: penalised Fisher scoring of the NB inverse
  * dispersion of gene g from (x[:,g], mu[:,g]); theta[nvisible] out. */
 int32_t scdbm_mle_theta(const scdbm_mat* x, const scdbm_mat* mu, double lambda, int32_t maxiter, double convtol,

@@ -212,10 +212,14 @@ class Mat:
             self.h = handle
 
     @classmethod
-    def borrowed(cls, ctx, handle):
+    def shared(cls, ctx, handle, owner=None):
+        """Wraps a shared handle returned by `scdbm_particles_layer` / `scdbm_trainer_*`: the library counts
+        it as one more reference on the matrix, released by `close()`; `owner` is kept alive as well."""
         r, c, k = C.c_int64(), C.c_int64(), C.c_int32()
         check(lib().scdbm_mat_shape(handle, C.byref(r), C.byref(c), C.byref(k)))
-        return cls(ctx, r.value, c.value, k.value, handle, owns=False)
+        m = cls(ctx, r.value, c.value, k.value, handle, owns=True)
+        m._keepalive = owner
+        return m
 
     @classmethod
     def from_host(cls, ctx, x, kind):
@@ -438,7 +442,7 @@ class DeviceParticles:
     def layer(self, i):
         h = C.c_void_p()
         check(lib().scdbm_particles_layer(self.h, i, C.byref(h)))
-        return Mat.borrowed(self.model.ctx, h)
+        return Mat.shared(self.model.ctx, h, self)
 
     @property
     def clock(self):
@@ -615,7 +619,6 @@ def samples(bm, nsamples, burnin=50, samplelast=True, row_offset=0, device=False
     if samplelast:
         p = sampleparticles(m, nsamples, burnin, row_offset, device=True)
         out = p.layer(0)
-        out._keepalive = p
     else:
         p = sampleparticles(m, nsamples, burnin - 1, row_offset, device=True)
         out = Mat(m.ctx, nsamples, m.units[0], L.MAT_REAL)
@@ -748,7 +751,7 @@ class RBMTrainer:
     def chainstate(self):
         h = C.c_void_p()
         check(lib().scdbm_trainer_chainstate(self.h, C.byref(h)))
-        return Mat.borrowed(self.model.ctx, h)
+        return Mat.shared(self.model.ctx, h, self)
 
     def track_mean(self, enable=True):
         check(lib().scdbm_trainer_track_mean(self.h, int(enable)))
@@ -756,7 +759,7 @@ class RBMTrainer:
     def estimated_mean(self):
         h = C.c_void_p()
         check(lib().scdbm_trainer_estimated_mean(self.h, C.byref(h)))
-        return Mat.borrowed(self.model.ctx, h)
+        return Mat.shared(self.model.ctx, h, self)
 
     def close(self):
         if self.h:

@@ -137,12 +137,17 @@ static void model_release(scdbm_model* m) {
     if (--m->live == 0 && m->closed) model_free(m);
 }
 
+// Reference-counted: the creator holds one reference; every handle handed out by scdbm_particles_layer /
+// scdbm_trainer_chainstate / scdbm_trainer_estimated_mean adds one, so a handle can never dangle when its
+// particles / trainer object is destroyed first.  scdbm_mat_destroy drops one reference.
 struct scdbm_mat {
     scdbm_ctx* ctx;
     MatView v;
     bool owns;
     int64_t* csr_indptr = nullptr;   // device row pointers of the pending CSR download (scdbm_mat_csr_prepare)
     int64_t csr_nnz = -1;
+    int64_t refs = 1;
+    scdbm_mat* parent = nullptr;     // view (owns == false): the matrix whose planes `v` aliases, retained
 };
 
 struct scdbm_particles {
@@ -224,8 +229,13 @@ static scdbm_mat* mat_new(scdbm_ctx* ctx, int64_t rows, int64_t cols, int kind) 
     }
     return m;
 }
+static scdbm_mat* mat_retain(scdbm_mat* m) {
+    if (m) m->refs++;
+    return m;
+}
+// drops one reference; the last one frees (stream-ordered for the device memory)
 static void mat_free(scdbm_mat* m) {
-    if (!m) return;
+    if (!m || --m->refs > 0) return;
     if (m->csr_indptr) cudaFreeAsync(m->csr_indptr, m->ctx->stream);
     if (m->owns) {
         cudaStream_t st = m->ctx->stream;
@@ -238,7 +248,15 @@ static void mat_free(scdbm_mat* m) {
         ctx_release(c);
         return;
     }
+    scdbm_mat* parent = m->parent;
     delete m;
+    mat_free(parent);
+}
+// non-owning view of another matrix' planes (mean-field: layer 0 of mu is the data matrix); keeps `of` alive
+static scdbm_mat* mat_view_of(scdbm_mat* of) {
+    auto* m = new scdbm_mat{of->ctx, of->v, false};
+    m->parent = mat_retain(of);
+    return m;
 }
 static MatView rows_view(const MatView& v, int64_t rows) {
     MatView r = v;
@@ -1224,7 +1242,7 @@ int32_t scdbm_particles_destroy(scdbm_particles* p) {
     cudaStreamSynchronize(p->model->ctx->stream);
     for (auto* x : p->cur) mat_free(x);
     for (auto* x : p->nxt) mat_free(x);
-    if (p->alias0) delete p->alias0;
+    mat_free(p->alias0);
     cudaFree(p->hoist);
     scdbm_model* pm = p->model;
     delete p;
@@ -1265,7 +1283,7 @@ int32_t scdbm_particles_layer(scdbm_particles* p, int32_t layer, scdbm_mat** bor
     REQUIRE(layer >= 0 && layer < (int)p->cur.size(), "layer index out of range");
     scdbm_mat* x = (layer == 0 && p->real_valued) ? p->alias0 : p->cur[layer];
     REQUIRE(x, "layer 0 of mean-field particles is set by scdbm_meanfield");
-    *borrowed = x;
+    *borrowed = mat_retain(x);
     API_END
 }
 
@@ -1372,7 +1390,10 @@ static void meanfield_impl(scdbm_model* m, const scdbm_mat* x, double eps, int m
     REQUIRE(mu->real_valued, "mu must be created with real_valued = 1");
     REQUIRE(mu->n == n, "mu must have as many particles as x has rows");
     REQUIRE(x->v.cols == m->L[0].V, "data width does not match the visible layer");
-    if (!mu->alias0) mu->alias0 = new scdbm_mat{c, x->v, false};
+    if (!mu->alias0 || mu->alias0->parent != x) {
+        mat_free(mu->alias0);   // handles given out for the previous data matrix stay valid (they hold references)
+        mu->alias0 = mat_view_of(const_cast<scdbm_mat*>(x));
+    }
     mu->alias0->v = x->v;
     if (n == 0) { if (niter) *niter = 0; if (delta_out) *delta_out = 0; return; }
     // hoist x*W1 (loop invariant; the reference recomputes it, quirk B10)
@@ -1678,7 +1699,7 @@ int32_t scdbm_trainer_chainstate(scdbm_trainer* t, scdbm_mat** borrowed) {
     API_BEGIN
     REQUIRE(t && borrowed, "NULL argument");
     REQUIRE(t->chain, "trainer was created without PCD");
-    *borrowed = t->chain;
+    *borrowed = mat_retain(t->chain);
     API_END
 }
 
@@ -1783,7 +1804,7 @@ int32_t scdbm_trainer_estimated_mean(scdbm_trainer* t, scdbm_mat** borrowed) {
     API_BEGIN
     REQUIRE(t && borrowed, "NULL argument");
     REQUIRE(t->est, "no epoch has been trained with scdbm_trainer_track_mean enabled");
-    *borrowed = t->est;
+    *borrowed = mat_retain(t->est);
     API_END
 }
 

@@ -248,9 +248,27 @@ def test_nb_same_uniforms(pkg, ctx):
     got = pkg.samplevisible(m, h1, u=u, tick=9)
     ref = om.samplevisible(dbm[0], h1, px.Rng(SEED), 0, 9, u=u)
     bad = (got != ref) & inv
-    # an inversion draw can only differ where u falls within fp32 round-off of a CDF step
+    # an inversion draw can only differ where u falls within fp32 round-off of a CDF step: every
+    # mismatch must be off by one AND have u inside the ambiguity band around the CDF value that separates the two
     assert bad.sum() <= max(2, int(2e-4 * inv.sum())), f"{bad.sum()} inversion mismatches of {inv.sum()}"
     assert np.all(np.abs(got[bad] - ref[bad]) <= 1)
+    from scipy.stats import nbinom
+    rr = np.broadcast_to(dbm[0].inversedispersion, mu.shape)
+    step = nbinom.cdf(np.minimum(got, ref)[bad], rr[bad], rr[bad] / (mu[bad] + rr[bad]))
+    dist = np.abs(u[bad] - step)
+    print(f"[G2] NB same-uniforms: {int(bad.sum())} mismatches of {int(inv.sum())}; max |u - CDF step| = {dist.max() if dist.size else 0.0:.2e}")
+    assert np.all(dist <= 4e-6), "NB mismatch outside the ambiguity band of its CDF step"
+    # adversarial: uniforms placed right beside the CDF step of the oracle's own draw
+    k0 = np.where(inv, ref, 0.0)
+    cdf0 = nbinom.cdf(k0, rr, rr / (mu + rr))
+    u2 = np.clip(np.round(cdf0 * 2**23 - 0.5) + 0.5 + g.integers(-3, 4, cdf0.shape), 0.5, 2**23 - 0.5) / 2**23
+    got2 = pkg.samplevisible(m, h1, u=u2, tick=9)
+    ref2 = om.samplevisible(dbm[0], h1, px.Rng(SEED), 0, 9, u=u2)
+    bad2 = (got2 != ref2) & inv
+    assert np.all(np.abs(got2[bad2] - ref2[bad2]) <= 1)
+    step2 = nbinom.cdf(np.minimum(got2, ref2)[bad2], rr[bad2], rr[bad2] / (mu[bad2] + rr[bad2]))
+    print(f"[G2] NB adversarial uniforms: {int(bad2.sum())} mismatches of {int(inv.sum())}")
+    assert np.all(np.abs(u2[bad2] - step2) <= 4e-6)
     # tiny K: exact equality expected
     tiny = small_dbm((8, 4, 2), seed=9)
     mt = dm_of(pkg, ctx, tiny)
