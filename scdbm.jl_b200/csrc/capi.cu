@@ -281,6 +281,7 @@ static EpiParams epi_base(scdbm_ctx* ctx) {
     e.mu_inv_max = ctx->mu_inv_max;
     e.k0 = (uint32_t)(ctx->seed & 0xFFFFFFFFu);
     e.k1 = (uint32_t)(ctx->seed >> 32);
+    philox_round_keys(e.k0, e.k1, e.rk);
     return e;
 }
 
@@ -621,8 +622,10 @@ int32_t scdbm_model_create(scdbm_ctx* c, int32_t nrbms, const int32_t* units, in
         CK(cudaMallocAsync(&L.b, (size_t)L.H * sizeof(float), c->stream));
         CK(cudaMallocAsync(&L.r, (size_t)L.V * sizeof(float), c->stream));
         if (L.kind == SCDBM_VIS_NEGBIN) {
-            CK(cudaMallocAsync(&L.nbc, (size_t)L.V * sizeof(float4), c->stream));
-            // padded past the last column tile of any tile width: the padding never queues a draw
+            // both per-gene tables are padded past the last column tile of any tile width (the padding never queues a draw;
+            // a 2^-32 event -- Philox word == 0xFFFFFFFF -- reads benign constants there)
+            CK(cudaMallocAsync(&L.nbc, (size_t)(round_up(L.V, 256) + 256) * sizeof(float4), c->stream));
+            k_fill_nbc_pad<<<grid1d(round_up(L.V, 256) + 256), 256, 0, c->stream>>>(L.nbc, round_up(L.V, 256) + 256);
             CK(cudaMallocAsync(&L.nbT, (size_t)(round_up(L.V, 256) + 256) * sizeof(uint32_t), c->stream));
             CK(cudaMemsetAsync(L.nbT, 0xFF, (size_t)(round_up(L.V, 256) + 256) * sizeof(uint32_t), c->stream));
         }

@@ -61,6 +61,7 @@ struct EpiParams {
     float pshift;           // 1e-6 for the gamma-Poisson form of the reference, else 0
     float mu_inv_max;       // inversion / gamma-Poisson switch
     uint32_t k0, k1;        // Philox key (seed)
+    uint32_t rk[20];        // Philox round keys {k0 + i W0, k1 + i W1}: constant-bank operands of the sampling epilogues
     uint32_t tick, stream;  // Philox counter words 2,3
     uint32_t row_offset;    // global index of row 0 (chain sharding)
     const float* uniforms;  // optional explicit uniforms [rows x ldu], row-major fp32

@@ -205,6 +205,11 @@ __global__ void k_refresh_nbc(const float* __restrict__ a, const float* __restri
     nbT[i] = mt >= 8388608.0 ? 0xFFFFFFFFu : (mt <= 0.0 ? 0u : ((uint32_t)mt << 9));
 }
 
+__global__ void k_fill_nbc_pad(float4* nbc, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) nbc[i] = make_float4(-1.0f, 1.0f, 1e-6f, 0.0f);
+}
+
 // before an NB sampling launch into `flags`' matrix: tiles whose hi plane was in use (or marked) must be zero-filled
 // by this launch (-> 2); tiles that were zero-filled by the previous launch and got no new entry are clean (-> 0)
 __global__ void k_flags_advance(uint32_t* __restrict__ flags, int64_t n) {

@@ -164,7 +164,7 @@ __device__ __forceinline__ float nb_entry_draw(const EpiParams& e, float acc, fl
 }
 
 __device__ __forceinline__ void epi_bern4(const EpiParams& e, int64_t row, int64_t col0, const float (&acc)[4], int nvalid) {
-    const uint4 w = philox_group(e, (uint32_t)row, (uint32_t)(col0 >> 2));
+    const uint4 w = philox_group_rk(e, (uint32_t)row, (uint32_t)(col0 >> 2));
     const float u[4] = {u23(w.x), u23(w.y), u23(w.z), u23(w.w)};
     float o[4];
 #pragma unroll

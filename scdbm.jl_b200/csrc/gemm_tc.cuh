@@ -47,11 +47,12 @@ struct TcGradArgs {
 constexpr int TC_BM = 128, TC_BK = 64;
 constexpr int TC_A_TILE = TC_BM * TC_BK * 2;  // 16 KB
 constexpr int TC_MAX_STAGES = 8;
-// two-pass NB epilogue: queue entries per epilogue warp ({acc, u, pos} = 12 B each), sized to the shared
-// memory left beside the GEMM stages
-__host__ __device__ constexpr int tc_qcap(int epw) { return epw > 16 ? 256 : 384; }
-// per epilogue warp: queue (12 B per entry) + a 32 x CW fp16 staging tile of the lo count plane
-__host__ __device__ constexpr int tc_epi_smem(int epw, int cw) { return tc_qcap(epw) * 12 + 32 * cw * 2; }
+// two-pass NB epilogue, per epilogue warp: a queue of 8-byte entries {accumulator, Philox word} with the entry's position
+// inside the warp's 32 x CW block packed into bits the draw does not use, a small queue of 16-byte survivor
+// states {u, P, q, k | position} for draws that outlive the unrolled first steps, and a 32 x CW fp16 staging
+// tile of the lo count plane
+constexpr int TC_QCAP = 256, TC_SCAP = 64, TC_NB_STEPS = 3;
+__host__ __device__ constexpr int tc_epi_smem(int cw) { return TC_QCAP * 8 + TC_SCAP * 16 + 32 * cw * 2; }
 constexpr int TC_SMEM_BUDGET = 200 * 1024;
 
 struct alignas(64) TcMaps {
@@ -188,6 +189,28 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
                  : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// pass A of the NB epilogue for one element: `word >= T` (the draw is not decided by the zero shortcut) -> append the
+// 8-byte entry {x, y} to the warp's queue at shared address qbase + 8 * slot.  One compare feeds the ballot and
+// predicates the store; no branch.
+__device__ __forceinline__ void nb_enqueue(uint32_t word, uint32_t T, uint32_t x, uint32_t y, uint32_t lanes_below, uint32_t qbase, int& qn) {
+    uint32_t cnt;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 m, t;\n\t"
+        "setp.ge.u32 p, %2, %3;\n\t"
+        "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+        "and.b32 t, m, %6;\n\t"
+        "popc.b32 t, t;\n\t"
+        "add.u32 t, t, %1;\n\t"
+        "shl.b32 t, t, 3;\n\t"
+        "add.u32 t, t, %7;\n\t"
+        "@p st.shared.v2.u32 [t], {%4, %5};\n\t"
+        "popc.b32 %0, m;\n\t}"
+        : "=r"(cnt)
+        : "r"(qn), "r"(word), "r"(T), "r"(x), "r"(y), "r"(lanes_below), "r"(qbase)
+        : "memory");
+    qn += (int)cnt;
+}
 
 // tile schedule shared by the three warp roles: it = 0, 1, ... -> flat tile id m * n_tiles + n, or -1 at the end
 __device__ __forceinline__ int tc_tile(const TcParams& p, int it) {
@@ -333,40 +356,131 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
         int astage = 0;
         uint32_t aphase = 0;
         float delta_local = 0.0f;
-        // two-pass NB epilogue state (EK == 1): per-warp queue in dynamic shared memory behind the GEMM stages
-        float* q_acc = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (uint32_t)p.stages * (uint32_t)p.stage_bytes +
-                                                (uint32_t)(warp - 4) * (uint32_t)tc_epi_smem(EPW, CW));
-        uint2* q_aw = reinterpret_cast<uint2*>(q_acc);                                  // {accumulator, Philox word} per queued entry
-        uint32_t* q_pos = reinterpret_cast<uint32_t*>(q_aw + tc_qcap(EPW));
-        __nv_bfloat16* s_lo = reinterpret_cast<__nv_bfloat16*>(q_pos + tc_qcap(EPW));   // [32][CW] staging tile, 16 B aligned
-        int64_t cur_m0 = 0, cur_n0 = 0;
+        // two-pass NB epilogue state (EK == 1): per-warp queues in dynamic shared memory behind the GEMM stages
+        uint8_t* wsm = smem_raw + (smem_base - smem_u32(smem_raw)) + (uint32_t)p.stages * (uint32_t)p.stage_bytes +
+                       (uint32_t)(warp - 4) * (uint32_t)tc_epi_smem(CW);
+        uint2* Q = reinterpret_cast<uint2*>(wsm);                                   // {accumulator | row bit 4, Philox word | column, row bits 0-3}
+        uint4* S = reinterpret_cast<uint4*>(Q + TC_QCAP);                           // survivors {u, P, q, k << 16 | position}
+        uint16_t* s_lo = reinterpret_cast<uint16_t*>(S + TC_SCAP);                  // [32][CW] fp16 staging tile, 16 B aligned
+        int64_t cur_m0 = 0;
+        uint32_t cur_c0 = 0;                                                        // global column of the warp's slice
         const uint32_t lt = (1u << lane) - 1u;
         const float acc_scale = p.epi.acc_scale ? __ldg(p.epi.acc_scale) : 1.0f;   // 1/s of the fp16 weight planes
-        int qn = 0;
-        auto drain = [&]() {
+        int qn = 0, sn = 0;
+        const uint32_t qbase = smem_u32(Q);
+        // a finished draw: lo plane into the staging tile; counts >= 2048 (rare) patch the hi plane in global memory
+        auto put = [&](float k, int rl, int cl) {
+            float lo = k;
+            if (k >= COUNT_BASE) {
+                const EpiParams& e = p.epi;
+                const float hi = floorf(k * (1.0f / COUNT_BASE)) * COUNT_BASE;
+                lo = k - hi;
+                const int64_t r2 = cur_m0 + q * 32 + rl, c2 = (int64_t)cur_c0 + cl;
+                if (r2 < p.M && c2 < p.N) {
+                    e.out.p1[r2 * e.out.ld + c2] = plane_encode(hi);
+                    if (e.out.hiflag) e.out.hiflag[r2 / TC_BM] = 3u;
+                }
+            }
+            s_lo[rl * CW + cl] = __half_as_ushort(__float2half_rn(lo));
+        };
+        // second stage: `cnt` (<= 32) survivor states from S[base...], one per lane; the chop-down search runs to the end
+        auto stage2 = [&](int base, int cnt) {
+            const EpiParams& e = p.epi;
+            if (lane < cnt) {
+                const uint4 st = S[base + lane];
+                const int cl = (int)((st.w >> 4) & 31u), rl = (int)((st.w & 15u) | ((st.w >> 5) & 16u));
+                float u = __uint_as_float(st.x), P = __uint_as_float(st.y);
+                const float qq = __uint_as_float(st.z);
+                const float qr1 = qq * __ldg(&e.nbc[cur_c0 + cl].w);
+                float k = (float)(st.w >> 16);
+                float rk = fast_rcp(k + 1.0f);
+                while (u >= P && P > PMIN_F) {
+                    u -= P;
+                    k += 1.0f;
+                    const float ratio = fmaf(qr1, rk, qq);
+                    rk = fast_rcp(k + 1.0f);
+                    P *= ratio;
+                }
+                put(k, rl, cl);
+            }
+        };
+        // first stage over queue entries [0, n): NB mean, P0, then TC_NB_STEPS predicated steps of the search (no
+        // divergence: most draws end here); the rest are compacted into S and finished 32 at a time by stage2
+        auto stage1 = [&](int n) {
             const EpiParams& e = p.epi;
             __syncwarp();
-            for (int i0 = 0; i0 < qn; i0 += 32) {
+            for (int i0 = 0; i0 < n; i0 += 32) {
                 const int i = i0 + lane;
-                if (i < qn) {
-                    const uint32_t pos = q_pos[i];
-                    const int rl = (int)(pos & 31u), cl = (int)(pos >> 5);
-                    const int64_t r2 = cur_m0 + q * 32 + rl;
-                    const int64_t c2 = cur_n0 + slice * CW + cl;
-                    if (r2 < p.M && c2 < p.N) {                                          // pass A also queues rows/columns of the tile padding
-                        const uint2 aw = q_aw[i];
-                        const float k = nb_entry_draw(e, __uint_as_float(aw.x), u23(aw.y), (uint32_t)r2 + e.row_offset, (uint32_t)c2);
-                        const float hi = (k >= COUNT_BASE) ? floorf(k * (1.0f / COUNT_BASE)) * COUNT_BASE : 0.0f;
-                        s_lo[rl * CW + cl] = plane_encode(k - hi);
-                        if (hi > 0.0f) {                                                 // rare: count >= 2048
-                            e.out.p1[r2 * e.out.ld + c2] = plane_encode(hi);
-                            if (e.out.hiflag) e.out.hiflag[r2 / TC_BM] = 3u;
+                bool surv = false;
+                uint4 st = make_uint4(0u, 0u, 0u, 0u);
+                if (i < n) {
+                    const uint2 en = Q[i];
+                    const int cl = (int)((en.y >> 4) & 31u), rl = (int)((en.y & 15u) | ((en.x & 1u) << 4));
+                    const uint32_t col = cur_c0 + (uint32_t)cl;
+                    const float4 c = __ldg(e.nbc + col);                             // {a, r, 1e-6/r, r-1}; padded like nbT
+                    float u = u23(en.y);
+                    const float x = fmaf(e.wscale, __uint_as_float(en.x) * acc_scale, c.x);
+                    const float E = fast_ex2(x * 1.4426950408889634f);
+                    float om = 1.0f - E;
+                    // x -> 0-: 1 - e^x cancels; -expm1(x) = -x (1 + x/2 + ... + x^5/720), |err| < 2e-9 on (-1/8, 0)
+                    if (x > -0.125f)
+                        om = -x * fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, 1.0f / 720.0f, 1.0f / 120.0f), 1.0f / 24.0f), 1.0f / 6.0f), 0.5f), 1.0f);
+                    if (c.y * E > (e.mu_inv_max - 1e-6f) * om) {                      // mean above mu_inv_max: gamma-Poisson, out of line
+                        const RngAddr g{e.k0, e.k1, (uint32_t)(cur_m0 + q * 32 + rl) + e.row_offset, col, e.tick, e.stream & 0xFFu};
+                        put(nb_draw_slow(x, c.y, u, e.pshift, e.mu_inv_max, g), rl, cl);
+                    } else {
+                        const float pp = om * fast_rcp(fmaf(c.z, om, 1.0f)) - e.pshift;
+                        const float qq = 1.0f - pp, qr1 = qq * c.w;
+                        // the first TC_NB_STEPS steps of the chop-down search, computed speculatively (no predicated
+                        // updates): go[s] = "the search is still running after s steps"; the count is the number of
+                        // steps taken, the survivor state is the last (u, P)
+                        float P = fast_ex2(c.y * fast_lg2(pp));
+                        bool go = (P > PMIN_F) && (u >= P);
+                        int k = 0;
+#pragma unroll
+                        for (int sidx = 0; sidx < TC_NB_STEPS; ++sidx) {
+                            k += go ? 1 : 0;
+                            u -= P;
+                            P *= fmaf(qr1, 1.0f / (float)(sidx + 1), qq);
+                            go = go && (P > PMIN_F) && (u >= P);
+                        }
+                        if (go) {
+                            surv = true;
+                            st = make_uint4(__float_as_uint(u), __float_as_uint(P), __float_as_uint(qq),
+                                            ((uint32_t)TC_NB_STEPS << 16) | ((uint32_t)(rl & 16) << 5) | ((uint32_t)cl << 4) | (uint32_t)(rl & 15));
+                        } else {
+                            put((float)k, rl, cl);
                         }
                     }
                 }
+                const uint32_t smask = __ballot_sync(0xffffffffu, surv);
+                if (surv) S[sn + __popc(smask & lt)] = st;
+                sn += __popc(smask);
+                if (sn >= 32) {
+                    __syncwarp();
+                    sn -= 32;
+                    stage2(sn, 32);
+                    __syncwarp();
+                }
             }
+        };
+        // mid-tile: whole batches only, the remainder moves to the front of the queue
+        auto drain_full = [&]() {
+            const int rem = qn & 31, full = qn - rem;
+            stage1(full);
             __syncwarp();
+            uint2 t = make_uint2(0u, 0u);
+            if (lane < rem) t = Q[full + lane];
+            __syncwarp();
+            if (lane < rem) Q[lane] = t;
+            qn = rem;
+        };
+        auto drain_all = [&]() {
+            stage1(qn);
             qn = 0;
+            __syncwarp();
+            if (sn > 0) { stage2(0, sn); sn = 0; }
+            __syncwarp();
         };
         for (int it = 0, tile; (tile = tc_tile(p, it)) >= 0; ++it) {
             const int halves = (EK != 1 && p.pair) ? 2 : 1;
@@ -376,7 +490,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 // lo count plane: staged in the warp's shared-memory tile (zeroed here, patched by pass B, written
                 // out coalesced at the end of the tile).  hi plane (counts >= 2048, rare): coalesced zero-fill now where
                 // the row tile is marked (full 32 B sectors: 4 lanes x 16 B per row, 8 rows per store), scattered patches from pass B.
-                cur_m0 = m0; cur_n0 = n0;
+                cur_m0 = m0; cur_c0 = (uint32_t)n0 + (uint32_t)(slice * CW);
                 const MatView& o = p.epi.out;
                 // the hi plane of a row tile is all zero unless its flag says otherwise (bit 1: stale entries of an
                 // earlier sweep, or of an earlier column tile of this launch -- re-zeroing those is harmless)
@@ -397,39 +511,34 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
             const int64_t row = m0 + q * 32 + lane;
             float rowsum = 0.0f;
             if constexpr (EK == 1) {
-                // ---- two-pass NB draw.  Pass A (all elements): Philox uniform vs the per-gene lower bound L of
-                // the zero probability; u < L => 0 (placeholder zeros are stored for every element).  The
-                // other ~20 % are queued in shared memory and drawn densely, one per lane, in pass B.
+                // ---- two-pass NB draw.  Pass A (all elements): Philox word vs the per-gene integer threshold T of
+                // a lower bound L of the zero probability (u < L  <=>  word < T, exactly the fp32 comparison of the
+                // 23-bit uniform; T is padded to whole tiles with 0xFFFFFFFF): below => the draw is 0 (the staging
+                // tile is pre-zeroed).  The other ~20 % are appended (ballot + popc) to the warp's queue and drawn
+                // densely, one per lane, in pass B.  The entry's position rides in bits the draw ignores: the 9 low
+                // bits of the word (the uniform uses the top 23) and the last mantissa bit of the accumulator.
                 const EpiParams& e = p.epi;
-#pragma unroll 2
+                const uint32_t lane_lo = (uint32_t)lane & 15u, lane_hi = (uint32_t)lane >> 4;
+#pragma unroll 1
                 for (int g = 0; g < CW / 4; ++g) {
                     uint32_t r[4];
                     tmem_ld4(taddr + g * 4, r);
-                    tmem_wait_ld();
-                    // u < L  <=>  Philox word < per-gene integer threshold T (exactly the fp32 comparison of the 23-bit
-                    // uniform; T is padded to whole tiles with 0xFFFFFFFF): no int->float conversion in pass A
-                    const uint32_t col0 = (uint32_t)n0 + (uint32_t)(slice * CW + g * 4);
-                    const uint4 w = philox_group(e, (uint32_t)row, col0 >> 2);
+                    const uint32_t col0 = cur_c0 + (uint32_t)(g * 4);
+                    const uint4 w = philox_group_rk(e, (uint32_t)row, col0 >> 2);
                     const uint4 T = __ldg(reinterpret_cast<const uint4*>(e.nbT + col0));
+                    tmem_wait_ld();
                     const uint32_t wj[4] = {w.x, w.y, w.z, w.w}, Tj[4] = {T.x, T.y, T.z, T.w};
+                    const uint32_t pos0 = ((uint32_t)g << 6) | lane_lo;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const bool nz = wj[j] >= Tj[j];
-                        const uint32_t mask = __ballot_sync(0xffffffffu, nz);
-                        if (nz) {
-                            const int slot = qn + __popc(mask & lt);
-                            q_aw[slot] = make_uint2(__float_as_uint(__uint_as_float(r[j]) * acc_scale), wj[j]);
-                            q_pos[slot] = ((uint32_t)(g * 4 + j) << 5) | (uint32_t)lane;
-                        }
-                        qn += __popc(mask);
-                    }
-                    if (qn > tc_qcap(EPW) - 128) drain();
+                    for (int j = 0; j < 4; ++j)
+                        nb_enqueue(wj[j], Tj[j], (r[j] & ~1u) | lane_hi, (wj[j] & ~0x1FFu) | (pos0 + (uint32_t)(j << 4)), lt, qbase, qn);
+                    if (qn > TC_QCAP - 128) drain_full();
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[astage]));
                 if (++astage == ASTAGES) { astage = 0; aphase ^= 1u; }
-                drain();
+                drain_all();
                 {   // coalesced write-out of the staged lo plane
                     const MatView& o = p.epi.out;
 #pragma unroll
@@ -508,7 +617,7 @@ template <int BN, int EK, int EPW>
 inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, int num_sms, cudaStream_t stream) {
     const int slot = (BN == 64 ? 0 : BN == 128 ? 3 : 6) + EK;   // BN 192/224: slot 7
     constexpr int B_TILE = BN * TC_BK * 2;
-    const int qbytes = (EK == 1) ? EPW * tc_epi_smem(EPW, BN / (EPW / 4)) : 0;
+    const int qbytes = (EK == 1) ? EPW * tc_epi_smem(BN / (EPW / 4)) : 0;
     p.a_tiles = std::max(p.split_hi[0] ? 1 : p.nA[0], p.nsrc > 1 ? (p.split_hi[1] ? 1 : p.nA[1]) : 1);
     p.stage_bytes = p.a_tiles * (p.pair ? 2 : 1) * TC_A_TILE + 2 * B_TILE;
     p.stages = std::max(1, std::min(TC_MAX_STAGES, (TC_SMEM_BUDGET + 20 * 1024 - qbytes) / p.stage_bytes));

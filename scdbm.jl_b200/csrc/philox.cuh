@@ -32,6 +32,26 @@ __device__ __forceinline__ float u23(uint32_t w) {
 __device__ __forceinline__ uint4 philox_group(const EpiParams& e, uint32_t row, uint32_t colgroup) {
     return philox4x32_10(make_uint4(colgroup, row + e.row_offset, e.tick, e.stream), e.k0, e.k1);
 }
+// the same words with the round keys precomputed on the host (EpiParams::rk lives in the kernel's constant bank, so each
+// key is a direct operand of the round's LOP3 instead of two uniform-datapath additions per round)
+__device__ __forceinline__ uint4 philox_group_rk(const EpiParams& e, uint32_t row, uint32_t colgroup) {
+    uint4 c = make_uint4(colgroup, row + e.row_offset, e.tick, e.stream);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ e.rk[2 * i], lo1, hi0 ^ c.w ^ e.rk[2 * i + 1], lo0);
+    }
+    return c;
+}
+__host__ inline void philox_round_keys(uint32_t k0, uint32_t k1, uint32_t (&rk)[20]) {
+    for (int i = 0; i < 10; ++i) {
+        rk[2 * i] = k0;
+        rk[2 * i + 1] = k1;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
 // element addressing (rejection samplers)
 __device__ __forceinline__ uint4 philox_element(uint32_t k0, uint32_t k1, uint32_t row, uint32_t col, uint32_t tick,
                                                 uint32_t stream) {
