@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscdbm_b200.so")
+# SCDBM_B200_LIB: another build of the same library (kernel-tuning experiments under profiles/)
+LIB_PATH = os.environ.get("SCDBM_B200_LIB") or os.path.join(_HERE, "libscdbm_b200.so")
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUP = 0, -1, -2, -3, -4
 VIS_BERNOULLI, VIS_NEGBIN = 0, 1

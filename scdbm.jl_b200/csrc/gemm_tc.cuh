@@ -7,10 +7,10 @@
 // operand planes are extra MMA passes into the same fp32 TMEM accumulator.
 //
 // Persistent CTAs (one per SM), warp-specialised:
-//   warp 0      TMA producer      (cp.async.bulk.tensor -> 128B-swizzled smem ring)
-//   warp 1      MMA issuer        (tcgen05.mma kind::f16, M=128, N=BN, K=16 per instruction)
-//   warp 2      TMEM allocator
-//   warps 4-19  epilogue          (tcgen05.ld 32x32b -> bias/activation/Philox draw -> fp16 planes)
+//   warps 0 .. EPW-1  epilogue          (tcgen05.ld 32x32b -> bias/activation/Philox draw -> fp16 planes)
+//   warp EPW          TMA producer      (cp.async.bulk.tensor -> 128B-swizzled smem ring)
+//   warp EPW+1        MMA issuer        (tcgen05.mma kind::f16, M=128, N=BN, K=16 per instruction)
+//   warp EPW+2        TMEM allocator
 // Two TMEM accumulator stages (2 x BN columns) let the MMAs of tile j+1 run
 // under the (sampler-bound) epilogue of tile j.
 #pragma once
@@ -51,7 +51,14 @@ constexpr int TC_MAX_STAGES = 8;
 // inside the warp's 32 x CW block packed into bits the draw does not use, a small queue of 16-byte survivor
 // states {u, P, q, k | position} for draws that outlive the unrolled first steps, and a 32 x CW fp16 staging
 // tile of the lo count plane
-constexpr int TC_QCAP = 256, TC_SCAP = 64, TC_NB_STEPS = 3;
+#ifndef SCDBM_NB_STEPS
+#define SCDBM_NB_STEPS 3
+#endif
+#ifndef SCDBM_NB_EPW      // epilogue warps of the wide NB sampling kernel; its tile is 8 * SCDBM_NB_EPW columns
+#define SCDBM_NB_EPW 28
+#endif
+constexpr int TC_QCAP = 256, TC_SCAP = 64, TC_NB_STEPS = SCDBM_NB_STEPS;
+constexpr int TC_NB_EPW = SCDBM_NB_EPW, TC_NB_BN = 8 * TC_NB_EPW;
 __host__ __device__ constexpr int tc_epi_smem(int cw) { return TC_QCAP * 8 + TC_SCAP * 16 + 32 * cw * 2; }
 constexpr int TC_SMEM_BUDGET = 200 * 1024;
 
@@ -113,40 +120,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (!done && ++spins > (1u << 26)) __trap();  // never hang the GPU: a protocol bug becomes a launch error
     } while (!done);
 }
-// service warps (TMA producer, MMA issuer) share an SM sub-partition with epilogue warps: back off
-// between polls so that their spin does not take issue slots from the sampler
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+// Waits that may last long (an epilogue warp ahead of the MMA issuer; the issuer waiting for a TMEM stage): the
+// try_wait carries a suspend-time hint, so the hardware parks the warp until the phase completes instead of the warp
+// re-polling -- with the default time limit the 28 epilogue warps of the NB kernel spent 13 % of the SM's issue
+// slots on ~57 polls per tile (ncu capture prof_r02a).
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     uint32_t spins = 0;
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(20000u)
             : "memory");
         if (done) break;
-        __nanosleep(128);
-        if (++spins > (1u << 25)) __trap();
+        if (++spins > (1u << 22)) __trap();   // never hang the GPU: a protocol bug becomes a launch error
     }
 }
-__device__ __forceinline__ void mbar_wait_epi(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    uint32_t spins = 0;
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) break;
-        __nanosleep(400);
-        if (++spins > (1u << 24)) __trap();
-    }
-}
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) { mbar_wait_parked(bar, parity); }
+__device__ __forceinline__ void mbar_wait_epi(uint32_t bar, uint32_t parity) { mbar_wait_parked(bar, parity); }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
@@ -252,9 +246,13 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
     __shared__ uint32_t tmem_holder;
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    // Warp roles: epilogue warps are 0 .. EPW-1; the service warps sit ABOVE them (svc = warp - EPW: 0 TMA producer,
+    // 1 MMA issuer, 2 TMEM allocator).  The warp scheduler prefers the highest warp index among the eligible warps of
+    // a sub-partition, so the few instructions that keep the tensor pipe fed never queue behind the sampling epilogue.
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int svc = warp - EPW;
 
-    if (warp == 1 && lane == 0) {
+    if (svc == 1 && lane == 0) {
         for (int i = 0; i < p.stages; ++i) {
             mbar_init(smem_u32(&bar_full[i]), 1);
             mbar_init(smem_u32(&bar_empty[i]), 1);
@@ -265,7 +263,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    } else if (warp == 2) {
+    } else if (svc == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
                      "r"(TMEM_COLS)
                      : "memory");
@@ -276,7 +274,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = tmem_holder;
 
-    if (warp == 0) {
+    if (svc == 0) {
         if (lane == 0) {
             // ===================== TMA producer
             int stage = 0;
@@ -293,7 +291,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     const uint32_t tx = (uint32_t)nA * a_bytes + 2 * B_TILE;
                     for (int pass = 0; pass < npass; ++pass)
                         for (int kb = 0; kb < p.kblocks[s]; ++kb) {
-                            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+                            mbar_wait_parked(smem_u32(&bar_empty[stage]), phase ^ 1u);
                             const uint32_t full = smem_u32(&bar_full[stage]);
                             const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
                             mbar_expect_tx(full, tx);
@@ -305,7 +303,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (svc == 1) {
         if (lane == 0) {
             // ===================== MMA issuer
             int stage = 0, astage = 0;
@@ -323,7 +321,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     const uint32_t combos = (p.split_hi[s] || !hi) ? (p.combos[s] & 0x3u) : p.combos[s];
                     const int nkb = p.kblocks[s] * ((p.split_hi[s] && hi) ? 2 : 1);    // second pass: the hi count plane in the same A slot
                     for (int kb = 0; kb < nkb; ++kb) {
-                        mbar_wait(smem_u32(&bar_full[stage]), phase);
+                        mbar_wait_parked(smem_u32(&bar_full[stage]), phase);
                         tc_fence_after();
                         const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
                         const uint32_t sb = sa + (uint32_t)p.a_tiles * a_bytes;
@@ -347,18 +345,18 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 if (++astage == ASTAGES) { astage = 0; aphase ^= 1u; }
             }
         }
-    } else if (warp >= 4) {
+    } else if (svc < 0) {
         // ===================== epilogue warps
-        // TMEM lanes tie a warp to its row quadrant; the column slice rotates per tile so that no warp keeps the
-        // expensive genes for the whole kernel
+        // TMEM lanes tie a warp to its row quadrant (warp index mod 4); the column slice rotates per tile so that no
+        // warp keeps the expensive genes for the whole kernel
         const int q = warp & 3;
-        int slice = (warp - 4) >> 2;
+        int slice = warp >> 2;
         int astage = 0;
         uint32_t aphase = 0;
         float delta_local = 0.0f;
         // two-pass NB epilogue state (EK == 1): per-warp queues in dynamic shared memory behind the GEMM stages
         uint8_t* wsm = smem_raw + (smem_base - smem_u32(smem_raw)) + (uint32_t)p.stages * (uint32_t)p.stage_bytes +
-                       (uint32_t)(warp - 4) * (uint32_t)tc_epi_smem(CW);
+                       (uint32_t)warp * (uint32_t)tc_epi_smem(CW);
         uint2* Q = reinterpret_cast<uint2*>(wsm);                                   // {accumulator | row bit 4, Philox word | column, row bits 0-3}
         uint4* S = reinterpret_cast<uint4*>(Q + TC_QCAP);                           // survivors {u, P, q, k << 16 | position}
         uint16_t* s_lo = reinterpret_cast<uint16_t*>(S + TC_SCAP);                  // [32][CW] fp16 staging tile, 16 B aligned
@@ -368,30 +366,31 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
         const float acc_scale = p.epi.acc_scale ? __ldg(p.epi.acc_scale) : 1.0f;   // 1/s of the fp16 weight planes
         int qn = 0, sn = 0;
         const uint32_t qbase = smem_u32(Q);
-        // a finished draw: lo plane into the staging tile; counts >= 2048 (rare) patch the hi plane in global memory
-        auto put = [&](float k, int rl, int cl) {
-            float lo = k;
-            if (k >= COUNT_BASE) {
-                const EpiParams& e = p.epi;
-                const float hi = floorf(k * (1.0f / COUNT_BASE)) * COUNT_BASE;
-                lo = k - hi;
-                const int64_t r2 = cur_m0 + q * 32 + rl, c2 = (int64_t)cur_c0 + cl;
-                if (r2 < p.M && c2 < p.N) {
-                    e.out.p1[r2 * e.out.ld + c2] = plane_encode(hi);
-                    if (e.out.hiflag) e.out.hiflag[r2 / TC_BM] = 3u;
-                }
+        // Entry position = index into the warp's [32][CW] staging tile (row * CW + column, 10 bits).
+        // A finished draw: lo plane into the staging tile; counts >= 2048 (rare) patch the hi plane in global memory
+        auto put_big = [&](float k, int idx) {
+            const EpiParams& e = p.epi;
+            const float hi = floorf(k * (1.0f / COUNT_BASE)) * COUNT_BASE;
+            const int64_t r2 = cur_m0 + q * 32 + idx / CW, c2 = (int64_t)cur_c0 + idx % CW;
+            if (r2 < p.M && c2 < p.N) {
+                e.out.p1[r2 * e.out.ld + c2] = plane_encode(hi);
+                if (e.out.hiflag) e.out.hiflag[r2 / TC_BM] = 3u;
             }
-            s_lo[rl * CW + cl] = __half_as_ushort(__float2half_rn(lo));
+            s_lo[idx] = __half_as_ushort(__float2half_rn(k - hi));
+        };
+        auto put = [&](float k, int idx) {
+            if (k >= COUNT_BASE) put_big(k, idx);
+            else s_lo[idx] = __half_as_ushort(__float2half_rn(k));
         };
         // second stage: `cnt` (<= 32) survivor states from S[base...], one per lane; the chop-down search runs to the end
         auto stage2 = [&](int base, int cnt) {
             const EpiParams& e = p.epi;
             if (lane < cnt) {
                 const uint4 st = S[base + lane];
-                const int cl = (int)((st.w >> 4) & 31u), rl = (int)((st.w & 15u) | ((st.w >> 5) & 16u));
+                const int idx = (int)(st.w & 0x3FFu);
                 float u = __uint_as_float(st.x), P = __uint_as_float(st.y);
                 const float qq = __uint_as_float(st.z);
-                const float qr1 = qq * __ldg(&e.nbc[cur_c0 + cl].w);
+                const float qr1 = qq * __ldg(&e.nbc[cur_c0 + (uint32_t)(idx % CW)].w);
                 float k = (float)(st.w >> 16);
                 float rk = fast_rcp(k + 1.0f);
                 while (u >= P && P > PMIN_F) {
@@ -401,13 +400,14 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     rk = fast_rcp(k + 1.0f);
                     P *= ratio;
                 }
-                put(k, rl, cl);
+                put(k, idx);
             }
         };
-        // first stage over queue entries [0, n): NB mean, P0, then TC_NB_STEPS predicated steps of the search (no
+        // first stage over queue entries [0, n): NB mean, P0, then TC_NB_STEPS speculative steps of the search (no
         // divergence: most draws end here); the rest are compacted into S and finished 32 at a time by stage2
         auto stage1 = [&](int n) {
             const EpiParams& e = p.epi;
+            const float mu_lim = e.mu_inv_max - 1e-6f;
             __syncwarp();
             for (int i0 = 0; i0 < n; i0 += 32) {
                 const int i = i0 + lane;
@@ -415,8 +415,8 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 uint4 st = make_uint4(0u, 0u, 0u, 0u);
                 if (i < n) {
                     const uint2 en = Q[i];
-                    const int cl = (int)((en.y >> 4) & 31u), rl = (int)((en.y & 15u) | ((en.x & 1u) << 4));
-                    const uint32_t col = cur_c0 + (uint32_t)cl;
+                    const int idx = (int)((en.y & 0x1FFu) | ((en.x & 1u) << 9));
+                    const uint32_t col = cur_c0 + (uint32_t)(idx % CW);
                     const float4 c = __ldg(e.nbc + col);                             // {a, r, 1e-6/r, r-1}; padded like nbT
                     float u = u23(en.y);
                     const float x = fmaf(e.wscale, __uint_as_float(en.x) * acc_scale, c.x);
@@ -425,32 +425,29 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     // x -> 0-: 1 - e^x cancels; -expm1(x) = -x (1 + x/2 + ... + x^5/720), |err| < 2e-9 on (-1/8, 0)
                     if (x > -0.125f)
                         om = -x * fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, 1.0f / 720.0f, 1.0f / 120.0f), 1.0f / 24.0f), 1.0f / 6.0f), 0.5f), 1.0f);
-                    if (c.y * E > (e.mu_inv_max - 1e-6f) * om) {                      // mean above mu_inv_max: gamma-Poisson, out of line
-                        const RngAddr g{e.k0, e.k1, (uint32_t)(cur_m0 + q * 32 + rl) + e.row_offset, col, e.tick, e.stream & 0xFFu};
-                        put(nb_draw_slow(x, c.y, u, e.pshift, e.mu_inv_max, g), rl, cl);
+                    if (c.y * E > mu_lim * om) {                                      // mean above mu_inv_max: gamma-Poisson, out of line
+                        const RngAddr g{e.k0, e.k1, (uint32_t)(cur_m0 + q * 32 + idx / CW) + e.row_offset, col, e.tick, e.stream & 0xFFu};
+                        put(nb_draw_slow(x, c.y, u, e.pshift, e.mu_inv_max, g), idx);
                     } else {
                         const float pp = om * fast_rcp(fmaf(c.z, om, 1.0f)) - e.pshift;
                         const float qq = 1.0f - pp, qr1 = qq * c.w;
                         // the first TC_NB_STEPS steps of the chop-down search, computed speculatively (no predicated
-                        // updates): go[s] = "the search is still running after s steps"; the count is the number of
-                        // steps taken, the survivor state is the last (u, P)
+                        // updates): `go` = "the search is still running"; the count is the number of steps taken
+                        // (written as its fp16 word: 0, 1, 2, 3), the survivor state is the last (u, P)
                         float P = fast_ex2(c.y * fast_lg2(pp));
                         bool go = (P > PMIN_F) && (u >= P);
-                        int k = 0;
+                        uint32_t k16 = 0u;
 #pragma unroll
                         for (int sidx = 0; sidx < TC_NB_STEPS; ++sidx) {
-                            k += go ? 1 : 0;
+                            constexpr uint32_t F16[4] = {0x3C00u, 0x4000u, 0x4200u, 0x4400u};   // 1, 2, 3, 4
+                            k16 = go ? F16[sidx] : k16;
                             u -= P;
                             P *= fmaf(qr1, 1.0f / (float)(sidx + 1), qq);
                             go = go && (P > PMIN_F) && (u >= P);
                         }
-                        if (go) {
-                            surv = true;
-                            st = make_uint4(__float_as_uint(u), __float_as_uint(P), __float_as_uint(qq),
-                                            ((uint32_t)TC_NB_STEPS << 16) | ((uint32_t)(rl & 16) << 5) | ((uint32_t)cl << 4) | (uint32_t)(rl & 15));
-                        } else {
-                            put((float)k, rl, cl);
-                        }
+                        s_lo[idx] = (uint16_t)k16;                                   // a survivor's slot is rewritten by stage2
+                        surv = go;
+                        st = make_uint4(__float_as_uint(u), __float_as_uint(P), __float_as_uint(qq), ((uint32_t)TC_NB_STEPS << 16) | (uint32_t)idx);
                     }
                 }
                 const uint32_t smask = __ballot_sync(0xffffffffu, surv);
@@ -485,7 +482,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
         for (int it = 0, tile; (tile = tc_tile(p, it)) >= 0; ++it) {
             const int halves = (EK != 1 && p.pair) ? 2 : 1;
             const int64_t m0 = (int64_t)(tile / p.n_tiles) * (TC_BM * halves), n0 = (int64_t)(tile % p.n_tiles) * BN;
-            slice = (((warp - 4) >> 2) + it) % NS;
+            slice = ((warp >> 2) + it) % NS;
             if constexpr (EK == 1) {
                 // lo count plane: staged in the warp's shared-memory tile (zeroed here, patched by pass B, written
                 // out coalesced at the end of the tile).  hi plane (counts >= 2048, rare): coalesced zero-fill now where
@@ -518,7 +515,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 // densely, one per lane, in pass B.  The entry's position rides in bits the draw ignores: the 9 low
                 // bits of the word (the uniform uses the top 23) and the last mantissa bit of the accumulator.
                 const EpiParams& e = p.epi;
-                const uint32_t lane_lo = (uint32_t)lane & 15u, lane_hi = (uint32_t)lane >> 4;
+                // position of (lane, column c) in the staging tile: lane * CW + c; bit 9 travels in the accumulator's last bit
 #pragma unroll 1
                 for (int g = 0; g < CW / 4; ++g) {
                     uint32_t r[4];
@@ -528,10 +525,10 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     const uint4 T = __ldg(reinterpret_cast<const uint4*>(e.nbT + col0));
                     tmem_wait_ld();
                     const uint32_t wj[4] = {w.x, w.y, w.z, w.w}, Tj[4] = {T.x, T.y, T.z, T.w};
-                    const uint32_t pos0 = ((uint32_t)g << 6) | lane_lo;
+                    const uint32_t pos0 = (uint32_t)(lane * CW + g * 4);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        nb_enqueue(wj[j], Tj[j], (r[j] & ~1u) | lane_hi, (wj[j] & ~0x1FFu) | (pos0 + (uint32_t)(j << 4)), lt, qbase, qn);
+                        nb_enqueue(wj[j], Tj[j], (r[j] & ~1u) | (pos0 >> 9), (wj[j] & ~0x1FFu) | ((pos0 + (uint32_t)j) & 0x1FFu), lt, qbase, qn);
                     if (qn > TC_QCAP - 128) drain_full();
                 }
                 tc_fence_before();
@@ -588,7 +585,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (svc == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
@@ -615,7 +612,7 @@ inline bool tc_supported(const GemmArgs& g, int nsrc) {
 
 template <int BN, int EK, int EPW>
 inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, int num_sms, cudaStream_t stream) {
-    const int slot = (BN == 64 ? 0 : BN == 128 ? 3 : 6) + EK;   // BN 192/224: slot 7
+    const int slot = (BN == 64 ? 0 : BN == 128 ? 3 : 6) + EK;   // wide NB kernel: slot 7
     constexpr int B_TILE = BN * TC_BK * 2;
     const int qbytes = (EK == 1) ? EPW * tc_epi_smem(BN / (EPW / 4)) : 0;
     p.a_tiles = std::max(p.split_hi[0] ? 1 : p.nA[0], p.nsrc > 1 ? (p.split_hi[1] ? 1 : p.nA[1]) : 1);
@@ -649,7 +646,7 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
                                   cudaStream_t stream) {
     if (!t.encode) return cudaErrorNotSupported;
     const int ek = tc_epilogue_class(g, ops, nsrc);
-    const int BN = g.N <= 64 ? 64 : (ek == 1 && g.N >= 224) ? 224 : 128;
+    const int BN = g.N <= 64 ? 64 : (ek == 1 && g.N >= TC_NB_BN) ? TC_NB_BN : 128;
     TcMaps maps;
     TcParams p;
     memset(&p, 0, sizeof(p));
@@ -683,7 +680,7 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
         if (ek == 2) return tc_launch_bn<64, 2, 16>(t, maps, p, num_sms, stream);
         return tc_launch_bn<64, 0, 16>(t, maps, p, num_sms, stream);
     }
-    if (BN == 224) return tc_launch_bn<224, 1, 28>(t, maps, p, num_sms, stream);
+    if (BN == TC_NB_BN && ek == 1) return tc_launch_bn<TC_NB_BN, 1, TC_NB_EPW>(t, maps, p, num_sms, stream);
     if (ek == 1) return tc_launch_bn<128, 1, 16>(t, maps, p, num_sms, stream);
     if (ek == 2) return tc_launch_bn<128, 2, 16>(t, maps, p, num_sms, stream);
     return tc_launch_bn<128, 0, 16>(t, maps, p, num_sms, stream);
@@ -733,15 +730,16 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
     __shared__ uint32_t tmem_holder;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int svc = warp - 16;    // epilogue warps 0-15, service warps above them (see k_gemm_tc)
     const int nwork = p.m_tiles * p.n_tiles * p.splits;
 
-    if (warp == 1 && lane == 0) {
+    if (svc == 1 && lane == 0) {
         for (int i = 0; i < p.stages; ++i) { mbar_init(smem_u32(&bar_full[i]), 1); mbar_init(smem_u32(&bar_empty[i]), 1); }
         mbar_init(smem_u32(&bar_tfull), 1);
         mbar_init(smem_u32(&bar_tempty), 16);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    } else if (warp == 2) {
+    } else if (svc == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(256u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -756,7 +754,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
         hi = (int)((int64_t)p.kblocks[s] * (sp + 1) / p.splits);
     };
 
-    if (warp == 0) {
+    if (svc == 0) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
@@ -783,7 +781,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (svc == 1) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0, aphase = 0;
@@ -819,8 +817,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
                 aphase ^= 1u;
             }
         }
-    } else if (warp >= 4) {
-        const int q = warp & 3, slice = (warp - 4) >> 2;
+    } else if (svc < 0) {
+        const int q = warp & 3, slice = warp >> 2;
         uint32_t aphase = 0;
         for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
             const int tile = w / p.splits, sp = w % p.splits;
@@ -860,7 +858,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (svc == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
     }
