@@ -57,9 +57,11 @@ constexpr int TC_MAX_STAGES = 8;
 #ifndef SCDBM_NB_EPW      // epilogue warps of the wide NB sampling kernel; its tile is 8 * SCDBM_NB_EPW columns
 #define SCDBM_NB_EPW 28
 #endif
-constexpr int TC_QCAP = 256, TC_SCAP = 64, TC_NB_STEPS = SCDBM_NB_STEPS;
+constexpr int TC_QCAP = 192, TC_SCAP = 64, TC_NB_STEPS = SCDBM_NB_STEPS;
 constexpr int TC_NB_EPW = SCDBM_NB_EPW, TC_NB_BN = 8 * TC_NB_EPW;
-__host__ __device__ constexpr int tc_epi_smem(int cw) { return TC_QCAP * 8 + TC_SCAP * 16 + 32 * cw * 2; }
+// ... and the slice's per-gene constants (nbc: 16 B, threshold: 4 B per column): with the shared-memory carve-out at its
+// maximum the L1 is too small to keep the per-gene tables, and every gather from them was an L2 round trip
+__host__ __device__ constexpr int tc_epi_smem(int cw) { return TC_QCAP * 8 + TC_SCAP * 16 + 32 * cw * 2 + cw * 20; }
 constexpr int TC_SMEM_BUDGET = 200 * 1024;
 
 struct alignas(64) TcMaps {
@@ -360,13 +362,20 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
         uint2* Q = reinterpret_cast<uint2*>(wsm);                                   // {accumulator | row bit 4, Philox word | column, row bits 0-3}
         uint4* S = reinterpret_cast<uint4*>(Q + TC_QCAP);                           // survivors {u, P, q, k << 16 | position}
         uint16_t* s_lo = reinterpret_cast<uint16_t*>(S + TC_SCAP);                  // [32][CW] fp16 staging tile, 16 B aligned
+        float4* sN = reinterpret_cast<float4*>(s_lo + 32 * CW);                     // the slice's {a, r, 1e-6/r, r-1}
+        uint32_t* sT = reinterpret_cast<uint32_t*>(sN + CW);                        // the slice's pass-A thresholds
+        int64_t flag_m0 = -1;
+        bool dirty = true;
         int64_t cur_m0 = 0;
         uint32_t cur_c0 = 0;                                                        // global column of the warp's slice
         const uint32_t lt = (1u << lane) - 1u;
         const float acc_scale = p.epi.acc_scale ? __ldg(p.epi.acc_scale) : 1.0f;   // 1/s of the fp16 weight planes
         int qn = 0, sn = 0;
         const uint32_t qbase = smem_u32(Q);
-        // Entry position = index into the warp's [32][CW] staging tile (row * CW + column, 10 bits).
+        // Entry position = index into the warp's [32][CW] staging tile (row * CW + column, 10 bits).  The tile is stored
+        // swizzled -- 4-byte word w of row r sits at word w ^ ((r >> 1) & (CW/2 - 1)) -- because the entries of one pass-B
+        // batch mostly share a column: their 2-byte result stores would otherwise hit two banks (16-way conflict).
+        auto swz = [&](int idx) { return idx ^ ((((idx / CW) >> 1) & (CW / 2 - 1)) << 1); };
         // A finished draw: lo plane into the staging tile; counts >= 2048 (rare) patch the hi plane in global memory
         auto put_big = [&](float k, int idx) {
             const EpiParams& e = p.epi;
@@ -376,21 +385,20 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 e.out.p1[r2 * e.out.ld + c2] = plane_encode(hi);
                 if (e.out.hiflag) e.out.hiflag[r2 / TC_BM] = 3u;
             }
-            s_lo[idx] = __half_as_ushort(__float2half_rn(k - hi));
+            s_lo[swz(idx)] = __half_as_ushort(__float2half_rn(k - hi));
         };
         auto put = [&](float k, int idx) {
             if (k >= COUNT_BASE) put_big(k, idx);
-            else s_lo[idx] = __half_as_ushort(__float2half_rn(k));
+            else s_lo[swz(idx)] = __half_as_ushort(__float2half_rn(k));
         };
         // second stage: `cnt` (<= 32) survivor states from S[base...], one per lane; the chop-down search runs to the end
         auto stage2 = [&](int base, int cnt) {
-            const EpiParams& e = p.epi;
             if (lane < cnt) {
                 const uint4 st = S[base + lane];
                 const int idx = (int)(st.w & 0x3FFu);
                 float u = __uint_as_float(st.x), P = __uint_as_float(st.y);
                 const float qq = __uint_as_float(st.z);
-                const float qr1 = qq * __ldg(&e.nbc[cur_c0 + (uint32_t)(idx % CW)].w);
+                const float qr1 = qq * sN[idx % CW].w;
                 float k = (float)(st.w >> 16);
                 float rk = fast_rcp(k + 1.0f);
                 while (u >= P && P > PMIN_F) {
@@ -417,7 +425,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     const uint2 en = Q[i];
                     const int idx = (int)((en.y & 0x1FFu) | ((en.x & 1u) << 9));
                     const uint32_t col = cur_c0 + (uint32_t)(idx % CW);
-                    const float4 c = __ldg(e.nbc + col);                             // {a, r, 1e-6/r, r-1}; padded like nbT
+                    const float4 c = sN[idx % CW];                                   // {a, r, 1e-6/r, r-1}
                     float u = u23(en.y);
                     const float x = fmaf(e.wscale, __uint_as_float(en.x) * acc_scale, c.x);
                     const float E = fast_ex2(x * 1.4426950408889634f);
@@ -445,7 +453,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                             P *= fmaf(qr1, 1.0f / (float)(sidx + 1), qq);
                             go = go && (P > PMIN_F) && (u >= P);
                         }
-                        s_lo[idx] = (uint16_t)k16;                                   // a survivor's slot is rewritten by stage2
+                        s_lo[swz(idx)] = (uint16_t)k16;                              // a survivor's slot is rewritten by stage2
                         surv = go;
                         st = make_uint4(__float_as_uint(u), __float_as_uint(P), __float_as_uint(qq), ((uint32_t)TC_NB_STEPS << 16) | (uint32_t)idx);
                     }
@@ -489,9 +497,17 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 // the row tile is marked (full 32 B sectors: 4 lanes x 16 B per row, 8 rows per store), scattered patches from pass B.
                 cur_m0 = m0; cur_c0 = (uint32_t)n0 + (uint32_t)(slice * CW);
                 const MatView& o = p.epi.out;
-                // the hi plane of a row tile is all zero unless its flag says otherwise (bit 1: stale entries of an
-                // earlier sweep, or of an earlier column tile of this launch -- re-zeroing those is harmless)
-                const bool dirty = !o.hiflag || (*reinterpret_cast<const volatile uint32_t*>(o.hiflag + m0 / TC_BM) & 2u) != 0u;
+                // per-gene constants of this slice (both tables are padded past the last tile): loads issued now, parked in
+                // shared memory after the zero-fill
+                float4 cn = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                uint32_t ct = 0u;
+                if (lane < CW) { cn = __ldg(p.epi.nbc + cur_c0 + lane); ct = __ldg(p.epi.nbT + cur_c0 + lane); }
+                // the hi plane of a row tile is all zero unless its flag says otherwise (bit 1: stale entries of an earlier
+                // sweep); read once per row tile -- a flag raised by this launch marks entries written into a clean plane
+                if (m0 != flag_m0) {
+                    flag_m0 = m0;
+                    dirty = !o.hiflag || (*reinterpret_cast<const volatile uint32_t*>(o.hiflag + m0 / TC_BM) & 2u) != 0u;
+                }
 #pragma unroll
                 for (int i = 0; i < (32 * CW * 2) / (32 * 16); ++i) {
                     const int idx = i * 32 + lane;                   // 16-byte chunk index within the region
@@ -500,6 +516,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     reinterpret_cast<uint4*>(s_lo)[idx] = make_uint4(0u, 0u, 0u, 0u);
                     if (dirty && r2 < p.M && c2 < o.ld) *reinterpret_cast<uint4*>(o.p1 + r2 * o.ld + c2) = make_uint4(0u, 0u, 0u, 0u);
                 }
+                if (lane < CW) { sN[lane] = cn; sT[lane] = ct; }
                 __syncwarp();
             }
             mbar_wait_epi(smem_u32(&bar_tfull[astage]), aphase);   // sleeps between polls: leaves the issue slots to the stragglers
@@ -522,7 +539,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     tmem_ld4(taddr + g * 4, r);
                     const uint32_t col0 = cur_c0 + (uint32_t)(g * 4);
                     const uint4 w = philox_group_rk(e, (uint32_t)row, col0 >> 2);
-                    const uint4 T = __ldg(reinterpret_cast<const uint4*>(e.nbT + col0));
+                    const uint4 T = *reinterpret_cast<const uint4*>(sT + g * 4);
                     tmem_wait_ld();
                     const uint32_t wj[4] = {w.x, w.y, w.z, w.w}, Tj[4] = {T.x, T.y, T.z, T.w};
                     const uint32_t pos0 = (uint32_t)(lane * CW + g * 4);
@@ -536,14 +553,18 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[astage]));
                 if (++astage == ASTAGES) { astage = 0; aphase ^= 1u; }
                 drain_all();
-                {   // coalesced write-out of the staged lo plane
+                {   // coalesced write-out of the staged lo plane (undoing the word swizzle of each row)
                     const MatView& o = p.epi.out;
 #pragma unroll
                     for (int i = 0; i < (32 * CW * 2) / (32 * 16); ++i) {
                         const int idx = i * 32 + lane;
                         const int rr = idx / (CW / 8), ch = idx % (CW / 8);
+                        const int sw = (rr >> 1) & (CW / 2 - 1);                       // word XOR of this row
+                        uint4 v = reinterpret_cast<const uint4*>(s_lo)[rr * (CW / 8) + (ch ^ (sw >> 2))];
+                        if (sw & 1) v = make_uint4(v.y, v.x, v.w, v.z);
+                        if (sw & 2) v = make_uint4(v.z, v.w, v.x, v.y);
                         const int64_t r2 = m0 + q * 32 + rr, c2 = n0 + slice * CW + ch * 8;
-                        if (r2 < p.M && c2 < o.ld) *reinterpret_cast<uint4*>(o.p0 + r2 * o.ld + c2) = reinterpret_cast<const uint4*>(s_lo)[idx];
+                        if (r2 < p.M && c2 < o.ld) *reinterpret_cast<uint4*>(o.p0 + r2 * o.ld + c2) = v;
                     }
                     __syncwarp();
                 }
