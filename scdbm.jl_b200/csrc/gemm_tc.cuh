@@ -226,6 +226,27 @@ __device__ __forceinline__ bool tc_use_hi(const TcParams& p, int s, int m_blk) {
     return (p.a_hiflag[s][2 * m_blk] & 1u) != 0u || (2 * m_blk + 1 <= last && (p.a_hiflag[s][2 * m_blk + 1] & 1u) != 0u);
 }
 
+// Long contractions are accumulated in chunks.  tcgen05.mma adds into its fp32 TMEM accumulator with truncation, so a
+// same-sign sum over thousands of k-steps drifts by ~0.5 ulp per step (measured: 4e-5 relative at K = 20 000, which a
+// sigmoid in its tail turns into 3e-4 -- outside gate G1).  A tile with more than TC_PROMO_KB k-blocks (K > 4 608) is therefore
+// contracted in chunks of <= TC_CHUNK_KB k-blocks, each into a fresh accumulator stage; the epilogue warps add the
+// chunks in registers (round-to-nearest fp32) and put the total back into TMEM before the usual epilogue runs.
+constexpr int TC_PROMO_KB = 72, TC_CHUNK_KB = 32;
+__device__ __forceinline__ int tc_tile_kblocks(const TcParams& p, int m_blk) {
+    int t = 0;
+    for (int s = 0; s < p.nsrc; ++s) t += p.kblocks[s] * ((p.split_hi[s] && tc_use_hi(p, s, m_blk)) ? 2 : 1);
+    return t;
+}
+__host__ __device__ __forceinline__ int tc_chunks(int tkb) { return tkb > TC_PROMO_KB ? (tkb + TC_CHUNK_KB - 1) / TC_CHUNK_KB : 1; }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ------------------------------------------------------------------ kernel
 // EK: epilogue class -- 0 generic (all modes, accurate math, explicit uniforms), 1 Philox-fed NB draw
 // (fast math), 2 Philox-fed Bernoulli draw (fast math).  Separate instantiations keep each kernel's
@@ -241,7 +262,6 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
     constexpr uint32_t TMEM_COLS = (EK == 1) ? ((ASTAGES * BN <= 256) ? 256 : 512) : ((2 * ASTAGES * BN <= 256) ? 256 : 512);
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // c = F32, a = b = F16, K-major
     static_assert(CW == 16 || CW == 32, "epilogue slice must be 16 or 32 columns");
-    (void)tmem_ld16;
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_tfull[2], bar_tempty[2];
@@ -312,17 +332,24 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
             uint32_t phase = 0, aphase = 0;
             for (int it = 0, tile; (tile = tc_tile(p, it)) >= 0; ++it) {
                 const int m_blk = tile / p.n_tiles;
-                mbar_wait_backoff(smem_u32(&bar_tempty[astage]), aphase ^ 1u);
-                tc_fence_after();
                 const int halves = p.pair ? 2 : 1;
                 const uint32_t a_bytes = (uint32_t)halves * TC_A_TILE;
-                const uint32_t tmem_d = tmem_base + (uint32_t)(astage * halves) * BN;
-                uint32_t accumulate = 0;
+                // chunked accumulation (see tc_chunks): every chunk gets a fresh accumulator stage
+                const int tkb = tc_tile_kblocks(p, m_blk);
+                const int nch = tc_chunks(tkb), per = (tkb + nch - 1) / nch;
+                int done = 0, in_chunk = 0;
+                uint32_t tmem_d = 0, accumulate = 0;
                 for (int s = 0; s < p.nsrc; ++s) {
                     const bool hi = tc_use_hi(p, s, m_blk);
                     const uint32_t combos = (p.split_hi[s] || !hi) ? (p.combos[s] & 0x3u) : p.combos[s];
                     const int nkb = p.kblocks[s] * ((p.split_hi[s] && hi) ? 2 : 1);    // second pass: the hi count plane in the same A slot
                     for (int kb = 0; kb < nkb; ++kb) {
+                        if (in_chunk == 0) {
+                            mbar_wait_backoff(smem_u32(&bar_tempty[astage]), aphase ^ 1u);
+                            tc_fence_after();
+                            tmem_d = tmem_base + (uint32_t)(astage * halves) * BN;
+                            accumulate = 0;
+                        }
                         mbar_wait_parked(smem_u32(&bar_full[stage]), phase);
                         tc_fence_after();
                         const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
@@ -341,10 +368,14 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                         accumulate = 1;
                         tc_commit(smem_u32(&bar_empty[stage]));   // smem slot is free once these MMAs retire
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                        ++done;
+                        if (++in_chunk == per || done == tkb) {
+                            tc_commit(smem_u32(&bar_tfull[astage]));      // chunk (or whole accumulator) ready for the epilogue warps
+                            if (++astage == ASTAGES) { astage = 0; aphase ^= 1u; }
+                            in_chunk = 0;
+                        }
                     }
                 }
-                tc_commit(smem_u32(&bar_tfull[astage]));          // accumulator ready for the epilogue
-                if (++astage == ASTAGES) { astage = 0; aphase ^= 1u; }
             }
         }
     } else if (svc < 0) {
@@ -519,8 +550,50 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 if (lane < CW) { sN[lane] = cn; sT[lane] = ct; }
                 __syncwarp();
             }
-            mbar_wait_epi(smem_u32(&bar_tfull[astage]), aphase);   // sleeps between polls: leaves the issue slots to the stragglers
-            tc_fence_after();
+            if constexpr (EK != 1) {
+                // chunked accumulation: add all but the last chunk in registers, then fold the last one in and put
+                // the total back into the last chunk's TMEM stage (promotion never runs in pair mode)
+                const int nch = tc_chunks(tc_tile_kblocks(p, tile / p.n_tiles));
+                if (nch > 1) {
+                    float sum[CW];
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) sum[i] = 0.0f;
+                    for (int c = 0; c < nch; ++c) {
+                        mbar_wait_epi(smem_u32(&bar_tfull[astage]), aphase);
+                        tc_fence_after();
+                        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(astage * BN + slice * CW);
+#pragma unroll
+                        for (int g = 0; g < CW / 16; ++g) {
+                            uint32_t r[16];
+                            tmem_ld16(ta + g * 16, r);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) sum[g * 16 + i] += __uint_as_float(r[i]);
+                        }
+                        if (c + 1 < nch) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[astage]));
+                            if (++astage == ASTAGES) { astage = 0; aphase ^= 1u; }
+                        } else {
+#pragma unroll
+                            for (int g = 0; g < CW / 16; ++g) {
+                                uint32_t r[16];
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(sum[g * 16 + i]);
+                                tmem_st16(ta + g * 16, r);
+                            }
+                            tmem_wait_st();
+                        }
+                    }
+                } else {
+                    mbar_wait_epi(smem_u32(&bar_tfull[astage]), aphase);
+                    tc_fence_after();
+                }
+            } else {
+                mbar_wait_epi(smem_u32(&bar_tfull[astage]), aphase);
+                tc_fence_after();
+            }
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(astage * halves * BN + slice * CW);
             const int64_t row = m0 + q * 32 + lane;
             float rowsum = 0.0f;
@@ -676,7 +749,9 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
     p.N = g.N;
     // pair mode: 256-row work tiles (two MMA row tiles per weight-tile load) when there is enough work to keep
     // every SM busy with pairs; the NB sampling kernel keeps single tiles (its two 224-column stages fill TMEM)
-    p.pair = (ek != 1 && g.M >= (int64_t)2 * TC_BM * num_sms) ? 1 : 0;
+    int max_kb = 0;
+    for (int s = 0; s < nsrc; ++s) max_kb += (int)((ops[s].K + TC_BK - 1) / TC_BK) * ((ops[s].a.p1 && ops[s].a.kind == MAT_COUNT) ? 2 : 1);
+    p.pair = (ek != 1 && g.M >= (int64_t)2 * TC_BM * num_sms && tc_chunks(max_kb) == 1) ? 1 : 0;
     const int rows_per_tile = p.pair ? 2 * TC_BM : TC_BM;
     p.m_tiles = (int)((g.M + rows_per_tile - 1) / rows_per_tile);
     p.n_tiles = (int)((g.N + BN - 1) / BN);
@@ -746,8 +821,9 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
 __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant__ TcGradMaps maps, const __grid_constant__ TcGradParams p) {
     constexpr uint32_t IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(TG_BN >> 3) << 17) |
                                ((uint32_t)(TC_BM >> 4) << 24);   // c = F32, a = b = F16, both MN-major
+    constexpr uint32_t TG_TMEM = 512;   // 2 chunk stages x {positive, negative} accumulator x 128 columns
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_tfull, bar_tempty;
+    __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_holder;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -756,12 +832,11 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
 
     if (svc == 1 && lane == 0) {
         for (int i = 0; i < p.stages; ++i) { mbar_init(smem_u32(&bar_full[i]), 1); mbar_init(smem_u32(&bar_empty[i]), 1); }
-        mbar_init(smem_u32(&bar_tfull), 1);
-        mbar_init(smem_u32(&bar_tempty), 16);
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bar_tfull[i]), 1); mbar_init(smem_u32(&bar_tempty[i]), 16); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     } else if (svc == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(256u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(TG_TMEM) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -773,6 +848,18 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
     auto kb_range = [&](int s, int sp, int& lo, int& hi) {
         lo = (int)((int64_t)p.kblocks[s] * sp / p.splits);
         hi = (int)((int64_t)p.kblocks[s] * (sp + 1) / p.splits);
+    };
+    // The contraction runs over the samples (K = 100 000 at BASELINE config C4): accumulated in chunks of <= TC_CHUNK_KB
+    // k-blocks, each into a fresh pair of TMEM accumulators, combined and summed in registers by the epilogue warps
+    // (round-to-nearest fp32; tcgen05.mma's own accumulation truncates -- see tc_chunks).
+    auto chunking = [&](int sp, int& n0, int& tkb, int& nch, int& per) {
+        int lo0, hi0, lo1, hi1;
+        kb_range(0, sp, lo0, hi0);
+        kb_range(1, sp, lo1, hi1);
+        n0 = hi0 - lo0;
+        tkb = n0 + (hi1 - lo1);
+        nch = tkb > 0 ? (tkb + TC_CHUNK_KB - 1) / TC_CHUNK_KB : 1;
+        per = (tkb + nch - 1) / nch;
     };
 
     if (svc == 0) {
@@ -787,7 +874,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
                     kb_range(s, sp, lo, hi);
                     for (int kb = lo; kb < hi; ++kb) {
                         const int nA = (p.a_hiflag[s] && p.nA[s] == 2 && (p.a_hiflag[s][kb / 2] & 1u) == 0u) ? 1 : p.nA[s];
-                        mbar_wait_backoff(smem_u32(&bar_empty[stage]), phase ^ 1u);
+                        mbar_wait_parked(smem_u32(&bar_empty[stage]), phase ^ 1u);
                         const uint32_t full = smem_u32(&bar_full[stage]);
                         const uint32_t sa = smem_base + (uint32_t)stage * TG_STAGE, sb = sa + 2 * TG_PLANE;
                         mbar_expect_tx(full, (uint32_t)((nA + p.nB[s]) * TG_PLANE));
@@ -804,22 +891,35 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
         }
     } else if (svc == 1) {
         if (lane == 0) {
-            int stage = 0;
+            int stage = 0, astage = 0;
             uint32_t phase = 0, aphase = 0;
             for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
                 const int sp = w % p.splits;
-                mbar_wait_backoff(smem_u32(&bar_tempty), aphase ^ 1u);
-                tc_fence_after();
+                int n0, tkb, nch, per;
+                chunking(sp, n0, tkb, nch, per);
+                if (tkb == 0) {   // nothing to contract in this split: hand the epilogue an (ignored) stage so the protocol stays in step
+                    mbar_wait_parked(smem_u32(&bar_tempty[astage]), aphase ^ 1u);
+                    tc_commit(smem_u32(&bar_tfull[astage]));
+                    if (++astage == 2) { astage = 0; aphase ^= 1u; }
+                    continue;
+                }
+                int done = 0, in_chunk = 0;
+                uint32_t acc_used = 0;      // bit s: accumulator s has been written in this chunk
                 for (int s = 0; s < 2; ++s) {
-                    const uint32_t tmem_d = tmem_base + (uint32_t)s * TG_BN;
-                    uint32_t accumulate = 0;
                     int lo, hi;
                     kb_range(s, sp, lo, hi);
                     for (int kb = lo; kb < hi; ++kb) {
+                        if (in_chunk == 0) {
+                            mbar_wait_parked(smem_u32(&bar_tempty[astage]), aphase ^ 1u);
+                            tc_fence_after();
+                            acc_used = 0;
+                        }
+                        const uint32_t tmem_d = tmem_base + (uint32_t)(astage * 2 + s) * TG_BN;
                         const uint32_t combos = (p.a_hiflag[s] && p.nA[s] == 2 && (p.a_hiflag[s][kb / 2] & 1u) == 0u) ? (p.combos[s] & 0x3u) : p.combos[s];
-                        mbar_wait_backoff(smem_u32(&bar_full[stage]), phase);
+                        mbar_wait_parked(smem_u32(&bar_full[stage]), phase);
                         tc_fence_after();
                         const uint32_t sa = smem_base + (uint32_t)stage * TG_STAGE, sb = sa + 2 * TG_PLANE;
+                        uint32_t accumulate = (acc_used >> s) & 1u;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             if (!((combos >> c) & 1u)) continue;
@@ -830,58 +930,77 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
                                 accumulate = 1;
                             }
                         }
+                        acc_used |= 1u << s;
                         tc_commit(smem_u32(&bar_empty[stage]));
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-                    }
-                }
-                tc_commit(smem_u32(&bar_tfull));
-                aphase ^= 1u;
-            }
-        }
-    } else if (svc < 0) {
-        const int q = warp & 3, slice = warp >> 2;
-        uint32_t aphase = 0;
-        for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
-            const int tile = w / p.splits, sp = w % p.splits;
-            const int64_t m0 = (int64_t)(tile / p.n_tiles) * TC_BM, n0 = (int64_t)(tile % p.n_tiles) * TG_BN;
-            int lo0, hi0, lo1, hi1;
-            kb_range(0, sp, lo0, hi0);
-            kb_range(1, sp, lo1, hi1);
-            mbar_wait_epi(smem_u32(&bar_tfull), aphase);
-            aphase ^= 1u;
-            tc_fence_after();
-            const int64_t row = m0 + q * 32 + lane;
-            float* dst = (p.splits > 1 ? p.partial + (int64_t)sp * p.V * p.H : p.out);
-#pragma unroll 1
-            for (int g = 0; g < 8; ++g) {
-                uint32_t r0[4], r1[4];
-                const uint32_t col = (uint32_t)(slice * 32 + g * 4);
-                tmem_ld4(tmem_base + ((uint32_t)(q * 32) << 16) + col, r0);
-                tmem_ld4(tmem_base + ((uint32_t)(q * 32) << 16) + TG_BN + col, r1);
-                tmem_wait_ld();
-                const int64_t c0 = n0 + col;
-                if (row < p.V) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (c0 + j < p.H) {
-                            // a source with no k-blocks in this split never wrote its accumulator: treat as zero
-                            const float a0 = hi0 > lo0 ? __uint_as_float(r0[j]) : 0.0f;
-                            const float a1 = hi1 > lo1 ? __uint_as_float(r1[j]) : 0.0f;
-                            dst[row * p.H + c0 + j] = fmaf(p.scale[0], a0, p.scale[1] * a1);
+                        ++done;
+                        if (++in_chunk == per || done == tkb) {
+                            tc_commit(smem_u32(&bar_tfull[astage]));
+                            if (++astage == 2) { astage = 0; aphase ^= 1u; }
+                            in_chunk = 0;
                         }
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bar_tempty));
+        }
+    } else if (svc < 0) {
+        const int q = warp & 3, slice = warp >> 2;
+        int astage = 0;
+        uint32_t aphase = 0;
+        for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+            const int tile = w / p.splits, sp = w % p.splits;
+            const int64_t m0 = (int64_t)(tile / p.n_tiles) * TC_BM, nn0 = (int64_t)(tile % p.n_tiles) * TG_BN;
+            int n0, tkb, nch, per;
+            chunking(sp, n0, tkb, nch, per);
+            float sum[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sum[i] = 0.0f;
+            for (int c = 0; c < nch; ++c) {
+                mbar_wait_epi(smem_u32(&bar_tfull[astage]), aphase);
+                tc_fence_after();
+                // which accumulators did this chunk write?  flattened k-blocks [c per, min((c+1) per, tkb)); source 0 owns [0, n0)
+                const int c_lo = c * per, c_hi = min((c + 1) * per, tkb);
+                const bool use0 = tkb > 0 && c_lo < n0, use1 = tkb > 0 && c_hi > n0;
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(astage * 2) * TG_BN + (uint32_t)(slice * 32);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    uint32_t r0[16], r1[16];
+                    tmem_ld16(ta + g * 16, r0);
+                    tmem_ld16(ta + TG_BN + g * 16, r1);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float a0 = use0 ? __uint_as_float(r0[i]) : 0.0f;
+                        const float a1 = use1 ? __uint_as_float(r1[i]) : 0.0f;
+                        sum[g * 16 + i] += fmaf(p.scale[0], a0, p.scale[1] * a1);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[astage]));
+                if (++astage == 2) { astage = 0; aphase ^= 1u; }
+            }
+            const int64_t row = m0 + q * 32 + lane;
+            float* dst = (p.splits > 1 ? p.partial + (int64_t)sp * p.V * p.H : p.out);
+            if (row < p.V) {
+                const int64_t c0 = nn0 + slice * 32;
+                float* d = dst + row * p.H + c0;
+                if (c0 + 32 <= p.H && (p.H & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0u) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(d + i) = make_float4(sum[i], sum[i + 1], sum[i + 2], sum[i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c0 + i < p.H) d[i] = sum[i];
+                }
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (svc == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TG_TMEM) : "memory");
     }
 }
 
