@@ -30,7 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 UNITS = [2000, 256, 64]
-NB_DRAM_BYTES_PER_CHAIN = 4630.0   # measured: (0.5274 + 4.1025) GB per NB down-sweep launch over 1e6 chains (ncu capture prof_r01g)
+C4_UNITS = [20000, 1024, 256, 64]
 MODEL_SEED = 3
 SEED = 20261019
 
@@ -57,6 +57,30 @@ def peaks():
         return {"tflops_burst": p["bf16_tflops"], "tflops_sustained": p["bf16_tflops_sustained"],
                 "hbm_gbs": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
     return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def kernel_source_hash():
+    """sha256 over the CUDA sources the library is built from: ties a committed ncu capture to the code it profiled."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "scdbm.jl_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(f.encode())
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def static_profile():
+    """ncu counters are NOT measured by this run: they come from a committed capture (profiles/r02_ncu_static.json,
+    written by profiles/ncu_to_static.py) and are reported only while the kernel sources are byte-identical to the
+    ones that were profiled."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_static.json")
+    if not os.path.exists(path):
+        return None
+    sp = json.load(open(path))
+    if sp.get("kernel_source_sha") != kernel_source_hash():
+        return {"stale": True, "capture": sp.get("capture"), "note": "kernel sources changed since the capture; counters withheld"}
+    return sp
 
 
 class ClockSampler(threading.Thread):
@@ -172,16 +196,23 @@ def run_ours(args):
     pk = peaks()
     flops = 2.0 * n * UNITS[1] * UNITS[0]
     achieved = flops / (k_ms * 1e-3) / 1e12
-    roofline = {"kernel": "fused NB down-sweep GEMM (v|h1: tcgen05/SIMT GEMM + NB-mean + Philox NB draw)",
+    # algorithmic HBM bytes of one launch: read h1 (fp16), write the lo count plane (fp16; the hi plane is written
+    # lazily, flag-driven, and stays untouched at scRNA-seq counts) -- computed for THIS run, not measured
+    nb_bytes = float(n) * (UNITS[1] * 2 + UNITS[0] * 2)
+    roofline = {"kernel": "fused NB down-sweep GEMM (v|h1: tcgen05 GEMM + NB-mean + Philox NB draw), k_gemm_tc<224,1,28>",
                 "bound": "tensor", "achieved": achieved, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tflops_burst"],
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel: 4.63e9 B per launch at 1,000,000 chains
-                # (ncu --set full capture, profiles/r01_ncu_summary.md); the lo count plane is written once per sweep
-                "traffic": NB_DRAM_BYTES_PER_CHAIN * n, "traffic_source": "ncu --set full capture prof_r01g (profiles/r01_ncu_summary.md) scaled by chains",
-                "issue_active_pct_ncu": 72.7, "pipes_pct_ncu": {"alu": 43.8, "fma_heavy": 38.7, "xu": 33.7, "tensor": 12.5},
+                "traffic": None, "algorithmic_bytes_per_launch": nb_bytes,
+                "algorithmic_gbs": nb_bytes / (k_ms * 1e-3) / 1e9, "hbm_frac_algorithmic": nb_bytes / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                "traffic_note": "`traffic` (dram bytes from ncu) is not measured by this run: see static_profile",
                 "peak_source": pk["source"] + ", burst (kernel timed alone)",
                 "launch_ms": k_ms, "flops_per_launch": flops, "nb_draws_per_sec": n * UNITS[0] / (k_ms * 1e-3),
-                "note": "sampled sweeps are bound by the draw epilogue (issue/MUFU), not by the tensor pipe; see DESIGN.md"}
+                "note": "sampled sweeps are bound by the draw epilogue (issue slots / dependency latency), not by the tensor pipe; see DESIGN.md"}
+    sp = static_profile()
+    if sp is not None:
+        roofline["static_profile"] = sp
+        if not sp.get("stale") and n == sp.get("chains"):
+            roofline["traffic"] = sp.get("nb_downsweep", {}).get("dram_bytes_per_launch")
     # the deterministic part of the sweep for comparison: the dual-source up-sweep (h1 | v, h2), tensor-bound
     h1out = pkg.Mat(ctx, n, UNITS[1], pkg.MAT_BINARY)
     v0, h2 = p.layer(0), p.layer(2)
@@ -262,6 +293,19 @@ def run_ours(args):
                       "note": "scdbm_mat_csr_prepare + scdbm_mat_download_csr into pinned buffers, synchronous (not overlapped)"}
         del ib, vb
 
+    del p, dm, h1, v0, h2
+    extra = {}
+    if not args.no_secondary:
+        comm_ready = False
+        if world > 1:
+            pkg.init_comm_from_torch(ctx)             # the library's own NCCL communicator (id carried by torch.distributed)
+            comm_ready = True
+        extra["strong_c3"] = strong_c3(pkg, ctx, torch, dist, world, rank, args, host_model, barrier)
+        extra["dp_pcd_c4"] = dp_pcd_c4(pkg, ctx, torch, dist, world, rank, args, barrier, pk)
+        extra["ais_c5"] = ais_c5(pkg, ctx, torch, dist, world, rank, args, barrier, pk)
+        if comm_ready:
+            ctx.comm_destroy()
+
     line = {
         "metric": "Gibbs sweeps x chains / sec (synthetic-cell generation, 2-layer scDBM)",
         "value": value, "unit": "sweeps*chains/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -275,6 +319,7 @@ def run_ours(args):
         "gpu_launches": launches, "tc_launches": tc_launches,
         "e2e": e2e, "roofline": roofline, "clocks": sampler.summary(),
     }
+    line.update(extra)
     if rank == 0 and world == 1 and not args.no_training:
         line["training"] = training_metrics(pkg, ctx, with_cpu=not args.no_cpu_baseline)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -284,6 +329,195 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
 
+
+
+# ------------------------------------------------- other BASELINE configs, fixed TOTAL work (strong scaling over --gpus)
+def _max_over_ranks(torch, dist, world, x):
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def strong_c3(pkg, ctx, torch, dist, world, rank, args, host_model, barrier):
+    """C3 exactly as BASELINE.json words it: 1 M cells TOTAL, chains sharded over the GPUs (no collective)."""
+    total, burnin = args.chains, args.burnin
+    shard = pkg.mostevenbatches(total, world)
+    dm = pkg.DeviceModel.from_host(host_model, ctx)
+    p = pkg.DeviceParticles(dm, shard[rank], sum(shard[:rank]))
+    p.init(False)
+    pkg.gibbssample_(p, dm, burnin)
+    barrier()
+    ctx.timer_start()
+    reps = 2
+    for _ in range(reps):
+        p.init(False)
+        pkg.gibbssample_(p, dm, burnin)
+    ms = _max_over_ranks(torch, dist, world, ctx.timer_stop()) / reps
+    barrier()
+    return {"metric": "Gibbs sweeps x chains / sec", "scaling": "strong", "chains_total": total, "burnin": burnin,
+            "ms_per_pass": ms, "value": total * burnin / (ms * 1e-3), "unit": "sweeps*chains/s", "collective": "none"}
+
+
+def dp_pcd_c4(pkg, ctx, torch, dist, world, rank, args, barrier, pk):
+    """C4: 3-layer scDBM 20000->1024->256->64, PCD (`traindbm!`) on 100 000 cells TOTAL with 8192 persistent
+    particles TOTAL; rows and particles sharded over the GPUs, one NCCL allreduce of the gradient block per step
+    (inside the library), global mean-field stopping rule.  Data are generated on the device per shard."""
+    cells, parts, steps = args.c4_cells, args.c4_particles, args.c4_steps
+    layers = make_model(C4_UNITS, seed=4)
+    host = [pkg.NegativeBinomialBernoulliRBM(**layers[0])] + [pkg.BernoulliRBM(**l) for l in layers[1:]]
+    dm = pkg.DeviceModel.from_host(host, ctx)
+    rows = pkg.mostevenbatches(cells, world)
+    pshard = pkg.mostevenbatches(parts, world)
+    g = np.random.default_rng(4)
+    gene_mean = np.clip(np.exp(g.normal(-1.5, 1.5, C4_UNITS[0])), 1e-3, 50.0)
+    x = pkg.Mat(ctx, rows[rank], C4_UNITS[0], pkg.MAT_COUNT).generate_counts(gene_mean, np.full(C4_UNITS[0], 0.5), 0.3, seed=4,
+                                                                             row_offset=sum(rows[:rank]))
+    p = pkg.DeviceParticles(dm, pshard[rank], row_offset=sum(pshard[:rank])).init(False)
+    lib, ck = pkg.lib(), pkg._lib.check
+    mu = pkg.DeviceParticles(dm, rows[rank], real_valued=True)
+    opt = pkg.LoglikelihoodOptimizer().initialized(dm)
+    import ctypes as C
+    its = C.c_int32()
+
+    def step():
+        if world > 1:
+            ck(lib.scdbm_dbm_pcd_step_dp(dm.h, x.h, p.h, mu.h, opt.h, 1e-4, 5, 1e-3, cells, parts, C.byref(its)))
+        else:
+            ck(lib.scdbm_dbm_pcd_step(dm.h, x.h, p.h, mu.h, opt.h, 1e-4, 5, 1e-3, C.byref(its)))
+
+    for _ in range(2):
+        step()
+    barrier()
+    ctx.launch_count(reset=True)
+    ctx.timer_start()
+    for _ in range(steps):
+        step()
+    ms = _max_over_ranks(torch, dist, world, ctx.timer_stop()) / steps
+    launches = ctx.launch_count() / steps
+    barrier()
+    # the exchange step alone: allreduce(sum) of the whole gradient block on the context's stream
+    ar_ms = None
+    nfl = opt.buffer()[1]
+    if world > 1:
+        for _ in range(2):
+            ck(lib.scdbm_allreduce_gradient(opt.h))
+        barrier()
+        ctx.timer_start()
+        for _ in range(5):
+            ck(lib.scdbm_allreduce_gradient(opt.h))
+        ar_ms = _max_over_ranks(torch, dist, world, ctx.timer_stop()) / 5
+        barrier()
+    S = sum(a * b for a, b in zip(C4_UNITS[:-1], C4_UNITS[1:]))
+    S_hid = sum(a * b for a, b in zip(C4_UNITS[1:-1], C4_UNITS[2:]))
+    mf = int(its.value)
+    flops = 5 * parts * 4 * S + cells * (2 * S + mf * 4 * S_hid) + 2 * (cells + parts) * S       # SURVEY 8d, x W1 hoisted
+    out = {"metric": "DBM PCD steps / sec (traindbm!)", "scaling": "strong", "units": C4_UNITS, "cells_total": cells,
+           "particles_total": parts, "steps": steps, "ms_per_step": ms, "value": 1e3 / ms, "unit": "steps/s",
+           "meanfield_iterations": mf, "launches_per_step": launches,
+           "collective": "ncclAllReduce(sum) of {dW, da, db} on a second stream, in row blocks under the gradient GEMM; "
+                         "ncclAllReduce(max) of one word per mean-field iteration" if world > 1 else "none (1 GPU, same total work)",
+           "allreduce_bytes_per_step": int(nfl * 4) if world > 1 else 0, "allreduce_alone_ms": ar_ms,
+           "allreduce_busbw_gbs": (2.0 * (world - 1) / world * nfl * 4 / (ar_ms * 1e-3) / 1e9) if ar_ms else None,
+           "algorithmic_flops_per_step": flops, "achieved_tflops_aggregate": flops / (ms * 1e-3) / 1e12,
+           "frac_of_tensor_peak_sustained": flops / (ms * 1e-3) / 1e12 / (world * pk["tflops_sustained"])}
+    if rank == 0 and world == 1:
+        out["kernels"] = c4_kernel_rooflines(pkg, ctx, dm, x, mu, p, opt, cells, parts, pk)
+    return out
+
+
+def c4_kernel_rooflines(pkg, ctx, dm, x, mu, p, opt, cells, parts, pk):
+    """Live CUDA-event timings of the deterministic GEMMs at the C4 shapes (K4 mean-field, K5 gradient)."""
+    lib, ck = pkg.lib(), pkg._lib.check
+    V, H1 = C4_UNITS[0], C4_UNITS[1]
+    res = {}
+
+    def timed(f, reps=3):
+        f()
+        ctx.timer_start()
+        for _ in range(reps):
+            f()
+        return ctx.timer_stop() / reps
+
+    # K4: the positive phase.  One fixed iteration = the hoisted x W1 GEMM (n x 20000 x 1024, count operand) + the
+    # initialisation pass + one Gauss-Seidel sweep over the hidden layers; the hoisted GEMM dominates
+    t1 = timed(lambda: ck(lib.scdbm_meanfield(dm.h, x.h, 0.0, 1, mu.h, None, None)))
+    t3 = timed(lambda: ck(lib.scdbm_meanfield(dm.h, x.h, 0.0, 5, mu.h, None, None)))
+    per_iter = (t3 - t1) / 4
+    S_hid = sum(a * b for a, b in zip(C4_UNITS[1:-1], C4_UNITS[2:]))
+    f_init = 2.0 * cells * (V * H1 + S_hid)
+    res["K4_meanfield"] = {"kernel": "k_gemm_tc<128,0,16> (hoisted x*W1, chunk-promoted fp32 accumulation) + hidden-layer sweeps",
+                           "bound": "tensor", "init_ms": t1 - per_iter, "per_iteration_ms": per_iter,
+                           "achieved": f_init / ((t1 - per_iter) * 1e-3) / 1e12, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
+                           "frac": f_init / ((t1 - per_iter) * 1e-3) / 1e12 / pk["tflops_burst"],
+                           "per_iteration_tflops": 4.0 * cells * S_hid / (per_iter * 1e-3) / 1e12,
+                           "note": "count x (W hi + W lo) = 2 plane products issued per algorithmic FLOP"}
+    # K5: StackedOptimizer gradient, all layers (layer 0: (cells + particles) x 20000 x 1024)
+    tg = timed(lambda: ck(lib.scdbm_compute_gradient_dbm(opt.h, dm.h, mu.h, p.h, 0.0, 0.0)))
+    S = sum(a * b for a, b in zip(C4_UNITS[:-1], C4_UNITS[1:]))
+    fg = 2.0 * (cells + parts) * S
+    res["K5_gradient"] = {"kernel": "k_grad_tc (MN-major operands, two TMEM accumulators, chunk-promoted) + column sums",
+                          "bound": "tensor", "launch_ms": tg, "achieved": fg / (tg * 1e-3) / 1e12, "peak": pk["tflops_burst"],
+                          "unit": "TFLOP/s", "frac": fg / (tg * 1e-3) / 1e12 / pk["tflops_burst"],
+                          "note": "count x real (positive phase) = 2 plane products, count x binary (negative) = 1"}
+    return res
+
+
+def ais_c5(pkg, ctx, torch, dist, world, rank, args, barrier, pk):
+    """C5 slice: `aislogimpweights` on the 3-layer scDBM, 65 536 particles TOTAL sharded over the GPUs, the first
+    `--ais-temps` transitions of the 10 000-step schedule collect(0:1e-4:1); the final logmeanexp is reduced over ranks
+    with two scalar allreduces."""
+    parts, T, burnin = args.ais_particles, args.ais_temps, 5
+    layers = make_model(C4_UNITS, seed=4)
+    host = [pkg.NegativeBinomialBernoulliRBM(**layers[0])] + [pkg.BernoulliRBM(**l) for l in layers[1:]]
+    dm = pkg.DeviceModel.from_host(host, ctx)
+    shard = pkg.mostevenbatches(parts, world)
+    off = sum(shard[:rank])
+    temps = np.arange(T + 1) * 1e-4
+    pkg.aislogimpweights(dm, temperatures=temps[:3], nparticles=shard[rank], burnin=burnin, row_offset=off, ctx=ctx)   # warm-up
+    barrier()
+    ctx.timer_start()
+    w = pkg.aislogimpweights(dm, temperatures=temps, nparticles=shard[rank], burnin=burnin, row_offset=off, ctx=ctx)
+    ms = _max_over_ranks(torch, dist, world, ctx.timer_stop())
+    lme = pkg.logmeanexp_sharded(w, ctx)
+    barrier()
+    S = sum(a * b for a, b in zip(C4_UNITS[:-1], C4_UNITS[1:]))
+    flops = T * (burnin * parts * 4.0 * S + 2.0 * parts * S)
+    out = {"metric": "AIS particles x temperatures / sec", "scaling": "strong", "units": C4_UNITS, "particles_total": parts,
+           "transitions": T, "burnin": burnin, "seconds": ms * 1e-3, "value": parts * T / (ms * 1e-3), "unit": "particle*temperatures/s",
+           "collective": "two scalar ncclAllReduce (max, sum) for logmeanexp" if world > 1 else "none",
+           "logmeanexp_slice": float(lme), "algorithmic_flops": flops, "achieved_tflops_aggregate": flops / (ms * 1e-3) / 1e12,
+           "nb_draws_per_sec": T * burnin * parts * C4_UNITS[0] / (ms * 1e-3)}
+    if rank == 0 and world == 1:
+        # K8: the AIS ratio sweeps alone (h1 x W1' -> 20000 softplus differences per particle, row-summed in the epilogue,
+        # plus the even hidden layer): scdbm_ais_run with burnin = 0 launches nothing else per temperature, so the
+        # difference of a 12- and a 2-temperature call is 10 ratio steps (allocation, init and download cancel)
+        P = min(parts, 16384)
+        lib, ck = pkg.lib(), pkg._lib.check
+
+        def ratio_call(ntemps):
+            t = np.ascontiguousarray(0.5 + 1e-4 * np.arange(ntemps))
+            outw = np.zeros(P)
+            ck(lib.scdbm_ais_run(dm.h, t.ctypes.data_as(pkg._lib.D), ntemps, P, 0, 0, outw.ctypes.data_as(pkg._lib.D)))
+
+        def timed(ntemps):
+            ratio_call(ntemps)
+            best = 1e30
+            for _ in range(3):
+                ctx.sync()
+                ctx.timer_start()
+                ratio_call(ntemps)
+                best = min(best, ctx.timer_stop())
+            return best
+
+        t_ratio = (timed(12) - timed(2)) / 10
+        fr = 2.0 * P * (C4_UNITS[0] * C4_UNITS[1] + C4_UNITS[1] * C4_UNITS[2] + C4_UNITS[2] * C4_UNITS[3])
+        out["K8_ais_ratio"] = {"kernel": "k_gemm_tc<128,0,16> EPI_AIS_RATIO: visible layer summed out from h1 (N = 20000, K = 1024) + "
+                                         "even hidden layer; one temperature step without Gibbs transitions",
+                               "bound": "tensor", "particles": P, "per_temperature_ms": t_ratio, "achieved": fr / (t_ratio * 1e-3) / 1e12,
+                               "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": fr / (t_ratio * 1e-3) / 1e12 / pk["tflops_burst"],
+                               "note": "binary x (W hi + W lo) = 2 plane products; 2 softplus evaluations (4 MUFU) per output element"}
+    return out
 
 # ---------------------------------------- secondary metric: CD / PCD epochs per second
 def synth_counts(n, V, seed, r=0.5):
@@ -418,6 +652,12 @@ def main():
     ap.add_argument("--cpu-chains", type=int, default=1500, help="chains per worker in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-training", action="store_true", help="skip the secondary CD/PCD epochs/sec metrics")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the strong-scaling C3 / C4 data-parallel PCD / C5 AIS legs")
+    ap.add_argument("--c4-cells", type=int, default=100_000, help="C4: cells in total (sharded over the GPUs)")
+    ap.add_argument("--c4-particles", type=int, default=8192)
+    ap.add_argument("--c4-steps", type=int, default=5)
+    ap.add_argument("--ais-particles", type=int, default=65536, help="C5: particles in total (sharded over the GPUs)")
+    ap.add_argument("--ais-temps", type=int, default=20, help="C5: transitions timed (slice of the 10 000)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -49,23 +49,18 @@ def main():
     w = pkg.aislogimpweights(dm, temperatures=temps, nparticles=shard[rank], burnin=a.burnin, row_offset=off, ctx=ctx)
     dt = time.perf_counter() - t0
     print(f"[rank {rank}] {shard[rank]} particles, {a.temperatures} transitions: {dt:.3f} s", file=sys.stderr, flush=True)
-    # logmeanexp over all ranks: max, then sum of exp (src/evaluating.jl:935-943)
-    wmax, n = float(w.max()), float(len(w))
+    # logmeanexp over all ranks (src/evaluating.jl:935-943): two scalar allreduces through the library's communicator
     if world > 1:
-        t = torch.tensor([wmax], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        wmax = float(t.item())
-    s = float(np.exp(w - wmax).sum())
+        pkg.init_comm_from_torch(ctx)
+    lme = pkg.logmeanexp_sharded(w, ctx)
     if world > 1:
-        t = torch.tensor([s, n, dt], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t[:2])
-        td = t[2:].clone()
+        td = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(td, op=dist.ReduceOp.MAX)
-        s, n, dt = float(t[0].item()), float(t[1].item()), float(td.item())
+        dt = float(td.item())
     if rank == 0:
         print(json.dumps({"n_gpus": world, "units": a.units, "particles": a.particles, "transitions": a.temperatures, "burnin": a.burnin,
                           "seconds": dt, "particle_temperatures_per_sec": a.particles * a.temperatures / dt,
-                          "logmeanexp_slice": wmax + np.log(s) - np.log(n)}), flush=True)
+                          "logmeanexp_slice": float(lme)}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Data-parallel DBM PCD (`traindbm!`, src/dbmtraining.jl:287-297) over N GPUs:
 data rows and persistent particles are sharded by rank; per step one NCCL
-allreduce(sum) of the contiguous gradient block {dW_l, da_l, db_l}.
+allreduce(sum) of the contiguous gradient block {dW_l, da_l, db_l}, issued by the
+library itself (scdbm_comm_init / scdbm_dbm_pcd_step_dp); torch.distributed only
+carries the 128-byte communicator id and the final timing reduction.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port 29511 examples/dp_pcd.py --cells 20000 --units 2000 256 64 --steps 5 [--check]
@@ -10,7 +12,6 @@ allreduce(sum) of the contiguous gradient block {dW_l, da_l, db_l}.
 compares the parameters (fp32 reduction-order tolerance).
 """
 import argparse
-import ctypes as C
 import json
 import os
 import sys
@@ -23,28 +24,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 from bench import make_model  # noqa: E402
-
-
-class NcclAllreduce:
-    """allreduce hook for pkg.traindbm_: wraps the library's gradient buffer (raw device pointer)
-    as a torch tensor and sums it over ranks with NCCL."""
-
-    def __init__(self, device):
-        self.device = device
-        self.bytes = 0
-
-    def global_counts(self, nrows, nparticles):
-        t = torch.tensor([nrows, nparticles], dtype=torch.float64, device=self.device)
-        dist.all_reduce(t)
-        return float(t[0].item()), float(t[1].item())
-
-    def __call__(self, ptr, nfloats):
-        class _Arr:  # __cuda_array_interface__ view of the library-owned buffer
-            __cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (ptr, False), "version": 3}
-        t = torch.as_tensor(_Arr(), device=self.device)
-        dist.all_reduce(t)
-        torch.cuda.current_stream().synchronize()
-        self.bytes += nfloats * 4
 
 
 def counts(n, V, seed):
@@ -82,17 +61,18 @@ def main():
     dm = pkg.DeviceModel.from_host(host, ctx)
     xm = pkg.Mat.from_host(ctx, x[rows], pkg.MAT_COUNT)
     p = pkg.DeviceParticles(dm, pshard[rank], row_offset=poff).init(False)
-    hook = NcclAllreduce(dev)
+    pkg.init_comm_from_torch(ctx)
     dist.barrier()
     torch.cuda.synchronize()
     ctx.timer_start()
-    pkg.traindbm_(dm, xm, epochs=a.steps, learningrate=1e-3, particles=p, allreduce=hook, device=True, ctx=ctx)
+    pkg.traindbm_(dm, xm, epochs=a.steps, learningrate=1e-3, particles=p, global_nsamples=a.cells,
+                  global_nparticles=a.particles, device=True, ctx=ctx)
     ms = ctx.timer_stop()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     res = {"n_gpus": world, "cells": a.cells, "units": a.units, "particles": a.particles, "steps": a.steps,
            "ms_per_step": float(t.item()) / a.steps, "pcd_steps_per_sec": a.steps / (float(t.item()) * 1e-3),
-           "allreduce_bytes_per_step": hook.bytes // a.steps}
+           "allreduce_bytes_per_step": 4 * sum(u * v + u + v for u, v in zip(a.units[:-1], a.units[1:]))}
     if a.check and rank == 0:
         ctx1 = pkg.Context(local, 20261019)
         dm1 = pkg.DeviceModel.from_host(host, ctx1)

@@ -197,7 +197,8 @@ int32_t scdbm_sample_dropout(scdbm_mat* v, const scdbm_mat* x, const double* mid
 /* ---- mean-field (src/dbmtraining.jl:175-228) ------------------------------
  * mu: particles with nparticles == rows(x); layer 0 is set to x.  Runs until
  * the global max-abs change <= eps or maxiter iterations (maxiter <= 0: no cap).
- * x.W1 is hoisted out of the loop. */
+ * x.W1 is hoisted out of the loop.  The stopping rule is evaluated on the device; iterations are
+ * launched four at a time and those after convergence are no-ops, so the host synchronises once per group. */
 int32_t scdbm_meanfield(scdbm_model* m, const scdbm_mat* x, double eps, int32_t maxiter, scdbm_particles* mu,
                         int32_t* niter, double* delta);
 
@@ -247,6 +248,30 @@ int32_t scdbm_rbm_train_epoch(scdbm_trainer* t, const scdbm_mat* x, const int32_
  * gibbssample!(particles, dbm, nsteps); meanfield; gradient; update. */
 int32_t scdbm_dbm_pcd_step(scdbm_model* m, const scdbm_mat* x, scdbm_particles* particles, scdbm_particles* mu,
                            scdbm_opt* o, double learningrate, int32_t nsteps, double eps, int32_t* mf_iters);
+
+/* ---- data-parallel exchange (NCCL over NVLink, libnccl.so.2 resolved at run time) ------------------
+ * One process per GPU.  Rank 0 obtains a 128-byte id (scdbm_comm_unique_id), hands it to the other ranks by any
+ * out-of-band means, and every rank calls scdbm_comm_init on its context.  With a communicator
+ *  - scdbm_dbm_pcd_step_dp is traindbm!(dbm, x, particles, opt) (src/dbmtraining.jl:287-297) over row shards of x
+ *    and shards of the particles: every rank forms its partial sums scaled by the GLOBAL 1/n+ and 1/n-
+ *    (src/optimizers.jl:272-283), the gradient block {dW_l, da_l, db_l} is summed by allreduce on a second stream
+ *    while later blocks are still being computed, and every rank applies the same update;
+ *  - scdbm_meanfield / the step use the reference's GLOBAL stopping rule: one scalar allreduce(max) of the
+ *    iteration's max |change| (src/dbmtraining.jl:194-225), so all ranks run the same number of iterations and the
+ *    result does not depend on the sharding (every rank must call it, an empty shard included);
+ *  - scdbm_allreduce_gradient sums the optimizer's whole block in place on the context's stream (for callers that
+ *    drive computegradient! / updateparameters! themselves);
+ *  - scdbm_comm_allreduce_f64 reduces <= 64 host scalars (op 0 sum, 1 max): logmeanexp over particle shards
+ *    (src/evaluating.jl:935-943,979-984).
+ * Generation and AIS need no collective: chains / particles are addressed by their global index (row_offset). */
+int32_t scdbm_comm_unique_id(uint8_t* id128);
+int32_t scdbm_comm_init(scdbm_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t nranks);
+int32_t scdbm_comm_destroy(scdbm_ctx* ctx);
+int32_t scdbm_allreduce_gradient(scdbm_opt* o);
+int32_t scdbm_comm_allreduce_f64(scdbm_ctx* ctx, double* values, int32_t n, int32_t op);
+int32_t scdbm_dbm_pcd_step_dp(scdbm_model* m, const scdbm_mat* x, scdbm_particles* particles, scdbm_particles* mu,
+                              scdbm_opt* o, double learningrate, int32_t nsteps, double eps, int64_t global_nsamples,
+                              int64_t global_nparticles, int32_t* mf_iters);
 
 /* ---- AIS (src/evaluating.jl:18-46,164-206,265-355,1314-1364,1596-1648) -----
  * Returns nparticles log importance weights.  temperatures[0..ntemps-1]

@@ -76,6 +76,12 @@ PROTOTYPES = {
     "scdbm_rbm_train_epoch": [P, P, C.POINTER(I32), F64, I32, F64, F64],
     "scdbm_dbm_pcd_step": [P, P, P, P, P, F64, I32, F64, C.POINTER(I32)],
     "scdbm_ais_run": [P, D, I32, I64, I32, U64, D],
+    "scdbm_comm_unique_id": [C.POINTER(C.c_uint8)],
+    "scdbm_comm_init": [P, C.POINTER(C.c_uint8), I32, I32],
+    "scdbm_comm_destroy": [P],
+    "scdbm_allreduce_gradient": [P],
+    "scdbm_comm_allreduce_f64": [P, D, I32, I32],
+    "scdbm_dbm_pcd_step_dp": [P, P, P, P, P, F64, I32, F64, I64, I64, C.POINTER(I32)],
     "scdbm_gibbs_cond": [P, P, C.POINTER(C.c_uint8), I64, I64, I32],
     "scdbm_sample_dropout": [P, P, D, D, I32, I32, U32, U64],
     "scdbm_trainer_track_mean": [P, I32],

@@ -64,6 +64,38 @@ class Context:
         check(lib().scdbm_launch_count(self.h, C.byref(n), int(reset)))
         return n.value
 
+    # ---- data-parallel communicator (NCCL inside the library)
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id; rank 0 creates it and hands it to the other ranks out of band."""
+        buf = (C.c_uint8 * 128)()
+        check(lib().scdbm_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, nranks):
+        if len(unique_id) != 128:
+            raise ValueError("unique_id must be the 128 bytes of Context.comm_unique_id()")
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(lib().scdbm_comm_init(self.h, buf, int(rank), int(nranks)))
+        return self
+
+    def comm_destroy(self):
+        check(lib().scdbm_comm_destroy(self.h))
+
+    @property
+    def comm_size(self):
+        return int(self.get("comm_size"))
+
+    @property
+    def comm_rank(self):
+        return int(self.get("comm_rank"))
+
+    def allreduce(self, values, op="sum"):
+        """Sum / max of a few host scalars over the ranks (logmeanexp over particle shards, global sample counts)."""
+        v = np.ascontiguousarray(np.atleast_1d(values), dtype=np.float64).copy()
+        check(lib().scdbm_comm_allreduce_f64(self.h, _ptr(v), len(v), {"sum": 0, "max": 1}[op]))
+        return v
+
     def close(self):
         if self.h:
             lib().scdbm_ctx_destroy(self.h)
@@ -74,6 +106,38 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def exchange_unique_id(make_id, rank, broadcast):
+    """Rank 0 calls `make_id()`; `broadcast(obj_or_None) -> obj` carries it to every rank (torch.distributed
+    `broadcast_object_list`, MPI bcast, a file ...).  Returns the 128-byte id on every rank."""
+    uid = make_id() if rank == 0 else None
+    uid = broadcast(uid)
+    if not isinstance(uid, (bytes, bytearray)) or len(uid) != 128:
+        raise RuntimeError("unique id exchange failed: expected 128 bytes on every rank")
+    return bytes(uid)
+
+
+def init_comm_from_torch(ctx):
+    """Gives `ctx` a communicator spanning the ranks of an initialised `torch.distributed` process group (used only
+    to carry the 128-byte id; the collectives of the hot path are the library's own NCCL calls)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+
+    def bcast(obj):
+        box = [obj]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    return ctx.comm_init(exchange_unique_id(Context.comm_unique_id, rank, bcast), rank, world)
+
+
+def logmeanexp_sharded(w, ctx):
+    """`logmeanexp` (src/evaluating.jl:935-943) of importance weights sharded over the ranks of `ctx`'s communicator."""
+    w = np.asarray(w, float)
+    wmax = float(ctx.allreduce([w.max() if len(w) else -np.inf], "max")[0])
+    s, n = ctx.allreduce([np.exp(w - wmax).sum(), float(len(w))], "sum")
+    return wmax + np.log(s) - np.log(n)
 
 
 _default_ctx = None
@@ -911,9 +975,11 @@ def defaultfinetuninglearningrates(learningrate, epochs):
 
 
 def traindbm_(dbm, x, epochs=10, nparticles=100, learningrate=0.005, learningrates=None, monitoring=None,
-              particles=None, nsteps=5, eps=0.001, allreduce=None, device=False, ctx=None):
-    """`traindbm!` (src/dbmtraining.jl:250-297).  `allreduce(ptr, nfloats)`:
-    optional hook that sums the gradient block over data-parallel ranks."""
+              particles=None, nsteps=5, eps=0.001, global_nsamples=None, global_nparticles=None, device=False, ctx=None):
+    """`traindbm!` (src/dbmtraining.jl:250-297).  When the model's context has a communicator (`Context.comm_init`),
+    `x` and `particles` are this rank's shards and the step is data-parallel: partial sums scaled by the global counts,
+    gradient block summed by NCCL inside the library, global mean-field stopping rule, identical update on every rank.
+    `global_nsamples` / `global_nparticles` default to the sums of the shard sizes over the ranks."""
     m = _model(dbm, ctx)
     xm = _as_mat(m.ctx, x, _data_kind(m))
     if learningrates is None:
@@ -923,19 +989,17 @@ def traindbm_(dbm, x, epochs=10, nparticles=100, learningrate=0.005, learningrat
     p = particles if particles is not None else DeviceParticles(m, nparticles).init(False)
     mu = DeviceParticles(m, xm.rows, real_valued=True)
     opt = LoglikelihoodOptimizer().initialized(m)
+    dp = m.ctx.comm_size > 1
+    if dp and (global_nsamples is None or global_nparticles is None):
+        tot = m.ctx.allreduce([xm.rows, p.n], "sum")          # once, outside the epoch loop
+        global_nsamples = int(tot[0]) if global_nsamples is None else global_nsamples
+        global_nparticles = int(tot[1]) if global_nparticles is None else global_nparticles
     for epoch in range(epochs):
-        if allreduce is None:
-            check(lib().scdbm_dbm_pcd_step(m.h, xm.h, p.h, mu.h, opt.h, float(learningrates[epoch]), nsteps, eps, None))
+        if dp:
+            check(lib().scdbm_dbm_pcd_step_dp(m.h, xm.h, p.h, mu.h, opt.h, float(learningrates[epoch]), nsteps, eps,
+                                              int(global_nsamples), int(global_nparticles), None))
         else:
-            check(lib().scdbm_gibbs(m.h, p.h, nsteps, 1.0, 1.0, 1.0))
-            check(lib().scdbm_meanfield(m.h, xm.h, eps, 0, mu.h, None, None))
-            npos, nneg = allreduce.global_counts(xm.rows, p.n)
-            opt.computegradient_dbm_(mu, p, m, 1.0 / npos, 1.0 / nneg)
-            ptr, nfl = opt.buffer()
-            m.ctx.sync()
-            allreduce(ptr, nfl)
-            opt.learningrate = float(learningrates[epoch])
-            opt.updateparameters_(m)
+            check(lib().scdbm_dbm_pcd_step(m.h, xm.h, p.h, mu.h, opt.h, float(learningrates[epoch]), nsteps, eps, None))
         if monitoring is not None:
             monitoring(m.to_host(), epoch + 1)
     opt.close()

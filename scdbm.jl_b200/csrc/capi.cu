@@ -5,6 +5,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "sparse.cuh"
+#include "comm.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -68,6 +69,16 @@ struct scdbm_ctx {
     uint16_t* stage16 = nullptr;
     size_t stage16_cap = 0;
     bool copy_pending = false;
+    // mean-field convergence state {delta bits, converged, iterations, last delta bits} on the device, mirrored into mapped
+    // pinned host memory by k_mf_check so that the host reads it without a copy
+    unsigned int* d_mf = nullptr;
+    unsigned int *h_mf = nullptr, *d_hmf = nullptr;
+    // data-parallel communicator (scdbm_comm_init): NCCL over NVLink, collectives ordered on the context's streams
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    cudaStream_t comm_stream = nullptr;     // gradient allreduce overlapping the remaining gradient GEMMs
+    cudaEvent_t ev_grad = nullptr, ev_comm = nullptr;
+    double* d_red = nullptr;                // small reduction buffer (scdbm_comm_allreduce_f64)
     int64_t live = 0;      // child handles still alive
     bool closed = false;   // scdbm_ctx_destroy was called; freed when `live` drops to 0
 };
@@ -79,6 +90,11 @@ static void ctx_free(scdbm_ctx* c) {
         cudaEventDestroy(c->ev_conv);
         cudaEventDestroy(c->ev_copy);
     }
+    if (c->comm) nccl_api().CommDestroy(c->comm);
+    if (c->comm_stream) { cudaStreamDestroy(c->comm_stream); cudaEventDestroy(c->ev_grad); cudaEventDestroy(c->ev_comm); }
+    cudaFree(c->d_red);
+    cudaFree(c->d_mf);
+    if (c->h_mf) cudaFreeHost(c->h_mf);
     cudaFree(c->stage16);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -517,6 +533,9 @@ int32_t scdbm_ctx_create(int32_t device, uint64_t seed, void* stream, scdbm_ctx*
     CK(cudaHostAlloc(&c->h_flag, sizeof(unsigned int), cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer(&c->d_flag, c->h_flag, 0));
     *c->h_flag = 0u;
+    CK(cudaMalloc(&c->d_mf, 4 * sizeof(unsigned int)));
+    CK(cudaHostAlloc(&c->h_mf, 4 * sizeof(unsigned int), cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer(&c->d_hmf, c->h_mf, 0));
     {   // keep freed state matrices in the device's default memory pool instead of returning them to the driver
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -566,6 +585,8 @@ int32_t scdbm_ctx_get_option(scdbm_ctx* c, const char* name, double* value) {
     else if (n == "seed") *value = (double)c->seed;
     else if (n == "num_sms") *value = c->num_sms;
     else if (n == "tc_launches") *value = (double)c->tc_launches;
+    else if (n == "comm_rank") *value = c->rank;
+    else if (n == "comm_size") *value = c->nranks;
     else throw Err(SCDBM_EINVAL, "unknown option: " + n);
     API_END
 }
@@ -1376,13 +1397,23 @@ int32_t scdbm_particles_visible_potential(scdbm_model* m, scdbm_particles* p, sc
 }
 
 // -------------------------------------------------------------- mean-field
-static float read_delta(scdbm_ctx* c) {
-    unsigned int bits = 0;
-    CK(cudaMemcpyAsync(&bits, c->d_delta, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    float f;
-    memcpy(&f, &bits, sizeof(f));
-    return f;
+// after one mean-field iteration: fold this iteration's max |change| into the convergence state.  One thread.
+//   st[0] delta bits of the iteration (reset), st[1] converged flag, st[2] iterations run, st[3] delta bits of the last one
+__global__ void k_mf_check(unsigned int* st, float eps, unsigned int* host_mirror) {
+    if (st[1] == 0u) {
+        const float delta = __uint_as_float(st[0]);
+        st[2] += 1u;
+        st[3] = st[0];
+        if (!(delta > eps)) st[1] = 1u;
+    }
+    st[0] = 0u;
+    host_mirror[1] = st[1];
+    host_mirror[2] = st[2];
+    host_mirror[3] = st[3];
+}
+
+static void nccl_check(ncclResult_t r, const char* what) {
+    if (r != ncclSuccess) throw Err(SCDBM_ECUDA, std::string(what) + ": " + nccl_api().GetErrorString(r));
 }
 
 static void meanfield_impl(scdbm_model* m, const scdbm_mat* x, double eps, int maxiter, scdbm_particles* mu, int* niter,
@@ -1398,11 +1429,14 @@ static void meanfield_impl(scdbm_model* m, const scdbm_mat* x, double eps, int m
         mu->alias0 = mat_view_of(const_cast<scdbm_mat*>(x));
     }
     mu->alias0->v = x->v;
-    if (n == 0) { if (niter) *niter = 0; if (delta_out) *delta_out = 0; return; }
+    // data-parallel: every rank iterates (an empty shard too) -- the stopping rule is the GLOBAL max over all rows
+    // (src/dbmtraining.jl:194-225), one scalar allreduce(max) per iteration
+    const bool global_delta = c->comm != nullptr;
+    if (n == 0 && !global_delta) { if (niter) *niter = 0; if (delta_out) *delta_out = 0; return; }
     // hoist x*W1 (loop invariant; the reference recomputes it, quirk B10)
     Layer& L0 = m->L[0];
-    if (!mu->hoist) CK(cudaMalloc(&mu->hoist, (size_t)n * L0.H * sizeof(float)));
-    {
+    if (!mu->hoist && n > 0) CK(cudaMalloc(&mu->hoist, (size_t)n * L0.H * sizeof(float)));
+    if (n > 0) {
         EpiParams e = epi_base(c);
         e.mode = EPI_RAW_F32;
         e.out_f32 = mu->hoist;
@@ -1410,6 +1444,7 @@ static void meanfield_impl(scdbm_model* m, const scdbm_mat* x, double eps, int m
         SweepSrc s{&x->v, &L0, true};
         run_sweep(c, &s, 1, n, L0.H, e);
     }
+    const unsigned int* skip = nullptr;
     auto from_hoist = [&](const MatView& out, float factor, const MatView* prev) {
         // sigm(factor * (x W1 + b1)) with no contraction
         EpiParams e = epi_base(c);
@@ -1418,49 +1453,82 @@ static void meanfield_impl(scdbm_model* m, const scdbm_mat* x, double eps, int m
         e.addend = mu->hoist; e.ld_add = L0.H;
         e.factor = factor;
         e.out = out;
-        if (prev) { e.prev = *prev; e.delta_bits = c->d_delta; }
+        e.skip = skip;
+        if (prev) { e.prev = *prev; e.delta_bits = c->d_mf; }
         run_sweep(c, nullptr, 0, n, L0.H, e);
     };
     // bottom-up initialisation with doubled weights except for the top layer (dbmtraining.jl:182-186)
     DrawCfg d;
-    for (int i = 1; i < nl; ++i) {
+    for (int i = 1; i < nl && n > 0; ++i) {
         const float factor = (i < nl - 1) ? 2.0f : 1.0f;
         if (i == 1) from_hoist(mu->cur[1]->v, factor, nullptr);
         else op_hidden(m, i - 1, mu->cur[i - 1]->v, mu->cur[i]->v, factor, SCDBM_OUT_POTENTIAL, d);
     }
-    double delta = 1.0;
-    int it = 0;
-    // the reference loops without a cap; fp32 round-off can keep delta above a tiny eps forever, so stop
-    // after MF_ITER_CAP sweeps and report the delta reached (the caller sees delta > eps)
-    const int MF_ITER_CAP = 10000;
-    while (delta > eps && it < (maxiter > 0 ? maxiter : MF_ITER_CAP)) {
-        CK(cudaMemsetAsync(c->d_delta, 0, sizeof(unsigned int), c->stream));
-        for (int i = 1; i < nl - 1; ++i) {
-            const MatView& cur = mu->cur[i]->v;
-            op_dbm_layer(m, i, i == 1 ? nullptr : &mu->cur[i - 1]->v, i == 1 ? mu->hoist : nullptr, L0.H, mu->cur[i + 1]->v, cur,
-                         SCDBM_OUT_POTENTIAL, d, &cur, c->d_delta);
-        }
-        // last layer from the NEW layer below (Gauss-Seidel, dbmtraining.jl:218-224)
-        {
-            const MatView& cur = mu->cur[nl - 1]->v;
-            if (nl == 2) from_hoist(cur, 1.0f, &cur);
-            else {
-                Layer& L = m->L[nl - 2];
-                EpiParams e = epi_base(c);
-                e.mode = EPI_SIGM;
-                e.bias0 = L.b;
-                e.out = cur;
-                e.prev = cur;
-                e.delta_bits = c->d_delta;
-                SweepSrc s{&mu->cur[nl - 2]->v, &L, true};
-                run_sweep(c, &s, 1, n, L.H, e);
+    // Fixed-point iterations.  The stopping rule lives on the device: k_mf_check raises a flag once the max |change| of an
+    // iteration is <= eps, and the sweeps of iterations launched after that are no-ops.  Iterations are launched in groups
+    // of MF_GROUP without any host round trip; the host looks at the (mapped) state once per group.
+    // The reference loops without a cap; fp32 round-off can keep delta above a tiny eps forever, so stop after MF_ITER_CAP
+    // sweeps and report the delta reached (the caller sees delta > eps).
+    const int MF_ITER_CAP = 10000, MF_GROUP = 4;
+    const int cap = maxiter > 0 ? maxiter : MF_ITER_CAP;
+    CK(cudaMemsetAsync(c->d_mf, 0, 4 * sizeof(unsigned int), c->stream));
+    c->h_mf[1] = c->h_mf[2] = c->h_mf[3] = 0u;
+    skip = c->d_mf + 1;
+    int launched = 0;
+    bool done = !(1.0 > eps);   // `delta = 1.0; while delta > eps` (dbmtraining.jl:194)
+    float last_delta = done ? 1.0f : 0.0f;
+    while (!done && launched < cap) {
+        const int group = std::min(MF_GROUP, cap - launched);
+        for (int gi = 0; gi < group; ++gi) {
+            if (n > 0) {
+                for (int i = 1; i < nl - 1; ++i) {
+                    const MatView& cur = mu->cur[i]->v;
+                    // intermediate layers from both neighbours (Gauss-Seidel over layers, dbmtraining.jl:197-207)
+                    Layer& Lb = m->L[i - 1];
+                    Layer& La = m->L[i];
+                    EpiParams e = epi_base(c);
+                    e.mode = EPI_SIGM;
+                    e.bias0 = Lb.b;
+                    e.bias1 = La.a;
+                    e.out = cur;
+                    e.prev = cur;
+                    e.delta_bits = c->d_mf;
+                    e.skip = skip;
+                    SweepSrc srcs[2];
+                    int ns = 0;
+                    if (i == 1) { e.addend = mu->hoist; e.ld_add = L0.H; }
+                    else srcs[ns++] = SweepSrc{&mu->cur[i - 1]->v, &Lb, true};
+                    srcs[ns++] = SweepSrc{&mu->cur[i + 1]->v, &La, false};
+                    run_sweep(c, srcs, ns, n, Lb.H, e);
+                }
+                // last layer from the NEW layer below (Gauss-Seidel, dbmtraining.jl:218-224)
+                const MatView& cur = mu->cur[nl - 1]->v;
+                if (nl == 2) from_hoist(cur, 1.0f, &cur);
+                else {
+                    Layer& L = m->L[nl - 2];
+                    EpiParams e = epi_base(c);
+                    e.mode = EPI_SIGM;
+                    e.bias0 = L.b;
+                    e.out = cur;
+                    e.prev = cur;
+                    e.delta_bits = c->d_mf;
+                    e.skip = skip;
+                    SweepSrc s{&mu->cur[nl - 2]->v, &L, true};
+                    run_sweep(c, &s, 1, n, L.H, e);
+                }
             }
+            // non-negative floats order like their bit patterns: max over ranks of the uint32 word
+            if (global_delta) nccl_check(nccl_api().AllReduce(c->d_mf, c->d_mf, 1, ncclUint32, ncclMax, c->comm, c->stream), "ncclAllReduce(max delta)");
+            k_mf_check<<<1, 1, 0, c->stream>>>(c->d_mf, (float)eps, c->d_hmf);
+            c->launches++;
         }
-        delta = read_delta(c);
-        ++it;
+        launched += group;
+        CK(cudaStreamSynchronize(c->stream));
+        done = c->h_mf[1] != 0u;
+        memcpy(&last_delta, &c->h_mf[3], sizeof(float));
     }
-    if (niter) *niter = it;
-    if (delta_out) *delta_out = delta;
+    if (niter) *niter = (int)c->h_mf[2];
+    if (delta_out) *delta_out = last_delta;
 }
 
 int32_t scdbm_meanfield(scdbm_model* m, const scdbm_mat* x, double eps, int32_t maxiter, scdbm_particles* mu,
@@ -1504,18 +1572,28 @@ int32_t scdbm_opt_destroy(scdbm_opt* o) {
     API_END
 }
 
-// dW = pos_scale * v'h - neg_scale * vm'hm ; da, db likewise from column sums
-static void gradient_layer(scdbm_opt* o, int l, const MatView& v, const MatView& vm, const MatView& h, const MatView& hm,
-                           float pos_scale, float neg_scale) {
+// dW rows [v0, v0 + vn) of layer l:  pos_scale * v'h - neg_scale * vm'hm  (vn < 0: all rows)
+static void gradient_weights(scdbm_opt* o, int l, const MatView& v_, const MatView& vm_, const MatView& h, const MatView& hm,
+                             float pos_scale, float neg_scale, int64_t v0 = 0, int64_t vn = -1) {
     scdbm_model* m = o->model;
     scdbm_ctx* c = m->ctx;
     Layer& L = m->L[l];
-    REQUIRE(v.cols == L.V && vm.cols == L.V && h.cols == L.H && hm.cols == L.H, "gradient: widths do not match the RBM");
-    REQUIRE(v.rows == h.rows && vm.rows == hm.rows, "gradient: row counts of v/h (or vmodel/hmodel) differ");
+    REQUIRE(v_.cols == L.V && vm_.cols == L.V && h.cols == L.H && hm.cols == L.H, "gradient: widths do not match the RBM");
+    REQUIRE(v_.rows == h.rows && vm_.rows == hm.rows, "gradient: row counts of v/h (or vmodel/hmodel) differ");
+    if (vn < 0) vn = L.V;
+    auto cols_view = [&](const MatView& x) {
+        MatView r = x;
+        r.p0 += v0;
+        if (r.p1) r.p1 += v0;
+        if (r.f) r.f += v0;
+        r.cols = vn;
+        return r;
+    };
+    const MatView v = cols_view(v_), vm = cols_view(vm_);
     GemmArgs g;
     memset(&g, 0, sizeof(g));
     g.nsrc = 2;
-    g.M = L.V;
+    g.M = vn;
     g.N = L.H;
     auto opT = [](const MatView& x) { return x.f ? Operand{nullptr, nullptr, x.f, 1, x.ld, x.kind} : Operand{x.p0, x.p1, nullptr, 1, x.ld, x.kind}; };
     g.src[0].a = opT(v);
@@ -1528,16 +1606,16 @@ static void gradient_layer(scdbm_opt* o, int l, const MatView& v, const MatView&
     g.src[1].scale = -neg_scale;
     g.epi = epi_base(c);
     g.epi.mode = EPI_RAW_F32;
-    g.epi.out_f32 = o->buf + o->offW[l];
+    g.epi.out_f32 = o->buf + o->offW[l] + v0 * L.H;
     g.epi.ldo = L.H;
     bool done = false;
-    const double work = (double)L.V * (double)L.H * (double)(v.rows + vm.rows);
+    const double work = (double)vn * (double)L.H * (double)(v.rows + vm.rows);
     if (c->engine == SCDBM_ENGINE_TC || (c->engine == SCDBM_ENGINE_AUTO && work >= (double)(1 << 24))) {
-        TcGradArgs ga{v, h, vm, hm, pos_scale, -neg_scale, g.epi.out_f32, L.V, L.H, nullptr, 1};
+        TcGradArgs ga{v, h, vm, hm, pos_scale, -neg_scale, g.epi.out_f32, vn, L.H, nullptr, 1};
         if (tc_grad_supported(ga)) {
             ga.splits = tc_grad_splits(ga, c->num_sms);
             if (ga.splits > 1) {
-                const int64_t need = (int64_t)ga.splits * L.V * L.H;
+                const int64_t need = (int64_t)ga.splits * vn * L.H;
                 if (c->scratch_cap < need) {
                     CK(cudaStreamSynchronize(c->stream));
                     cudaFree(c->scratch);
@@ -1555,6 +1633,14 @@ static void gradient_layer(scdbm_opt* o, int l, const MatView& v, const MatView&
     }
     if (!done) CK(launch_gemm_simt(g, c->stream));
     c->launches++;
+}
+
+// da, db of layer l from column sums (deterministic two-pass reduction)
+static void gradient_biases(scdbm_opt* o, int l, const MatView& v, const MatView& vm, const MatView& h, const MatView& hm,
+                            float pos_scale, float neg_scale) {
+    scdbm_model* m = o->model;
+    scdbm_ctx* c = m->ctx;
+    Layer& L = m->L[l];
     float* ga = o->buf + o->offA[l];
     float* gb = o->buf + o->offB[l];
     CK(cudaMemsetAsync(ga, 0, (size_t)(L.V + L.H) * sizeof(float), c->stream));  // offA and offB are adjacent
@@ -1563,6 +1649,49 @@ static void gradient_layer(scdbm_opt* o, int l, const MatView& v, const MatView&
     colsum(c, h, pos_scale, gb, true);
     colsum(c, hm, -neg_scale, gb, true);
     CK(cudaGetLastError());
+}
+
+static void gradient_layer(scdbm_opt* o, int l, const MatView& v, const MatView& vm, const MatView& h, const MatView& hm,
+                           float pos_scale, float neg_scale) {
+    gradient_weights(o, l, v, vm, h, hm, pos_scale, neg_scale);
+    gradient_biases(o, l, v, vm, h, hm, pos_scale, neg_scale);
+}
+
+// ---- data-parallel exchange: allreduce(sum) of gradient ranges on the communication stream, ordered behind the work
+// queued so far on the context's stream; comm_join() makes the context's stream wait for all of them
+static void comm_allreduce_range(scdbm_ctx* c, float* ptr, int64_t n) {
+    if (!c->comm || n <= 0) return;
+    CK(cudaEventRecord(c->ev_grad, c->stream));
+    CK(cudaStreamWaitEvent(c->comm_stream, c->ev_grad, 0));
+    nccl_check(nccl_api().AllReduce(ptr, ptr, (size_t)n, ncclFloat32, ncclSum, c->comm, c->comm_stream), "ncclAllReduce(gradient)");
+}
+static void comm_join(scdbm_ctx* c) {
+    if (!c->comm) return;
+    CK(cudaEventRecord(c->ev_comm, c->comm_stream));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+}
+
+// StackedOptimizer gradient of all layers; with a communicator the block is summed over ranks while it is being
+// produced: the weight gradient of a large layer is computed in row blocks and the allreduce of block i runs on the
+// communication stream (NVLink) under the GEMM of block i + 1
+static void gradient_dbm(scdbm_opt* o, scdbm_model* m, scdbm_particles* mu, scdbm_particles* p, float ps, float ns) {
+    scdbm_ctx* c = m->ctx;
+    for (int l = 0; l < (int)m->L.size(); ++l) {
+        Layer& L = m->L[l];
+        const MatView& v = l == 0 ? mu->alias0->v : mu->cur[l]->v;
+        const MatView &vm = p->cur[l]->v, &h = mu->cur[l + 1]->v, &hm = p->cur[l + 1]->v;
+        const int64_t nW = (int64_t)L.V * L.H;
+        const int nblk = (c->comm && nW >= (int64_t)(4 << 20)) ? 4 : 1;
+        const int64_t step = round_up((L.V + nblk - 1) / nblk, 128);
+        for (int64_t v0 = 0; v0 < L.V; v0 += step) {
+            const int64_t vn = std::min<int64_t>(step, L.V - v0);
+            gradient_weights(o, l, v, vm, h, hm, ps, ns, v0, vn);
+            comm_allreduce_range(c, o->buf + o->offW[l] + v0 * L.H, vn * L.H);
+        }
+        gradient_biases(o, l, v, vm, h, hm, ps, ns);
+        comm_allreduce_range(c, o->buf + o->offA[l], L.V + L.H);
+    }
+    comm_join(c);
 }
 
 int32_t scdbm_compute_gradient(scdbm_opt* o, scdbm_model* m, int32_t l, const scdbm_mat* v, const scdbm_mat* vmodel,
@@ -1776,9 +1905,8 @@ int32_t scdbm_rbm_train_epoch(scdbm_trainer* t, const scdbm_mat* x, const int32_
     API_END
 }
 
-int32_t scdbm_dbm_pcd_step(scdbm_model* m, const scdbm_mat* x, scdbm_particles* p, scdbm_particles* mu, scdbm_opt* o,
-                           double lr, int32_t nsteps, double eps, int32_t* mf_iters) {
-    API_BEGIN
+static void dbm_pcd_step_impl(scdbm_model* m, const scdbm_mat* x, scdbm_particles* p, scdbm_particles* mu, scdbm_opt* o, double lr,
+                              int32_t nsteps, double eps, int64_t global_npos, int64_t global_nneg, int32_t* mf_iters) {
     REQUIRE(m && x && p && mu && o, "NULL argument");
     REQUIRE(p->model == m && mu->model == m && o->model == m, "objects belong to different models");
     REQUIRE(m->L.size() >= 2, "traindbm! needs at least two RBM layers");
@@ -1786,13 +1914,98 @@ int32_t scdbm_dbm_pcd_step(scdbm_model* m, const scdbm_mat* x, scdbm_particles* 
     int it = 0;
     meanfield_impl(m, x, eps, 0, mu, &it, nullptr);            // :291
     if (mf_iters) *mf_iters = it;
-    const float ps = 1.0f / (float)std::max<int64_t>(mu->n, 1), ns = 1.0f / (float)std::max<int64_t>(p->n, 1);
-    for (int l = 0; l < (int)m->L.size(); ++l) {               // :293
-        const MatView& v = l == 0 ? mu->alias0->v : mu->cur[l]->v;
-        gradient_layer(o, l, v, p->cur[l]->v, mu->cur[l + 1]->v, p->cur[l + 1]->v, ps, ns);
-    }
+    const int64_t npos = global_npos > 0 ? global_npos : mu->n, nneg = global_nneg > 0 ? global_nneg : p->n;
+    gradient_dbm(o, m, mu, p, 1.0f / (float)std::max<int64_t>(npos, 1), 1.0f / (float)std::max<int64_t>(nneg, 1));   // :293
     for (int l = 0; l < (int)m->L.size(); ++l) update_layer(m, o, l, (float)lr);  // :294
     refresh_operands(m);
+}
+
+int32_t scdbm_dbm_pcd_step(scdbm_model* m, const scdbm_mat* x, scdbm_particles* p, scdbm_particles* mu, scdbm_opt* o,
+                           double lr, int32_t nsteps, double eps, int32_t* mf_iters) {
+    API_BEGIN
+    REQUIRE(!m || !m->ctx->comm, "the context has a communicator: call scdbm_dbm_pcd_step_dp with the global sample counts");
+    dbm_pcd_step_impl(m, x, p, mu, o, lr, nsteps, eps, 0, 0, mf_iters);
+    API_END
+}
+
+int32_t scdbm_dbm_pcd_step_dp(scdbm_model* m, const scdbm_mat* x, scdbm_particles* p, scdbm_particles* mu, scdbm_opt* o,
+                              double lr, int32_t nsteps, double eps, int64_t global_nsamples, int64_t global_nparticles,
+                              int32_t* mf_iters) {
+    API_BEGIN
+    REQUIRE(global_nsamples > 0 && global_nparticles > 0, "global sample / particle counts must be positive");
+    dbm_pcd_step_impl(m, x, p, mu, o, lr, nsteps, eps, global_nsamples, global_nparticles, mf_iters);
+    API_END
+}
+
+// ------------------------------------------------------------ communicator
+int32_t scdbm_comm_unique_id(uint8_t* id128) {
+    API_BEGIN
+    REQUIRE(id128, "NULL argument");
+    std::string err;
+    if (!nccl_api().load(err)) throw Err(SCDBM_EUNSUP, err);
+    ncclUniqueId id;
+    nccl_check(nccl_api().GetUniqueId(&id), "ncclGetUniqueId");
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    API_END
+}
+
+int32_t scdbm_comm_init(scdbm_ctx* c, const uint8_t* id128, int32_t rank, int32_t nranks) {
+    API_BEGIN
+    REQUIRE(c && id128, "NULL argument");
+    REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "rank must be in [0, nranks)");
+    REQUIRE(!c->comm, "the context already has a communicator");
+    std::string err;
+    if (!nccl_api().load(err)) throw Err(SCDBM_EUNSUP, err);
+    CK(cudaSetDevice(c->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    nccl_check(nccl_api().CommInitRank(&c->comm, nranks, id, rank), "ncclCommInitRank");
+    c->rank = rank;
+    c->nranks = nranks;
+    CK(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_grad, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+    if (!c->d_red) CK(cudaMalloc(&c->d_red, 64 * sizeof(double)));
+    API_END
+}
+
+int32_t scdbm_comm_destroy(scdbm_ctx* c) {
+    API_BEGIN
+    REQUIRE(c, "ctx is NULL");
+    if (c->comm) {
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaStreamSynchronize(c->comm_stream));
+        nccl_check(nccl_api().CommDestroy(c->comm), "ncclCommDestroy");
+        c->comm = nullptr;
+        cudaStreamDestroy(c->comm_stream);
+        cudaEventDestroy(c->ev_grad);
+        cudaEventDestroy(c->ev_comm);
+        c->comm_stream = nullptr;
+        c->rank = 0;
+        c->nranks = 1;
+    }
+    API_END
+}
+
+int32_t scdbm_allreduce_gradient(scdbm_opt* o) {
+    API_BEGIN
+    REQUIRE(o, "optimizer is NULL");
+    scdbm_ctx* c = o->model->ctx;
+    if (c->comm) nccl_check(nccl_api().AllReduce(o->buf, o->buf, (size_t)o->n, ncclFloat32, ncclSum, c->comm, c->stream), "ncclAllReduce(gradient)");
+    API_END
+}
+
+int32_t scdbm_comm_allreduce_f64(scdbm_ctx* c, double* values, int32_t n, int32_t op) {
+    API_BEGIN
+    REQUIRE(c && values, "NULL argument");
+    REQUIRE(n >= 0 && n <= 64, "at most 64 values");
+    REQUIRE(op == 0 || op == 1, "op must be 0 (sum) or 1 (max)");
+    if (!c->comm || n == 0) return SCDBM_OK;
+    CK(cudaMemcpyAsync(c->d_red, values, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    nccl_check(nccl_api().AllReduce(c->d_red, c->d_red, (size_t)n, ncclFloat64, op ? ncclMax : ncclSum, c->comm, c->stream), "ncclAllReduce(f64)");
+    CK(cudaMemcpyAsync(values, c->d_red, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     API_END
 }
 

@@ -69,6 +69,7 @@ struct EpiParams {
     MatView out;            // output state (not used by EPI_AIS_RATIO)
     MatView prev;           // mean-field: previous value of the same layer (p0 == nullptr: off)
     unsigned int* delta_bits; // mean-field: max |prev-new| as float bits (atomicMax)
+    const unsigned int* skip; // mean-field: device flag "the fixed point has converged" -- a set flag turns the launch into a no-op
     float t1, t2;           // AIS temperatures
     double* logw;           // AIS: per-row accumulator
     float* out_f32;         // EPI_RAW_F32 destination [M x ldo]

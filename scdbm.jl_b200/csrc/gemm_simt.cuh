@@ -20,6 +20,7 @@ __device__ __forceinline__ float operand_load(const Operand& o, int64_t mn, int6
 __global__ void __launch_bounds__(ST_THREADS) k_gemm_simt(const GemmArgs g) {
     __shared__ float As[ST_K][ST_M + 4];
     __shared__ float Bs[ST_K][ST_N + 4];
+    if (g.epi.skip && *g.epi.skip) return;   // speculatively launched mean-field iteration after convergence
     const int tid = threadIdx.x;
     const int tx = tid % 16, ty = tid / 16;  // thread computes rows ty*4.., cols tx*4..
     const int64_t m0 = (int64_t)blockIdx.y * ST_M, n0 = (int64_t)blockIdx.x * ST_N;

@@ -266,6 +266,9 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_holder;
+    if constexpr (EK == 0) {
+        if (p.epi.skip && *p.epi.skip) return;   // speculatively launched mean-field iteration after convergence (whole grid)
+    }
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     // Warp roles: epilogue warps are 0 .. EPW-1; the service warps sit ABOVE them (svc = warp - EPW: 0 TMA producer,
