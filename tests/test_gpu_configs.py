@@ -241,3 +241,42 @@ def test_c5_ais_slice(pkg, auto, c4):
     w2 = np.concatenate([pkg.aislogimpweights(m, temperatures=temps, nparticles=P // 2, burnin=burnin, ctx=auto),
                          pkg.aislogimpweights(m, temperatures=temps, nparticles=P // 2, burnin=burnin, row_offset=P // 2, ctx=auto)])
     assert np.allclose(w2, w, rtol=1e-10, atol=1e-10)
+
+
+# ------------------------------------------------------------ communicator (single rank: the NCCL path itself)
+def test_single_rank_communicator_matches_plain_step(pkg):
+    """A 1-rank NCCL communicator exercises every collective call of the data-parallel step (allreduce of the gradient
+    blocks on the second stream, allreduce(max) of the mean-field delta, scalar reductions); the result must equal
+    the plain step bit for bit.  (More ranks need more GPUs: `bench.py --gpus N` and tests/test_multi_gloo.py.)"""
+    units = [300, 128, 64]
+    dbm = synth.random_dbm(units, 5, wscale=(0.002, 0.02))
+    x, _, _ = synth.counts(500, units[0], seed=3)
+    res = []
+    for use_comm in (False, True):
+        c = pkg.Context(0, SEED)
+        if use_comm:
+            c.comm_init(pkg.Context.comm_unique_id(), 0, 1)
+            assert (c.comm_rank, c.comm_size) == (0, 1)
+            assert np.array_equal(c.allreduce([1.5, -2.0], "sum"), [1.5, -2.0])
+        m = pkg.DeviceModel.from_host(to_pkg_model(pkg, dbm), c)
+        xm = pkg.Mat.from_host(c, x, pkg.MAT_COUNT)
+        p = pkg.DeviceParticles(m, 64).init(False)
+        mu = pkg.DeviceParticles(m, 500, real_valued=True)
+        opt = pkg.LoglikelihoodOptimizer().initialized(m)
+        import ctypes as C
+        its = C.c_int32()
+        for _ in range(2):
+            if use_comm:
+                pkg._lib.check(pkg.lib().scdbm_dbm_pcd_step_dp(m.h, xm.h, p.h, mu.h, opt.h, 0.01, 5, 1e-3, 500, 64, C.byref(its)))
+            else:
+                pkg._lib.check(pkg.lib().scdbm_dbm_pcd_step(m.h, xm.h, p.h, mu.h, opt.h, 0.01, 5, 1e-3, C.byref(its)))
+        res.append(([m.get_layer(l).weights for l in range(2)], its.value))
+        if use_comm:
+            with pytest.raises(pkg.ScdbmError):          # the plain step refuses to run on a context with a communicator
+                pkg._lib.check(pkg.lib().scdbm_dbm_pcd_step(m.h, xm.h, p.h, mu.h, opt.h, 0.01, 5, 1e-3, None))
+            w = np.array([0.3, -1.0, 2.0])
+            assert abs(pkg.logmeanexp_sharded(w, c) - pkg.logmeanexp(w)) < 1e-12
+            c.comm_destroy()
+    assert res[0][1] == res[1][1]
+    for a, b in zip(res[0][0], res[1][0]):
+        assert np.array_equal(a, b)
