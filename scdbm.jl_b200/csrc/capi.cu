@@ -32,6 +32,13 @@ struct Err : std::runtime_error {
     do {                                            \
         if (!(cond)) throw Err(SCDBM_EINVAL, msg);  \
     } while (0)
+#define REQUIRE_OR_RETURN(cond)                     \
+    do {                                            \
+        if (!(cond)) {                              \
+            g_err = "NULL argument";                \
+            return SCDBM_EINVAL;                    \
+        }                                           \
+    } while (0)
 #define API_BEGIN try {
 #define API_END                          \
     return SCDBM_OK;                     \
@@ -192,6 +199,7 @@ struct scdbm_trainer {
     scdbm_opt* opt = nullptr;
     int32_t* d_perm = nullptr;
     int64_t perm_cap = 0;
+    uint32_t* d_anyhi = nullptr;   // does the data matrix of this epoch hold counts >= 2048 anywhere?
     bool track_mean = false;      // record `estimatedmean` (model means in minibatch order) each epoch
     scdbm_mat* est = nullptr;
 };
@@ -377,21 +385,23 @@ static void run_sweep(scdbm_ctx* ctx, const SweepSrc* srcs, int nsrc, int64_t M,
 struct DevUniforms {
     float* d = nullptr;
     int64_t ld = 0;
-    ~DevUniforms() { cudaFree(d); }
+    cudaStream_t st = nullptr;
+    ~DevUniforms() { if (d) cudaFreeAsync(d, st); }
 };
 static void upload_uniforms(scdbm_ctx* ctx, const double* u, int64_t ldu, int64_t rows, int64_t cols, DevUniforms& out) {
     if (!u) return;
     REQUIRE(ldu >= rows, "uniforms: leading dimension smaller than the row count");
     double* stage = nullptr;
     const size_t nb = (size_t)ldu * cols * sizeof(double);
-    CK(cudaMalloc(&stage, std::max<size_t>(nb, 8)));
+    out.st = ctx->stream;
+    CK(cudaMallocAsync(&stage, std::max<size_t>(nb, 8), ctx->stream));
     CK(cudaMemcpyAsync(stage, u, nb, cudaMemcpyHostToDevice, ctx->stream));
     out.ld = cols;
-    CK(cudaMalloc(&out.d, std::max<size_t>((size_t)rows * cols * sizeof(float), 8)));
+    CK(cudaMallocAsync(&out.d, std::max<size_t>((size_t)rows * cols * sizeof(float), 8), ctx->stream));
     k_upload_uniforms<<<grid1d(rows * cols), 256, 0, ctx->stream>>>(stage, ldu, out.d, rows, cols, out.ld);
     ctx->launches++;
-    CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(stage);
+    CK(cudaFreeAsync(stage, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // the caller's host buffer must not be retained
 }
 
 static void refresh_nbc(scdbm_ctx* ctx, Layer& L, unsigned int* invalid = nullptr) {
@@ -624,6 +634,7 @@ int32_t scdbm_model_create(scdbm_ctx* c, int32_t nrbms, const int32_t* units, in
     ctx_retain(c);
     CK(cudaMallocAsync(&m->d_scale, 2 * sizeof(float), c->stream));
     CK(cudaMallocAsync(&m->d_wmax, sizeof(unsigned int), c->stream));
+    CK(cudaMemsetAsync(m->d_wmax, 0, sizeof(unsigned int), c->stream));
     {
         const float one[2] = {1.0f, 1.0f};
         CK(cudaMemcpyAsync(m->d_scale, one, sizeof(one), cudaMemcpyHostToDevice, c->stream));
@@ -803,13 +814,13 @@ int32_t scdbm_model_init_layer(scdbm_model* m, int32_t l, const scdbm_mat* x, co
     refresh_operands(m);
     // column means -> visible bias on the host (V numbers)
     float* d_sum = nullptr;
-    CK(cudaMalloc(&d_sum, L.V * sizeof(float)));
+    CK(cudaMallocAsync(&d_sum, L.V * sizeof(float), c->stream));
     CK(cudaMemsetAsync(d_sum, 0, L.V * sizeof(float), c->stream));
     colsum(c, x->v, 1.0f, d_sum, false);
     std::vector<float> s(L.V);
     CK(cudaMemcpyAsync(s.data(), d_sum, L.V * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaFreeAsync(d_sum, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(d_sum);
     std::vector<double> a(L.V), rr(L.V, 0.5), b(L.H, 0.0);
     if (r) for (int i = 0; i < L.V; ++i) rr[i] = r[i];
     for (int i = 0; i < L.V; ++i) {
@@ -864,7 +875,7 @@ int32_t scdbm_mat_upload(scdbm_mat* m, const double* x, int64_t ld) {
     // column-block staging keeps the fp64 staging buffer small
     const int64_t colblk = std::max<int64_t>(32, std::min<int64_t>(m->v.cols, (int64_t)(256ll << 20) / (8 * std::max<int64_t>(ld, 1)) / 32 * 32));
     double* stage = nullptr;
-    CK(cudaMalloc(&stage, (size_t)ld * colblk * sizeof(double)));
+    CK(cudaMallocAsync(&stage, (size_t)ld * colblk * sizeof(double), c->stream));
     for (int64_t c0 = 0; c0 < m->v.cols; c0 += colblk) {
         const int64_t nc = std::min(colblk, m->v.cols - c0);
         CK(cudaMemcpyAsync(stage, x + c0 * ld, (size_t)ld * nc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -880,7 +891,7 @@ int32_t scdbm_mat_upload(scdbm_mat* m, const double* x, int64_t ld) {
         c->launches++;
         CK(cudaStreamSynchronize(c->stream));
     }
-    cudaFree(stage);
+    cudaFreeAsync(stage, c->stream);
     API_END
 }
 
@@ -892,7 +903,7 @@ int32_t scdbm_mat_download(const scdbm_mat* m, double* x, int64_t ld) {
     scdbm_ctx* c = m->ctx;
     const int64_t colblk = std::max<int64_t>(32, std::min<int64_t>(m->v.cols, (int64_t)(256ll << 20) / (8 * std::max<int64_t>(ld, 1)) / 32 * 32));
     double* stage = nullptr;
-    CK(cudaMalloc(&stage, (size_t)ld * colblk * sizeof(double)));
+    CK(cudaMallocAsync(&stage, (size_t)ld * colblk * sizeof(double), c->stream));
     CK(cudaMemsetAsync(stage, 0, (size_t)ld * colblk * sizeof(double), c->stream));
     for (int64_t c0 = 0; c0 < m->v.cols; c0 += colblk) {
         const int64_t nc = std::min(colblk, m->v.cols - c0);
@@ -913,60 +924,20 @@ int32_t scdbm_mat_download(const scdbm_mat* m, double* x, int64_t ld) {
         }
         CK(cudaStreamSynchronize(c->stream));
     }
-    cudaFree(stage);
+    cudaFreeAsync(stage, c->stream);
     API_END
 }
 
+int32_t scdbm_mat_download_u16_async(const scdbm_mat* m, uint16_t* x);
+int32_t scdbm_wait_downloads(scdbm_ctx* ctx);
+
+// synchronous form: the asynchronous snapshot + copy-engine drain below (context-owned stream, events and snapshot
+// buffer: nothing is created or allocated per call once the buffer has grown), then wait
 int32_t scdbm_mat_download_u16(const scdbm_mat* m, uint16_t* x) {
-    API_BEGIN
-    REQUIRE(m && x, "NULL argument");
-    const int64_t n = m->v.rows * m->v.cols;
-    if (n == 0) return SCDBM_OK;
-    scdbm_ctx* c = m->ctx;
-    // chunked and double-buffered: the plane -> uint16 conversion of chunk i+1 (context stream) overlaps the
-    // device -> host copy of chunk i (copy stream).  Pinned host memory gives full PCIe bandwidth.
-    // whole 128-row tiles per chunk: the hi-plane flags are per row tile
-    const int64_t chunk_rows = std::max<int64_t>(128, (int64_t)(64ll << 20) / std::max<int64_t>(2 * m->v.cols, 1) / 128 * 128);
-    uint16_t* stage[2] = {nullptr, nullptr};
-    cudaStream_t cs = nullptr;
-    cudaEvent_t ek[2] = {nullptr, nullptr}, ec[2] = {nullptr, nullptr};
-    auto cleanup = [&]() {
-        for (int i = 0; i < 2; ++i) { cudaFree(stage[i]); if (ek[i]) cudaEventDestroy(ek[i]); if (ec[i]) cudaEventDestroy(ec[i]); }
-        if (cs) cudaStreamDestroy(cs);
-    };
-    try {
-        CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            CK(cudaMalloc(&stage[i], (size_t)chunk_rows * m->v.cols * sizeof(uint16_t)));
-            CK(cudaEventCreateWithFlags(&ek[i], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&ec[i], cudaEventDisableTiming));
-        }
-        int b = 0;
-        for (int64_t r0 = 0; r0 < m->v.rows; r0 += chunk_rows, b ^= 1) {
-            const int64_t nr = std::min(chunk_rows, m->v.rows - r0);
-            MatView sub = m->v;
-            sub.p0 += r0 * sub.ld;
-            if (sub.p1) sub.p1 += r0 * sub.ld;
-            if (sub.f) sub.f += r0 * sub.ld;
-            if (sub.hiflag) sub.hiflag += r0 / 128;
-            sub.rows = nr;
-            if (r0 >= 2 * chunk_rows) CK(cudaStreamWaitEvent(c->stream, ec[b], 0));   // staging buffer free again
-            k_download_u16<<<(unsigned)((nr + 7) / 8), dim3(32, 8), 0, c->stream>>>(sub, stage[b]);
-            CK(cudaGetLastError());
-            c->launches++;
-            CK(cudaEventRecord(ek[b], c->stream));
-            CK(cudaStreamWaitEvent(cs, ek[b], 0));
-            CK(cudaMemcpyAsync(x + r0 * m->v.cols, stage[b], (size_t)nr * m->v.cols * sizeof(uint16_t), cudaMemcpyDeviceToHost, cs));
-            CK(cudaEventRecord(ec[b], cs));
-        }
-        CK(cudaStreamSynchronize(cs));
-        CK(cudaStreamSynchronize(c->stream));
-    } catch (...) {
-        cleanup();
-        throw;
-    }
-    cleanup();
-    API_END
+    REQUIRE_OR_RETURN(m && x);
+    const int32_t st = scdbm_mat_download_u16_async(m, x);
+    if (st != SCDBM_OK) return st;
+    return scdbm_wait_downloads(m->ctx);
 }
 
 int32_t scdbm_mat_download_u16_async(const scdbm_mat* m, uint16_t* x) {
@@ -1039,12 +1010,13 @@ int32_t scdbm_mat_upload_compressed(scdbm_mat* m, int32_t major, const int64_t* 
     int32_t* d_idx = nullptr;
     float* d_val = nullptr;
     unsigned int* d_err = nullptr;
-    auto cleanup = [&]() { cudaFree(d_ptr); cudaFree(d_idx); cudaFree(d_val); cudaFree(d_err); };
+    cudaStream_t st = c->stream;
+    auto cleanup = [&]() { for (void* q : {(void*)d_ptr, (void*)d_idx, (void*)d_val, (void*)d_err}) if (q) cudaFreeAsync(q, st); };
     try {
-        CK(cudaMalloc(&d_ptr, (size_t)(nmajor + 1) * sizeof(int64_t)));
-        CK(cudaMalloc(&d_idx, (size_t)nnz * sizeof(int32_t)));
-        CK(cudaMalloc(&d_val, (size_t)nnz * sizeof(float)));
-        CK(cudaMalloc(&d_err, sizeof(unsigned int)));
+        CK(cudaMallocAsync(&d_ptr, (size_t)(nmajor + 1) * sizeof(int64_t), st));
+        CK(cudaMallocAsync(&d_idx, (size_t)nnz * sizeof(int32_t), st));
+        CK(cudaMallocAsync(&d_val, (size_t)nnz * sizeof(float), st));
+        CK(cudaMallocAsync(&d_err, sizeof(unsigned int), st));
         CK(cudaMemsetAsync(d_err, 0, sizeof(unsigned int), c->stream));
         CK(cudaMemcpyAsync(d_ptr, ptr, (size_t)(nmajor + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemcpyAsync(d_idx, idx, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
@@ -1176,15 +1148,15 @@ int32_t scdbm_mat_column_stats(const scdbm_mat* m, double* mean, double* var, do
     REQUIRE(R > 0 && C > 0, "matrix is empty");
     scdbm_ctx* c = m->ctx;
     double* d = nullptr;
-    CK(cudaMalloc(&d, 3 * C * sizeof(double)));
+    CK(cudaMallocAsync(&d, 3 * C * sizeof(double), c->stream));
     CK(cudaMemsetAsync(d, 0, 3 * C * sizeof(double), c->stream));
     dim3 grid((unsigned)((C + 31) / 32), (unsigned)std::min<int64_t>((R + 7) / 8, 256)), block(32, 8);
     k_colstats<<<grid, block, 0, c->stream>>>(m->v, d, d + C, d + 2 * C);
     c->launches++;
     std::vector<double> h(3 * C);
     CK(cudaMemcpyAsync(h.data(), d, 3 * C * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaFreeAsync(d, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(d);
     for (int64_t j = 0; j < C; ++j) {
         const double mu = h[j] / R;
         if (mean) mean[j] = mu;
@@ -1643,6 +1615,12 @@ static void gradient_biases(scdbm_opt* o, int l, const MatView& v, const MatView
     Layer& L = m->L[l];
     float* ga = o->buf + o->offA[l];
     float* gb = o->buf + o->offB[l];
+    if (std::max(v.rows, vm.rows) <= 2048) {
+        k_bias_grad<<<(unsigned)((L.V + L.H + 31) / 32), dim3(32, 8), 0, c->stream>>>(v, vm, h, hm, pos_scale, neg_scale, ga, gb);
+        CK(cudaGetLastError());
+        c->launches++;
+        return;
+    }
     CK(cudaMemsetAsync(ga, 0, (size_t)(L.V + L.H) * sizeof(float), c->stream));  // offA and offB are adjacent
     colsum(c, v, pos_scale, ga, true);
     colsum(c, vm, -neg_scale, ga, true);
@@ -1736,14 +1714,31 @@ static void update_layer(scdbm_model* m, scdbm_opt* o, int l, float lr) {
     refresh_nbc(c, L);   // (weight planes: refresh_operands(m) once after all layers are updated)
 }
 
+// K6: update of ALL layers of the model, one fused kernel per layer (parameters, clamps, fp16 operand planes in both
+// orientations, NB sampling constants) after a one-thread kernel that fixes the round's weight scale
+static void update_all_layers(scdbm_model* m, scdbm_opt* o, float lr) {
+    scdbm_ctx* c = m->ctx;
+    k_weight_scale_next<<<1, 1, 0, c->stream>>>(m->d_wmax, m->d_scale);
+    for (int l = 0; l < (int)m->L.size(); ++l) {
+        Layer& L = m->L[l];
+        const bool nb = L.kind == SCDBM_VIS_NEGBIN;
+        dim3 grid((L.V + 31) / 32, (L.H + 31) / 32), block(32, 8);
+        k_update_layer<<<grid, block, 0, c->stream>>>(L.W, L.a, L.b, L.r, o->buf + o->offW[l], o->buf + o->offA[l], o->buf + o->offB[l], L.V, L.H,
+                                                     lr, nb ? 1 : 0, m->d_scale, L.w0, L.w1, L.ldh, L.t0, L.t1, L.ldv, m->d_wmax, c->mu_inv_max,
+                                                     L.nbc, L.nbT);
+        if (nb) L.nbL_mu = c->mu_inv_max;
+    }
+    CK(cudaGetLastError());
+    c->launches += 1 + (int64_t)m->L.size();
+}
+
 int32_t scdbm_update_parameters(scdbm_model* m, scdbm_opt* o, int32_t l, double lr) {
     API_BEGIN
     REQUIRE(m && o, "NULL argument");
     REQUIRE(o->model == m, "optimizer belongs to a different model");
     REQUIRE(l < (int)m->L.size(), "layer index out of range");
-    if (l >= 0) update_layer(m, o, l, (float)lr);
-    else for (int i = 0; i < (int)m->L.size(); ++i) update_layer(m, o, i, (float)lr);
-    refresh_operands(m);
+    if (l < 0 || m->L.size() == 1) update_all_layers(m, o, (float)lr);
+    else { update_layer(m, o, l, (float)lr); refresh_operands(m); }    // one layer of a stack: the shared scale needs the full refresh
     API_END
 }
 
@@ -1813,6 +1808,7 @@ int32_t scdbm_trainer_destroy(scdbm_trainer* t) {
     mat_free(t->est);
     scdbm_opt_destroy(t->opt);
     cudaFree(t->d_perm);
+    cudaFree(t->d_anyhi);
     scdbm_model* tm = t->model;
     delete t;
     model_release(tm);
@@ -1855,6 +1851,11 @@ int32_t scdbm_rbm_train_epoch(scdbm_trainer* t, const scdbm_mat* x, const int32_
         t->perm_cap = n;
     }
     CK(cudaMemcpyAsync(t->d_perm, perm, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    if (x->v.hiflag) {   // once per epoch: minibatches gathered from data without large counts skip the hi count plane
+        if (!t->d_anyhi) CK(cudaMalloc(&t->d_anyhi, sizeof(uint32_t)));
+        k_any_flag<<<1, 256, 0, c->stream>>>(x->v.hiflag, (n + 127) / 128, t->d_anyhi);
+        c->launches++;
+    }
     if (t->track_mean && (!t->est || t->est->v.rows != n)) {
         mat_free(t->est);
         t->est = nullptr;
@@ -1865,8 +1866,7 @@ int32_t scdbm_rbm_train_epoch(scdbm_trainer* t, const scdbm_mat* x, const int32_
         const int64_t thisb = std::min<int64_t>(B, n - s);
         const int64_t mrows = t->pcd ? B : thisb;  // PCD keeps the full chain (rbmtraining.jl:548-553)
         MatView v = rows_view(t->v->v, thisb), h = rows_view(t->h->v, thisb);
-        set_hiflags(c, v, true);
-        k_gather_rows<<<(unsigned)thisb, 128, 0, c->stream>>>(x->v, t->d_perm + s, v);
+        k_gather_rows<<<(unsigned)thisb, 128, 0, c->stream>>>(x->v, t->d_perm + s, v, x->v.hiflag ? t->d_anyhi : nullptr);   // sets the hi-plane flags of v
         c->launches++;
         DrawCfg d;
         op_hidden(m, t->l, v, h, up, SCDBM_OUT_POTENTIAL, d);                         // :556
@@ -1898,8 +1898,8 @@ int32_t scdbm_rbm_train_epoch(scdbm_trainer* t, const scdbm_mat* x, const int32_
         MatView hm = t->pcd ? t->chain->v : rows_view(t->hm->v, mrows);
         op_hidden(m, t->l, vm, hm, up, SCDBM_OUT_POTENTIAL, d);                        // :578
         gradient_layer(t->opt, t->l, v, rows_view(vm, thisb), h, rows_view(hm, thisb), 1.0f / (float)thisb, 1.0f / (float)thisb);
-        update_layer(m, t->opt, t->l, (float)lr);                                      // :586-587
-        refresh_operands(m);
+        if (m->L.size() == 1) update_all_layers(m, t->opt, (float)lr);                 // :586-587
+        else { update_layer(m, t->opt, t->l, (float)lr); refresh_operands(m); }
     }
     CK(cudaGetLastError());
     API_END
@@ -1916,8 +1916,7 @@ static void dbm_pcd_step_impl(scdbm_model* m, const scdbm_mat* x, scdbm_particle
     if (mf_iters) *mf_iters = it;
     const int64_t npos = global_npos > 0 ? global_npos : mu->n, nneg = global_nneg > 0 ? global_nneg : p->n;
     gradient_dbm(o, m, mu, p, 1.0f / (float)std::max<int64_t>(npos, 1), 1.0f / (float)std::max<int64_t>(nneg, 1));   // :293
-    for (int l = 0; l < (int)m->L.size(); ++l) update_layer(m, o, l, (float)lr);  // :294
-    refresh_operands(m);
+    update_all_layers(m, o, (float)lr);                                            // :294
 }
 
 int32_t scdbm_dbm_pcd_step(scdbm_model* m, const scdbm_mat* x, scdbm_particles* p, scdbm_particles* mu, scdbm_opt* o,
@@ -2031,12 +2030,12 @@ int32_t scdbm_mle_theta(const scdbm_mat* x, const scdbm_mat* mu, double lambda, 
     REQUIRE(x->v.rows > 0 && x->v.cols > 0 && maxiter >= 0, "empty input");
     scdbm_ctx* c = x->ctx;
     double* d = nullptr;
-    CK(cudaMalloc(&d, x->v.cols * sizeof(double)));
+    CK(cudaMallocAsync(&d, x->v.cols * sizeof(double), c->stream));
     k_mle_theta<<<(unsigned)x->v.cols, 256, 0, c->stream>>>(x->v, mu->v, lambda, maxiter, convtol, d);
     c->launches++;
     cudaError_t e = cudaMemcpyAsync(theta, d, x->v.cols * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    cudaFreeAsync(d, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(d);
     CK(e);
     API_END
 }
@@ -2052,15 +2051,14 @@ int32_t scdbm_sample_dropout(scdbm_mat* v, const scdbm_mat* x, const double* mid
     std::vector<float> h(2 * nparams);
     for (int i = 0; i < nparams; ++i) { h[i] = (float)mid[i]; h[nparams + i] = (float)shape[i]; }
     float* d = nullptr;
-    CK(cudaMalloc(&d, h.size() * sizeof(float)));
+    CK(cudaMallocAsync(&d, h.size() * sizeof(float), c->stream));
     CK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     DrawAddr da{(uint32_t)c->seed, (uint32_t)(c->seed >> 32), tick, stream_id(0, P_DROPOUT), (uint32_t)row_offset, nullptr, 0};
     set_hiflags(c, v->v, true);
     k_dropout<<<grid1d(v->v.rows * ((v->v.cols + 3) / 4)), 256, 0, c->stream>>>(v->v, x->v, d, d + nparams, nparams, log1p_form, da);
     c->launches++;
-    cudaError_t e = cudaStreamSynchronize(c->stream);
-    cudaFree(d);
-    CK(e);
+    cudaFreeAsync(d, c->stream);
+    CK(cudaStreamSynchronize(c->stream));   // `h` goes out of scope
     API_END
 }
 
@@ -2160,7 +2158,7 @@ int32_t scdbm_ais_run(scdbm_model* m, const double* temps, int32_t ntemps, int64
     REQUIRE(n > 0 && burnin >= 0, "nparticles must be positive, burnin non-negative");
     scdbm_ctx* c = m->ctx;
     double* d_logw = nullptr;
-    CK(cudaMalloc(&d_logw, n * sizeof(double)));
+    CK(cudaMallocAsync(&d_logw, n * sizeof(double), c->stream));
     CK(cudaMemsetAsync(d_logw, 0, n * sizeof(double), c->stream));
     scdbm_particles* p = nullptr;
     if (scdbm_particles_create(m, n, row_offset, 0, &p) != SCDBM_OK) throw Err(SCDBM_ENOMEM, g_err);
@@ -2202,11 +2200,11 @@ int32_t scdbm_ais_run(scdbm_model* m, const double* temps, int32_t ntemps, int64
         CK(cudaStreamSynchronize(c->stream));
     } catch (...) {
         scdbm_particles_destroy(p);
-        cudaFree(d_logw);
+        cudaFreeAsync(d_logw, c->stream);
         throw;
     }
     scdbm_particles_destroy(p);
-    cudaFree(d_logw);
+    cudaFreeAsync(d_logw, c->stream);
     API_END
 }
 

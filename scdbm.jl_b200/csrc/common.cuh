@@ -52,6 +52,9 @@ struct EpiParams {
     const float* bias1;     // second per-column bias (DBM intermediate layers; nullable)
     const float* addend;    // optional fp32 [rows x ld_add] added to the pre-activation
     int64_t ld_add;         //   (mean-field: the hoisted x*W1)
+    int32_t addend_splits;  // > 1: the addend is the sum of this many slabs, addend_stride elements apart (split-K partial sums)
+    int32_t addend_scaled;  // 1: the addend stands for the contraction itself (split-K): wscale multiplies it, as it would the accumulator
+    int64_t addend_stride;
     float factor;           // multiplies (wscale*acc + biases): up/down factor
     float wscale;           // multiplies acc only: AIS temperature (weights-only annealing)
     const float* acc_scale; // tensor-core engine: device scalar 1/s undoing the power-of-two scale s of the fp16 weight planes

@@ -150,6 +150,116 @@ __global__ void k_update(float* __restrict__ theta, const float* __restrict__ gr
     }
 }
 
+// ---- K6: the whole parameter update of one RBM layer in one pass (src/optimizers.jl:478-485,513-520):
+//   W += lr dW (NB: W = min(W, 0)),  a += lr da (NB: a = min(a, -1e-10)),  b += lr db,
+// and, from the updated values still in registers, every derived operand the sweeps read: the fp16 hi/lo planes of s W in
+// both orientations (32 x 32 shared-memory transpose tile) and, for an NB layer, the per-gene sampling constants and
+// pass-A thresholds (W <= 0 after the clamp, so the zero-probability bound depends on a and r only).  The block also
+// folds max |W| into `wmax` for the next round's scale.  HBM traffic: 8 B read + 12 B written per weight.
+// grad: the layer's block {dW [V x H] row-major, da [V], db [H]}.
+__global__ void k_update_layer(float* __restrict__ W, float* __restrict__ a, float* __restrict__ b, const float* __restrict__ r,
+                               const float* __restrict__ gW, const float* __restrict__ ga, const float* __restrict__ gb, int V, int H,
+                               float lr, int nb, const float* __restrict__ scale, __nv_bfloat16* w0, __nv_bfloat16* w1, int64_t ldh,
+                               __nv_bfloat16* t0, __nv_bfloat16* t1, int64_t ldv, unsigned int* __restrict__ wmax, float mu_inv_max,
+                               float4* __restrict__ nbc, uint32_t* __restrict__ nbT) {
+    __shared__ float t[32][33];
+    __shared__ float red[8];
+    const float s = scale[0];
+    const int v0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
+    float m = 0.0f;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int v = v0 + j, h = h0 + threadIdx.x;
+        float x = 0.0f;
+        if (v < V && h < H) {
+            const int64_t i = (int64_t)v * H + h;
+            float w = fmaf(lr, gW[i], W[i]);
+            if (nb) w = fminf(w, 0.0f);
+            W[i] = w;
+            m = fmaxf(m, fabsf(w));
+            x = s * w;
+            const __nv_bfloat16 hi = plane_encode(x);
+            w0[(int64_t)v * ldh + h] = hi;
+            w1[(int64_t)v * ldh + h] = plane_encode(x - plane_decode(hi));
+        }
+        t[j][threadIdx.x] = x;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int h = h0 + j, v = v0 + threadIdx.x;
+        if (v < V && h < H) {
+            const float x = t[threadIdx.x][j];
+            const __nv_bfloat16 hi = plane_encode(x);
+            t0[(int64_t)h * ldv + v] = hi;
+            t1[(int64_t)h * ldv + v] = plane_encode(x - plane_decode(hi));
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (threadIdx.x == 0) red[threadIdx.y] = m;
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        for (int j = 1; j < (int)blockDim.y; ++j) m = fmaxf(m, red[j]);
+        if (m > 0.0f) atomicMax(wmax, __float_as_uint(m));
+    }
+    // biases: one column / row of blocks each
+    if (blockIdx.y == 0 && threadIdx.y == 0) {
+        const int v = v0 + threadIdx.x;
+        if (v < V) {
+            float av = fmaf(lr, ga[v], a[v]);
+            if (nb) av = fminf(av, -1e-10f);
+            a[v] = av;
+            if (nb && nbc) {      // as k_refresh_nbc with sum_h max(W, 0) = 0
+                const float rr = r[v], c = 1e-6f / rr;
+                nbc[v] = make_float4(av, rr, c, rr - 1.0f);
+                const float om = -expm1f(av);
+                const float p = om / (1.0f + c * om) - 1e-6f;
+                const float mu_max = rr * expf(av) / om + 1e-6f;
+                float L = 0.0f;
+                if (p > 0.0f && mu_max < 0.99f * mu_inv_max) L = expf(rr * logf(p)) * (1.0f - 2e-5f);
+                const double mt = ceil(((double)L * 16777216.0 - 1.0) * 0.5);
+                nbT[v] = mt >= 8388608.0 ? 0xFFFFFFFFu : (mt <= 0.0 ? 0u : ((uint32_t)mt << 9));
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.y == 1) {
+        const int h = h0 + threadIdx.x;
+        if (h < H) b[h] = fmaf(lr, gb[h], b[h]);
+    }
+}
+// scale of the coming update round from the max |W| the previous round left behind (one thread); resets the running max
+__global__ void k_weight_scale_next(unsigned int* __restrict__ max_bits, float* __restrict__ scale) {
+    const float m = __uint_as_float(*max_bits);
+    int e = 0;
+    if (m > 0.0f && isfinite(m)) e = 10 - (int)ceilf(log2f(m));      // |s W| <= 2^10
+    e = max(-20, min(20, e));
+    scale[0] = exp2f((float)e);
+    scale[1] = exp2f((float)-e);
+    *max_bits = 0u;
+}
+
+// ---- bias gradients of one RBM in one launch (small batches; the two-pass column sums below serve large ones):
+//   da[c] = ps sum_rows v - ns sum_rows vm   (c < V),   db[c - V] = ps sum_rows h - ns sum_rows hm.   Deterministic.
+__global__ void k_bias_grad(MatView v, MatView vm, MatView h, MatView hm, float ps, float ns, float* __restrict__ da, float* __restrict__ db) {
+    __shared__ float red[8][33];
+    const int64_t V = v.cols, H = h.cols;
+    const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    const bool vis = c < V;
+    const MatView& P = vis ? v : h;
+    const MatView& N = vis ? vm : hm;
+    const int64_t cc = vis ? c : c - V;
+    float sp = 0.0f, sn = 0.0f;
+    if (c < V + H) {
+        for (int64_t r = threadIdx.y; r < P.rows; r += 8) sp += mat_load(P, r, cc);
+        for (int64_t r = threadIdx.y; r < N.rows; r += 8) sn += mat_load(N, r, cc);
+    }
+    red[threadIdx.y][threadIdx.x] = ps * sp - ns * sn;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < V + H) {
+        float tot = 0.0f;
+        for (int j = 0; j < 8; ++j) tot += red[j][threadIdx.x];
+        (vis ? da : db)[cc] = tot;
+    }
+}
+
 // ---- column sums of a state matrix, deterministic (no float atomics):
 // pass 1: partial[slab][c] = sum over the slab's rows; pass 2: out[c] (+)= scale * sum_slabs (fixed order)
 __global__ void k_colsum_partial(MatView m, float* __restrict__ partial) {
@@ -222,9 +332,18 @@ __global__ void k_fill_f32(float* p, int64_t n, float v) {
 }
 
 // ---- row gather: dst[i, :] = src[idx[i], :]   (minibatch, src/rbmtraining.jl:544)
-__global__ void k_gather_rows(MatView src, const int32_t* __restrict__ idx, MatView dst) {
+// does any row tile of a COUNT matrix use its hi plane?  (one block; out = 3 or 0, the value k_gather_rows gives its tiles)
+__global__ void k_any_flag(const uint32_t* __restrict__ flags, int64_t n, uint32_t* __restrict__ out) {
+    uint32_t any = 0u;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) any |= flags[i];
+    any = __syncthreads_or((int)(any & 1u));
+    if (threadIdx.x == 0) *out = any ? 3u : 0u;
+}
+// any_hi: device word written by k_any_flag for `src` (nullptr: assume counts >= 2048 may occur)
+__global__ void k_gather_rows(MatView src, const int32_t* __restrict__ idx, MatView dst, const uint32_t* __restrict__ any_hi) {
     const int64_t r = blockIdx.x;
     const int64_t s = idx[r];
+    if (dst.hiflag && threadIdx.x == 0 && (r & 127) == 0) dst.hiflag[r >> 7] = any_hi ? *any_hi : 3u;
     for (int64_t c = threadIdx.x; c < dst.ld; c += blockDim.x) {
         dst.p0[r * dst.ld + c] = src.p0[s * src.ld + c];
         if (dst.p1) dst.p1[r * dst.ld + c] = src.p1 ? src.p1[s * src.ld + c] : __ushort_as_bfloat16(0);

@@ -75,7 +75,11 @@ __device__ __forceinline__ float epi_apply4(const EpiParams& e, int64_t row, int
             if (e.bias0) b += e.bias0[col0 + j];
             if (e.bias1) b += e.bias1[col0 + j];
         }
-        if (e.addend && j < nvalid) b += e.addend[row * e.ld_add + col0 + j];
+        if (e.addend && j < nvalid) {
+            float t = e.addend[row * e.ld_add + col0 + j];
+            for (int sp = 1; sp < e.addend_splits; ++sp) t += e.addend[(int64_t)sp * e.addend_stride + row * e.ld_add + col0 + j];   // split-K slabs, fixed order
+            b += e.addend_scaled ? t * e.wscale : t;
+        }
         x[j] = e.factor * (e.wscale * acc[j] + b);
     }
     if (e.mode == EPI_AIS_RATIO) {

@@ -16,6 +16,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <unordered_map>
+
 #include "epilogue.cuh"
 
 namespace scdbm {
@@ -24,9 +26,28 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// cuTensorMapEncodeTiled costs a few microseconds on the host; the latency-bound training loops (BASELINE config C1:
+// ~30 descriptors per minibatch) re-use the same weight planes and minibatch buffers, so descriptors are cached by
+// everything they depend on (address, extents, row pitch, box).  A descriptor is a pure function of that key.
+struct TcMapKey {
+    const void* ptr;
+    int64_t rows, cols, ld;
+    int32_t box_rows, box_cols;
+    bool operator==(const TcMapKey& o) const {
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols;
+    }
+};
+struct TcMapKeyHash {
+    size_t operator()(const TcMapKey& k) const {
+        uint64_t h = (uint64_t)(uintptr_t)k.ptr * 0x9E3779B97F4A7C15ull;
+        h ^= (uint64_t)k.rows * 0xC2B2AE3D27D4EB4Full + ((uint64_t)k.cols << 17) + ((uint64_t)k.ld << 41) + ((uint64_t)k.box_rows << 7) + (uint64_t)k.box_cols;
+        return (size_t)(h ^ (h >> 29));
+    }
+};
 struct TcContext {
     PFN_tmapEncodeTiled encode = nullptr;
     bool attr_set[9] = {};
+    std::unordered_map<TcMapKey, CUtensorMap, TcMapKeyHash> maps;
 };
 
 struct TcOperandPlanes {
@@ -83,6 +104,8 @@ struct TcParams {
     int32_t pair;         // 1: a work tile is 256 rows = two M=128 MMA tiles sharing every B (weight) tile load:
                           //    a third less L2 -> shared-memory operand traffic (the up-sweep is L2-bandwidth-bound)
     const uint32_t* a_hiflag[2];   // per source: COUNT operand's per-row-tile "hi plane in use" flags (nullptr: always)
+    int32_t ksplit;       // > 1: split-K for latency-bound shapes with few tiles -- work item = (tile, split); each split contracts
+                          //      a slice of the k-blocks and stores raw fp32 partial sums (EPI_RAW_F32) into its own slab
     int32_t sched;        // 1: a CTA owns whole m-tiles and walks all n-tiles (balanced over genes, A re-used
                           //    back-to-back); 0: flat round-robin over (m, n) tiles, n fastest (few m-tiles)
     EpiParams epi;
@@ -126,6 +149,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // try_wait carries a suspend-time hint, so the hardware parks the warp until the phase completes instead of the warp
 // re-polling -- with the default time limit the 28 epilogue warps of the NB kernel spent 13 % of the SM's issue
 // slots on ~57 polls per tile (ncu capture prof_r02a).
+#ifndef SCDBM_PARK_NS
+#define SCDBM_PARK_NS 20000
+#endif
 __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     uint32_t spins = 0;
@@ -135,7 +161,7 @@ __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) 
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity), "r"(20000u)
+            : "r"(bar), "r"(parity), "r"((uint32_t)SCDBM_PARK_NS)
             : "memory");
         if (done) break;
         if (++spins > (1u << 22)) __trap();   // never hang the GPU: a protocol bug becomes a launch error
@@ -215,7 +241,16 @@ __device__ __forceinline__ int tc_tile(const TcParams& p, int it) {
         return m < p.m_tiles ? m * p.n_tiles + it % p.n_tiles : -1;
     }
     const int t = (int)blockIdx.x + it * (int)gridDim.x;
-    return t < p.m_tiles * p.n_tiles ? t : -1;
+    return t < p.m_tiles * p.n_tiles * max(p.ksplit, 1) ? t : -1;     // split-K: t is a work item, see tc_split_range
+}
+
+// split-K: work item id -> (tile, split) and the split's range of the tile's flattened k-block sequence
+__device__ __forceinline__ void tc_split_range(const TcParams& p, int work, int tkb, int& tile, int& lo, int& hi) {
+    if (p.ksplit <= 1) { tile = work; lo = 0; hi = tkb; return; }
+    tile = work / p.ksplit;
+    const int sp = work % p.ksplit;
+    lo = (int)((int64_t)tkb * sp / p.ksplit);
+    hi = (int)((int64_t)tkb * (sp + 1) / p.ksplit);
 }
 
 // hi count plane needed for work tile m_blk of source s?  (pair: either 128-row half flagged)
@@ -304,10 +339,13 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
             // ===================== TMA producer
             int stage = 0;
             uint32_t phase = 0;
-            for (int it = 0, tile; (tile = tc_tile(p, it)) >= 0; ++it) {
+            for (int it = 0, work; (work = tc_tile(p, it)) >= 0; ++it) {
                 const int rows = p.pair ? 2 * TC_BM : TC_BM;
                 const uint32_t a_bytes = (uint32_t)rows * TC_BK * 2;
+                int tile, klo, khi;
+                tc_split_range(p, work, tc_tile_kblocks(p, (p.ksplit > 1 ? work / p.ksplit : work) / p.n_tiles), tile, klo, khi);
                 const int m0 = (tile / p.n_tiles) * rows, n0 = (tile % p.n_tiles) * BN;
+                int f = 0;      // position in the tile's flattened k-block sequence
                 for (int s = 0; s < p.nsrc; ++s) {
                     // counts >= 2048 are rare: the hi plane of a COUNT operand is contracted only where this row tile has one
                     const bool hi = tc_use_hi(p, s, tile / p.n_tiles);
@@ -315,7 +353,8 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     const int nA = p.split_hi[s] ? 1 : (hi ? p.nA[s] : 1);
                     const uint32_t tx = (uint32_t)nA * a_bytes + 2 * B_TILE;
                     for (int pass = 0; pass < npass; ++pass)
-                        for (int kb = 0; kb < p.kblocks[s]; ++kb) {
+                        for (int kb = 0; kb < p.kblocks[s]; ++kb, ++f) {
+                            if (f < klo || f >= khi) continue;
                             mbar_wait_parked(smem_u32(&bar_empty[stage]), phase ^ 1u);
                             const uint32_t full = smem_u32(&bar_full[stage]);
                             const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
@@ -333,20 +372,24 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
             // ===================== MMA issuer
             int stage = 0, astage = 0;
             uint32_t phase = 0, aphase = 0;
-            for (int it = 0, tile; (tile = tc_tile(p, it)) >= 0; ++it) {
+            for (int it = 0, work; (work = tc_tile(p, it)) >= 0; ++it) {
+                int tile, klo, khi;
+                tc_split_range(p, work, tc_tile_kblocks(p, (p.ksplit > 1 ? work / p.ksplit : work) / p.n_tiles), tile, klo, khi);
                 const int m_blk = tile / p.n_tiles;
                 const int halves = p.pair ? 2 : 1;
                 const uint32_t a_bytes = (uint32_t)halves * TC_A_TILE;
                 // chunked accumulation (see tc_chunks): every chunk gets a fresh accumulator stage
-                const int tkb = tc_tile_kblocks(p, m_blk);
+                const int tkb = khi - klo;
                 const int nch = tc_chunks(tkb), per = (tkb + nch - 1) / nch;
+                int f = 0;
                 int done = 0, in_chunk = 0;
                 uint32_t tmem_d = 0, accumulate = 0;
                 for (int s = 0; s < p.nsrc; ++s) {
                     const bool hi = tc_use_hi(p, s, m_blk);
                     const uint32_t combos = (p.split_hi[s] || !hi) ? (p.combos[s] & 0x3u) : p.combos[s];
                     const int nkb = p.kblocks[s] * ((p.split_hi[s] && hi) ? 2 : 1);    // second pass: the hi count plane in the same A slot
-                    for (int kb = 0; kb < nkb; ++kb) {
+                    for (int kb = 0; kb < nkb; ++kb, ++f) {
+                        if (f < klo || f >= khi) continue;
                         if (in_chunk == 0) {
                             mbar_wait_backoff(smem_u32(&bar_tempty[astage]), aphase ^ 1u);
                             tc_fence_after();
@@ -521,7 +564,10 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
             if (sn > 0) { stage2(0, sn); sn = 0; }
             __syncwarp();
         };
-        for (int it = 0, tile; (tile = tc_tile(p, it)) >= 0; ++it) {
+        for (int it = 0, work; (work = tc_tile(p, it)) >= 0; ++it) {
+            int tile, klo, khi;
+            tc_split_range(p, work, EK == 1 ? 0 : tc_tile_kblocks(p, (p.ksplit > 1 ? work / p.ksplit : work) / p.n_tiles), tile, klo, khi);
+            const int64_t row_shift = p.ksplit > 1 ? (int64_t)(work % p.ksplit) * p.M : 0;    // split-K: slab of raw partial sums
             const int halves = (EK != 1 && p.pair) ? 2 : 1;
             const int64_t m0 = (int64_t)(tile / p.n_tiles) * (TC_BM * halves), n0 = (int64_t)(tile % p.n_tiles) * BN;
             slice = ((warp >> 2) + it) % NS;
@@ -556,7 +602,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
             if constexpr (EK != 1) {
                 // chunked accumulation: add all but the last chunk in registers, then fold the last one in and put
                 // the total back into the last chunk's TMEM stage (promotion never runs in pair mode)
-                const int nch = tc_chunks(tc_tile_kblocks(p, tile / p.n_tiles));
+                const int nch = tc_chunks(khi - klo);
                 if (nch > 1) {
                     float sum[CW];
 #pragma unroll
@@ -659,7 +705,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     const float acc[4] = {__uint_as_float(r[0]) * acc_scale, __uint_as_float(r[1]) * acc_scale, __uint_as_float(r[2]) * acc_scale,
                                           __uint_as_float(r[3]) * acc_scale};
                     if constexpr (EK == 2) epi_bern4(p.epi, rowh, col0, acc, nvalid);
-                    else rowsum += epi_apply4(p.epi, rowh, col0, acc, nvalid, delta_local);
+                    else rowsum += epi_apply4(p.epi, rowh + row_shift, col0, acc, nvalid, delta_local);
                 }
                 if constexpr (EK == 0) {
                     if (g == CW / 4 - 1) {                           // end of this row's slice: flush the AIS partial row sum
@@ -689,14 +735,26 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
 }
 
 // ------------------------------------------------------------------- host
-inline bool tc_make_map(TcContext& t, CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+inline bool tc_make_map_box(TcContext& t, CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols) {
+    const TcMapKey key{ptr, rows, cols, ld, box_rows, box_cols};
+    auto it = t.maps.find(key);
+    if (it != t.maps.end()) {
+        *map = it->second;
+        return true;
+    }
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    return t.encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    if (t.encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (t.maps.size() > 8192) t.maps.clear();
+    t.maps.emplace(key, *map);
+    return true;
+}
+inline bool tc_make_map(TcContext& t, CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    return tc_make_map_box(t, map, ptr, rows, cols, ld, box_rows, TC_BK);
 }
 
 // the tcgen05 kernel tiles any sweep whose operands exist as fp16 planes
@@ -715,6 +773,8 @@ inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, i
     p.a_tiles = std::max(p.split_hi[0] ? 1 : p.nA[0], p.nsrc > 1 ? (p.split_hi[1] ? 1 : p.nA[1]) : 1);
     p.stage_bytes = p.a_tiles * (p.pair ? 2 : 1) * TC_A_TILE + 2 * B_TILE;
     p.stages = std::max(1, std::min(TC_MAX_STAGES, (TC_SMEM_BUDGET + 20 * 1024 - qbytes) / p.stage_bytes));
+    // no more stages than k-blocks of a tile: a small shared-memory request keeps latency-bound launches cheap
+    p.stages = std::max(1, std::min(p.stages, p.kblocks[0] * (p.split_hi[0] ? 2 : 1) + (p.nsrc > 1 ? p.kblocks[1] * (p.split_hi[1] ? 2 : 1) : 0)));
     const int smem = p.stages * p.stage_bytes + 1024 + qbytes;
     if (!t.attr_set[slot]) {
         cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, EK, EPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
@@ -1017,13 +1077,7 @@ __global__ void k_grad_reduce(const float* __restrict__ partial, int splits, int
 }
 
 inline bool tc_make_map_mn(TcContext& t, CUtensorMap* map, const void* ptr, int64_t samples, int64_t units, int64_t ld) {
-    const cuuint64_t dims[2] = {(cuuint64_t)units, (cuuint64_t)samples};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    const cuuint32_t box[2] = {64, (cuuint32_t)TC_BK};
-    const cuuint32_t estr[2] = {1, 1};
-    return t.encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return tc_make_map_box(t, map, ptr, samples, units, ld, TC_BK, 64);      // box: 64 units (inner) x 64 samples
 }
 
 inline bool tc_grad_supported(const TcGradArgs& a) {
