@@ -61,22 +61,34 @@ __device__ __forceinline__ void mat_store4(const MatView& m, int64_t row, int64_
 }
 
 // log((1+e^{y1})/(1+e^{y2})) without cancellation: log1p(sigm(y2) * expm1(y1-y2))
-__device__ __forceinline__ float softplus_diff(float y2, float dy) { return log1pf(sigmf(y2) * expm1f(dy)); }
+// The transcendental-heavy bodies of the generic epilogue are out of line: inlined four times per column group they
+// made its loop body 52 KB of SASS -- larger than the 32 KB instruction cache level, i.e. an instruction-fetch stall on
+// every group (1.7 us per 4-column group in a latency-bound launch).
+__device__ __noinline__ float softplus_diff(float y2, float dy) { return log1pf(sigmf(y2) * expm1f(dy)); }
+__device__ __noinline__ float nb_mean_ool(float x, float r) { return nb_mean(x, r); }
+__device__ __noinline__ float nb_draw_ool(float x, float r, float u, float pshift, float mu_inv_max, RngAddr g) {
+    return nb_draw(nb_mean(x, r), r, u, pshift, mu_inv_max, g);
+}
 
 // Returns the AIS partial row sum (0 for other modes).  `row` is local to the
 // matrix; nvalid = number of in-range columns among col0..col0+3.
+// pre_bias / pre_r: the four columns' summed biases and inverse dispersions when the caller has them in registers
+// already (tensor-core engine: loaded once per tile and broadcast by shuffle); nullptr: loaded here.
 __device__ __forceinline__ float epi_apply4(const EpiParams& e, int64_t row, int64_t col0, const float (&acc)[4],
-                                            int nvalid, float& delta_local) {
-    float x[4], out[4];
+                                            int nvalid, float& delta_local, const float* pre_bias = nullptr, const float* pre_r = nullptr) {
+    float x[4], out[4], bias[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         float b = 0.0f;
-        if (j < nvalid) {
+        if (pre_bias) b = pre_bias[j];
+        else if (j < nvalid) {
             if (e.bias0) b += e.bias0[col0 + j];
             if (e.bias1) b += e.bias1[col0 + j];
         }
+        bias[j] = b;
         if (e.addend && j < nvalid) {
             float t = e.addend[row * e.ld_add + col0 + j];
+#pragma unroll 1
             for (int sp = 1; sp < e.addend_splits; ++sp) t += e.addend[(int64_t)sp * e.addend_stride + row * e.ld_add + col0 + j];   // split-K slabs, fixed order
             b += e.addend_scaled ? t * e.wscale : t;
         }
@@ -86,12 +98,7 @@ __device__ __forceinline__ float epi_apply4(const EpiParams& e, int64_t row, int
         float s = 0.0f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (j < nvalid) {
-                float b = 0.0f;
-                if (e.bias0) b += e.bias0[col0 + j];
-                if (e.bias1) b += e.bias1[col0 + j];
-                s += softplus_diff(e.t2 * acc[j] + b, (e.t1 - e.t2) * acc[j]);
-            }
+            if (j < nvalid) s += softplus_diff(e.t2 * acc[j] + bias[j], (e.t1 - e.t2) * acc[j]);
         }
         return s;
     }
@@ -117,12 +124,12 @@ __device__ __forceinline__ float epi_apply4(const EpiParams& e, int64_t row, int
                 case EPI_INPUT: o = x[j]; break;
                 case EPI_SIGM: o = sigmf(x[j]); break;
                 case EPI_SIGM_BERN: o = (u[j] < sigmf(x[j])) ? 1.0f : 0.0f; break;
-                case EPI_NBMEAN: o = nb_mean(x[j], e.r[col0 + j]); break;
+                case EPI_NBMEAN: o = nb_mean_ool(x[j], pre_r ? pre_r[j] : e.r[col0 + j]); break;
                 case EPI_NB_DRAW: {
-                    const float r = e.r[col0 + j];
+                    const float r = pre_r ? pre_r[j] : e.r[col0 + j];
                     const RngAddr g{e.k0, e.k1, (uint32_t)row + e.row_offset, (uint32_t)(col0 + j), e.tick,
                                     e.stream & 0xFFu};
-                    o = nb_draw(nb_mean(x[j], r), r, u[j], e.pshift, e.mu_inv_max, g);
+                    o = nb_draw_ool(x[j], r, u[j], e.pshift, e.mu_inv_max, g);
                 } break;
                 default: break;
             }
@@ -132,6 +139,40 @@ __device__ __forceinline__ float epi_apply4(const EpiParams& e, int64_t row, int
     }
     mat_store4(e.out, row, col0, out, nvalid);
     return 0.0f;
+}
+
+// ---- the deterministic epilogue class of the tensor-core engine (EK = 3): inputs, sigmoid potentials, NB means and raw
+// fp32 accumulators, with the optional mean-field extras (hoisted addend, previous value -> max |change|).  No draws,
+// no AIS: its loop body is a few hundred instructions, so latency-bound launches (training minibatches) and the
+// mean-field / positive-phase sweeps do not stall on instruction fetch the way the all-modes epilogue does.
+__device__ __forceinline__ void epi_det4(const EpiParams& e, int64_t row, int64_t col0, const float (&acc)[4], int nvalid,
+                                         float& delta_local, const float (&bias)[4], const float (&r4)[4]) {
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float b = bias[j];
+        if (e.addend && j < nvalid) {
+            float t = e.addend[row * e.ld_add + col0 + j];
+#pragma unroll 1
+            for (int sp = 1; sp < e.addend_splits; ++sp) t += e.addend[(int64_t)sp * e.addend_stride + row * e.ld_add + col0 + j];
+            b += e.addend_scaled ? t * e.wscale : t;
+        }
+        const float x = e.factor * fmaf(e.wscale, acc[j], b);
+        o[j] = e.mode == EPI_SIGM ? sigmf(x) : e.mode == EPI_NBMEAN ? nb_mean(x, r4[j]) : x;
+        if (j >= nvalid) o[j] = 0.0f;
+    }
+    if (e.mode == EPI_RAW_F32) {
+        float* d = e.out_f32 + row * e.ldo + col0;
+        if (nvalid == 4 && (reinterpret_cast<uintptr_t>(d) & 15u) == 0u) *reinterpret_cast<float4*>(d) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        else for (int j = 0; j < nvalid; ++j) d[j] = acc[j];
+        return;
+    }
+    if (e.prev.p0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < nvalid) delta_local = fmaxf(delta_local, fabsf(mat_load(e.prev, row, col0 + j) - o[j]));
+    }
+    mat_store4(e.out, row, col0, o, nvalid);
 }
 
 // ---- specialised sampling epilogues (tensor-core engine, Philox-fed): 4 consecutive columns
@@ -167,19 +208,12 @@ __device__ __forceinline__ float nb_entry_draw(const EpiParams& e, float acc, fl
     return k;
 }
 
-__device__ __forceinline__ void epi_bern4(const EpiParams& e, int64_t row, int64_t col0, const float (&acc)[4], int nvalid) {
+__device__ __forceinline__ void epi_bern4(const EpiParams& e, int64_t row, int64_t col0, const float (&acc)[4], int nvalid, const float (&bias)[4]) {
     const uint4 w = philox_group_rk(e, (uint32_t)row, (uint32_t)(col0 >> 2));
     const float u[4] = {u23(w.x), u23(w.y), u23(w.z), u23(w.w)};
     float o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float b = 0.0f;
-        if (j < nvalid) {
-            b = __ldg(e.bias0 + col0 + j);
-            if (e.bias1) b += __ldg(e.bias1 + col0 + j);
-        }
-        o[j] = (j < nvalid) ? bern_draw_fast(e.factor * fmaf(e.wscale, acc[j], b), u[j]) : 0.0f;
-    }
+    for (int j = 0; j < 4; ++j) o[j] = (j < nvalid) ? bern_draw_fast(e.factor * fmaf(e.wscale, acc[j], bias[j]), u[j]) : 0.0f;
     const int64_t i = row * e.out.ld + col0;
     if (nvalid == 4) {
         *reinterpret_cast<uint2*>(e.out.p0 + i) = make_uint2(pack_f16x2(o[0], o[1]), pack_f16x2(o[2], o[3]));

@@ -46,7 +46,7 @@ struct TcMapKeyHash {
 };
 struct TcContext {
     PFN_tmapEncodeTiled encode = nullptr;
-    bool attr_set[9] = {};
+    bool attr_set[16] = {};
     std::unordered_map<TcMapKey, CUtensorMap, TcMapKeyHash> maps;
 };
 
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_holder;
-    if constexpr (EK == 0) {
+    if constexpr (EK == 0 || EK == 3) {
         if (p.epi.skip && *p.epi.skip) return;   // speculatively launched mean-field iteration after convergence (whole grid)
     }
 
@@ -599,6 +599,15 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 if (lane < CW) { sN[lane] = cn; sT[lane] = ct; }
                 __syncwarp();
             }
+            float bias_l = 0.0f, r_l = 1.0f;       // this lane's column of the warp's slice: summed biases, inverse dispersion
+            if constexpr (EK != 1) {
+                const int64_t cl = n0 + slice * CW + lane;
+                if (lane < CW && cl < p.N) {
+                    if (p.epi.bias0) bias_l = __ldg(p.epi.bias0 + cl);
+                    if (p.epi.bias1) bias_l += __ldg(p.epi.bias1 + cl);
+                    if (p.epi.r && (p.epi.mode == EPI_NBMEAN || p.epi.mode == EPI_NB_DRAW)) r_l = __ldg(p.epi.r + cl);
+                }
+            }
             if constexpr (EK != 1) {
                 // chunked accumulation: add all but the last chunk in registers, then fold the last one in and put
                 // the total back into the last chunk's TMEM stage (promotion never runs in pair mode)
@@ -698,14 +707,21 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 const int64_t rowh = row + h * TC_BM;
                 uint32_t r[4];
                 tmem_ld4(taddr + h * BN + g * 4, r);   // warp-collective: outside any row/column predicate
+                float bias4[4], r4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    bias4[j] = __shfl_sync(0xffffffffu, bias_l, g * 4 + j);
+                    r4[j] = __shfl_sync(0xffffffffu, r_l, g * 4 + j);
+                }
                 tmem_wait_ld();
                 const int64_t col0 = n0 + slice * CW + g * 4;
                 const int nvalid = (int)max((int64_t)0, min((int64_t)4, p.N - col0));
                 if (rowh < p.M && nvalid > 0) {
                     const float acc[4] = {__uint_as_float(r[0]) * acc_scale, __uint_as_float(r[1]) * acc_scale, __uint_as_float(r[2]) * acc_scale,
                                           __uint_as_float(r[3]) * acc_scale};
-                    if constexpr (EK == 2) epi_bern4(p.epi, rowh, col0, acc, nvalid);
-                    else rowsum += epi_apply4(p.epi, rowh + row_shift, col0, acc, nvalid, delta_local);
+                    if constexpr (EK == 2) epi_bern4(p.epi, rowh, col0, acc, nvalid, bias4);
+                    else if constexpr (EK == 3) epi_det4(p.epi, rowh + row_shift, col0, acc, nvalid, delta_local, bias4, r4);
+                    else rowsum += epi_apply4(p.epi, rowh + row_shift, col0, acc, nvalid, delta_local, bias4, r4);
                 }
                 if constexpr (EK == 0) {
                     if (g == CW / 4 - 1) {                           // end of this row's slice: flush the AIS partial row sum
@@ -767,7 +783,7 @@ inline bool tc_supported(const GemmArgs& g, int nsrc) {
 
 template <int BN, int EK, int EPW>
 inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, int num_sms, cudaStream_t stream) {
-    const int slot = (BN == 64 ? 0 : BN == 128 ? 3 : 6) + EK;   // wide NB kernel: slot 7
+    const int slot = (BN == 64 ? 0 : BN == 128 ? 4 : 8) + EK;   // wide NB kernel: slot 9
     constexpr int B_TILE = BN * TC_BK * 2;
     const int qbytes = (EK == 1) ? EPW * tc_epi_smem(BN / (EPW / 4)) : 0;
     p.a_tiles = std::max(p.split_hi[0] ? 1 : p.nA[0], p.nsrc > 1 ? (p.split_hi[1] ? 1 : p.nA[1]) : 1);
@@ -796,6 +812,8 @@ inline int tc_epilogue_class(const GemmArgs& g, const TcOperandPlanes* ops, int 
             nsrc == 1 && ops[0].a.kind == MAT_BINARY && e.wscale >= 0.0f && e.wscale <= 1.0f) ek = 1;
         if (e.mode == EPI_SIGM_BERN && e.bias0 && !e.out.p1 && !e.out.f) ek = 2;
     }
+    // deterministic class: inputs / potentials / NB means / raw accumulators, mean-field extras allowed
+    if (ek == 0 && !e.uniforms && (e.mode == EPI_INPUT || e.mode == EPI_SIGM || e.mode == EPI_NBMEAN || e.mode == EPI_RAW_F32)) ek = 3;
     return ek;
 }
 
@@ -837,11 +855,13 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
     if (BN == 64) {
         if (ek == 1) return tc_launch_bn<64, 1, 16>(t, maps, p, num_sms, stream);
         if (ek == 2) return tc_launch_bn<64, 2, 16>(t, maps, p, num_sms, stream);
+        if (ek == 3) return tc_launch_bn<64, 3, 16>(t, maps, p, num_sms, stream);
         return tc_launch_bn<64, 0, 16>(t, maps, p, num_sms, stream);
     }
     if (BN == TC_NB_BN && ek == 1) return tc_launch_bn<TC_NB_BN, 1, TC_NB_EPW>(t, maps, p, num_sms, stream);
     if (ek == 1) return tc_launch_bn<128, 1, 16>(t, maps, p, num_sms, stream);
     if (ek == 2) return tc_launch_bn<128, 2, 16>(t, maps, p, num_sms, stream);
+    if (ek == 3) return tc_launch_bn<128, 3, 16>(t, maps, p, num_sms, stream);
     return tc_launch_bn<128, 0, 16>(t, maps, p, num_sms, stream);
 }
 
@@ -1125,10 +1145,10 @@ inline cudaError_t launch_grad_tc(TcContext& t, const TcGradArgs& a, int num_sms
     }
     p.stages = 3;
     const int smem = p.stages * TG_STAGE + 1024;
-    if (!t.attr_set[8]) {
+    if (!t.attr_set[15]) {
         cudaError_t e = cudaFuncSetAttribute(k_grad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        t.attr_set[8] = true;
+        t.attr_set[15] = true;
     }
     const int nwork = p.m_tiles * p.n_tiles * p.splits;
     k_grad_tc<<<std::min(nwork, num_sms), TG_THREADS, smem, stream>>>(maps, p);
