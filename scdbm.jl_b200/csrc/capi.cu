@@ -348,7 +348,31 @@ static void run_gemm(scdbm_ctx* ctx, GemmArgs& g, const SweepSrc* srcs, int nsrc
         } else {
             set_hiflags(ctx, g.epi.out, true);
         }
-        CK(launch_gemm_tc(ctx->tc, ops, nsrc, g, ctx->num_sms, ctx->stream));
+        const int S = tc_plan_split(g, ops, nsrc, ctx->num_sms);
+        if (S > 1) {
+            // split-K: S partial sums of the contraction as raw fp32 slabs [S][M][ldw], then one finishing launch
+            const int64_t ldw = round_up(g.N, 4), stride = g.M * ldw, need = (int64_t)S * stride;
+            if (ctx->scratch_cap < need) {
+                CK(cudaStreamSynchronize(ctx->stream));
+                cudaFree(ctx->scratch);
+                ctx->scratch = nullptr;
+                ctx->scratch_cap = 0;
+                CK(cudaMalloc(&ctx->scratch, need * sizeof(float)));
+                ctx->scratch_cap = need;
+            }
+            GemmArgs gp = g;
+            gp.epi.mode = EPI_RAW_F32;
+            gp.epi.out_f32 = ctx->scratch;
+            gp.epi.ldo = ldw;
+            gp.epi.bias0 = gp.epi.bias1 = nullptr;
+            CK(launch_gemm_tc(ctx->tc, ops, nsrc, gp, ctx->num_sms, ctx->stream, S));
+            const int64_t nthreads = g.M * ((g.N + 3) / 4);
+            k_det_finish<<<(unsigned)((nthreads + 127) / 128), 128, 0, ctx->stream>>>(ctx->scratch, S, stride, ldw, g.epi, g.M, g.N);
+            CK(cudaGetLastError());
+            ctx->launches++;
+        } else {
+            CK(launch_gemm_tc(ctx->tc, ops, nsrc, g, ctx->num_sms, ctx->stream));
+        }
         ctx->tc_launches++;
     } else {
         set_hiflags(ctx, g.epi.out, true);
@@ -1616,7 +1640,7 @@ static void gradient_biases(scdbm_opt* o, int l, const MatView& v, const MatView
     float* ga = o->buf + o->offA[l];
     float* gb = o->buf + o->offB[l];
     if (std::max(v.rows, vm.rows) <= 2048) {
-        k_bias_grad<<<(unsigned)((L.V + L.H + 31) / 32), dim3(32, 8), 0, c->stream>>>(v, vm, h, hm, pos_scale, neg_scale, ga, gb);
+        k_bias_grad<<<(unsigned)((L.V + L.H + 31) / 32), dim3(32, 32), 0, c->stream>>>(v, vm, h, hm, pos_scale, neg_scale, ga, gb);
         CK(cudaGetLastError());
         c->launches++;
         return;

@@ -150,6 +150,39 @@ __global__ void k_update(float* __restrict__ theta, const float* __restrict__ gr
     }
 }
 
+// ---- second half of a split-K sweep (latency-bound shapes: one or a few output tiles, long contraction): sums the S
+// slabs of raw fp32 partial sums in fixed order, adds the biases, applies the deterministic activation and writes the
+// state planes.  One thread per 4 consecutive columns of a row.
+__global__ void k_det_finish(const float* __restrict__ ws, int S, int64_t stride, int64_t ldw, EpiParams e, int64_t M, int64_t N) {
+    const int64_t groups = (N + 3) / 4;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * groups) return;
+    const int64_t row = i / groups, col0 = (i % groups) * 4;
+    const int nvalid = (int)min((int64_t)4, N - col0);
+    float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (nvalid == 4) {
+        float4 t = *reinterpret_cast<const float4*>(ws + row * ldw + col0);
+        for (int sp = 1; sp < S; ++sp) {
+            const float4 u = *reinterpret_cast<const float4*>(ws + (int64_t)sp * stride + row * ldw + col0);
+            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    } else {
+        for (int j = 0; j < nvalid; ++j)
+            for (int sp = 0; sp < S; ++sp) o[j] += ws[(int64_t)sp * stride + row * ldw + col0 + j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j >= nvalid) { o[j] = 0.0f; continue; }
+        float b = 0.0f;
+        if (e.bias0) b += e.bias0[col0 + j];
+        if (e.bias1) b += e.bias1[col0 + j];
+        const float x = e.factor * fmaf(e.wscale, o[j], b);
+        o[j] = e.mode == EPI_SIGM ? sigmf(x) : e.mode == EPI_NBMEAN ? nb_mean(x, e.r[col0 + j]) : x;
+    }
+    mat_store4(e.out, row, col0, o, nvalid);
+}
+
 // ---- K6: the whole parameter update of one RBM layer in one pass (src/optimizers.jl:478-485,513-520):
 //   W += lr dW (NB: W = min(W, 0)),  a += lr da (NB: a = min(a, -1e-10)),  b += lr db,
 // and, from the updated values still in registers, every derived operand the sweeps read: the fp16 hi/lo planes of s W in
@@ -239,7 +272,7 @@ __global__ void k_weight_scale_next(unsigned int* __restrict__ max_bits, float* 
 // ---- bias gradients of one RBM in one launch (small batches; the two-pass column sums below serve large ones):
 //   da[c] = ps sum_rows v - ns sum_rows vm   (c < V),   db[c - V] = ps sum_rows h - ns sum_rows hm.   Deterministic.
 __global__ void k_bias_grad(MatView v, MatView vm, MatView h, MatView hm, float ps, float ns, float* __restrict__ da, float* __restrict__ db) {
-    __shared__ float red[8][33];
+    __shared__ float red[32][33];
     const int64_t V = v.cols, H = h.cols;
     const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
     const bool vis = c < V;
@@ -247,15 +280,16 @@ __global__ void k_bias_grad(MatView v, MatView vm, MatView h, MatView hm, float 
     const MatView& N = vis ? vm : hm;
     const int64_t cc = vis ? c : c - V;
     float sp = 0.0f, sn = 0.0f;
-    if (c < V + H) {
-        for (int64_t r = threadIdx.y; r < P.rows; r += 8) sp += mat_load(P, r, cc);
-        for (int64_t r = threadIdx.y; r < N.rows; r += 8) sn += mat_load(N, r, cc);
+    if (c < V + H) {      // 32 row lanes: few dependent loads per thread (the launch is latency-bound)
+        for (int64_t r = threadIdx.y; r < P.rows; r += 32) sp += mat_load(P, r, cc);
+        for (int64_t r = threadIdx.y; r < N.rows; r += 32) sn += mat_load(N, r, cc);
     }
     red[threadIdx.y][threadIdx.x] = ps * sp - ns * sn;
     __syncthreads();
     if (threadIdx.y == 0 && c < V + H) {
         float tot = 0.0f;
-        for (int j = 0; j < 8; ++j) tot += red[j][threadIdx.x];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tot += red[j][threadIdx.x];
         (vis ? da : db)[cc] = tot;
     }
 }

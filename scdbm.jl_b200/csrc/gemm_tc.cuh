@@ -797,8 +797,8 @@ inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, i
         if (e != cudaSuccess) return e;
         t.attr_set[slot] = true;
     }
-    p.sched = p.m_tiles >= num_sms ? 1 : 0;
-    const int grid = p.sched ? std::min(p.m_tiles, num_sms) : std::min(p.m_tiles * p.n_tiles, num_sms);
+    p.sched = (p.m_tiles >= num_sms && p.ksplit <= 1) ? 1 : 0;
+    const int grid = p.sched ? std::min(p.m_tiles, num_sms) : std::min(p.m_tiles * p.n_tiles * std::max(p.ksplit, 1), num_sms);
     k_gemm_tc<BN, EK, EPW><<<grid, 32 * (4 + EPW), smem, stream>>>(maps, p);
     return cudaGetLastError();
 }
@@ -817,8 +817,21 @@ inline int tc_epilogue_class(const GemmArgs& g, const TcOperandPlanes* ops, int 
     return ek;
 }
 
+// split-K plan for latency-bound deterministic sweeps: few output tiles, long contraction, no mean-field extras.
+// Returns the number of splits (1: none).
+inline int tc_plan_split(const GemmArgs& g, const TcOperandPlanes* ops, int nsrc, int num_sms) {
+    const EpiParams& e = g.epi;
+    if (tc_epilogue_class(g, ops, nsrc) != 3 || e.mode == EPI_RAW_F32 || e.addend || e.prev.p0 || e.skip) return 1;
+    const int64_t tiles = ((g.M + TC_BM - 1) / TC_BM) * ((g.N + 127) / 128);
+    if (tiles * 4 > num_sms) return 1;
+    int kb = 0;
+    for (int s = 0; s < nsrc; ++s) kb += (int)((ops[s].K + TC_BK - 1) / TC_BK);
+    const int S = (int)std::min<int64_t>({16, kb / 2, num_sms / tiles});
+    return S >= 2 ? S : 1;
+}
+
 inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int nsrc, const GemmArgs& g, int num_sms,
-                                  cudaStream_t stream) {
+                                  cudaStream_t stream, int ksplit = 1) {
     if (!t.encode) return cudaErrorNotSupported;
     const int ek = tc_epilogue_class(g, ops, nsrc);
     const int BN = g.N <= 64 ? 64 : (ek == 1 && g.N >= TC_NB_BN) ? TC_NB_BN : 128;
@@ -837,6 +850,7 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
     p.m_tiles = (int)((g.M + rows_per_tile - 1) / rows_per_tile);
     p.n_tiles = (int)((g.N + BN - 1) / BN);
     p.epi = g.epi;
+    p.ksplit = ksplit;
     for (int s = 0; s < nsrc; ++s) {
         const MatView& a = ops[s].a;
         p.kblocks[s] = (int)((ops[s].K + TC_BK - 1) / TC_BK);
