@@ -301,8 +301,17 @@ __global__ void k_colsum_partial(MatView m, float* __restrict__ partial) {
     __shared__ float red[8][33];
     const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
     float s = 0.0f;
-    if (c < m.cols)
-        for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < m.rows; r += (int64_t)gridDim.y * 8) s += mat_load(m, r, c);
+    if (c < m.cols) {
+        if (m.kind == MAT_COUNT && m.hiflag) {      // hi count plane only where the row tile uses it (half the HBM reads)
+            for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < m.rows; r += (int64_t)gridDim.y * 8) {
+                float v = plane_decode(m.p0[r * m.ld + c]);
+                if (m.hiflag[r >> 7] & 1u) v += plane_decode(m.p1[r * m.ld + c]);
+                s += v;
+            }
+        } else {
+            for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < m.rows; r += (int64_t)gridDim.y * 8) s += mat_load(m, r, c);
+        }
+    }
     red[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && c < m.cols) {

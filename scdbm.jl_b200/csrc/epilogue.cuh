@@ -147,17 +147,34 @@ __device__ __forceinline__ float epi_apply4(const EpiParams& e, int64_t row, int
 // mean-field / positive-phase sweeps do not stall on instruction fetch the way the all-modes epilogue does.
 __device__ __forceinline__ void epi_det4(const EpiParams& e, int64_t row, int64_t col0, const float (&acc)[4], int nvalid,
                                          float& delta_local, const float (&bias)[4], const float (&r4)[4]) {
-    float o[4];
+    float o[4], add[4] = {0.0f, 0.0f, 0.0f, 0.0f}, old[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    // mean-field extras first, as two 16-byte loads in flight together (rows are 16-byte aligned: ld % 4 == 0)
+    const bool vec = nvalid == 4;
+    if (e.addend) {
+        const float* a = e.addend + row * e.ld_add + col0;
+        if (vec && (e.ld_add & 3) == 0 && (reinterpret_cast<uintptr_t>(e.addend) & 15u) == 0u) {
+            const float4 t = *reinterpret_cast<const float4*>(a);
+            add[0] = t.x; add[1] = t.y; add[2] = t.z; add[3] = t.w;
+        } else {
+            for (int j = 0; j < nvalid; ++j) add[j] = a[j];
+        }
+#pragma unroll 1
+        for (int sp = 1; sp < e.addend_splits; ++sp)
+            for (int j = 0; j < nvalid; ++j) add[j] += a[(int64_t)sp * e.addend_stride + j];
+        if (e.addend_scaled)
+            for (int j = 0; j < 4; ++j) add[j] *= e.wscale;
+    }
+    if (e.prev.p0) {
+        if (e.prev.f && vec) {
+            const float4 t = *reinterpret_cast<const float4*>(e.prev.f + row * e.prev.ld + col0);
+            old[0] = t.x; old[1] = t.y; old[2] = t.z; old[3] = t.w;
+        } else {
+            for (int j = 0; j < nvalid; ++j) old[j] = mat_load(e.prev, row, col0 + j);
+        }
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        float b = bias[j];
-        if (e.addend && j < nvalid) {
-            float t = e.addend[row * e.ld_add + col0 + j];
-#pragma unroll 1
-            for (int sp = 1; sp < e.addend_splits; ++sp) t += e.addend[(int64_t)sp * e.addend_stride + row * e.ld_add + col0 + j];
-            b += e.addend_scaled ? t * e.wscale : t;
-        }
-        const float x = e.factor * fmaf(e.wscale, acc[j], b);
+        const float x = e.factor * fmaf(e.wscale, acc[j], bias[j] + add[j]);
         o[j] = e.mode == EPI_SIGM ? sigmf(x) : e.mode == EPI_NBMEAN ? nb_mean(x, r4[j]) : x;
         if (j >= nvalid) o[j] = 0.0f;
     }
@@ -170,7 +187,7 @@ __device__ __forceinline__ void epi_det4(const EpiParams& e, int64_t row, int64_
     if (e.prev.p0) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            if (j < nvalid) delta_local = fmaxf(delta_local, fabsf(mat_load(e.prev, row, col0 + j) - o[j]));
+            if (j < nvalid) delta_local = fmaxf(delta_local, fabsf(old[j] - o[j]));
     }
     mat_store4(e.out, row, col0, o, nvalid);
 }

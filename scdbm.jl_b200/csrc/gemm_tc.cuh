@@ -797,7 +797,15 @@ inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, i
         if (e != cudaSuccess) return e;
         t.attr_set[slot] = true;
     }
+    // EK == 1 (NB draw): a CTA owns whole row tiles and walks all column tiles -- every CTA sees every gene, which balances
+    // the sampling epilogue.  Other classes: flat order with the column tile fastest, so the CTAs that share a row tile
+    // (A operand) stream it at the same time and the second reader hits L2 (owning it sequentially re-read A from
+    // HBM: in pair mode 148 CTAs x 1 MB of A exceed the 126 MB L2).
+#ifdef SCDBM_OLD_SCHED
     p.sched = (p.m_tiles >= num_sms && p.ksplit <= 1) ? 1 : 0;
+#else
+    p.sched = (EK == 1 && p.m_tiles >= num_sms && p.ksplit <= 1) ? 1 : 0;
+#endif
     const int grid = p.sched ? std::min(p.m_tiles, num_sms) : std::min(p.m_tiles * p.n_tiles * std::max(p.ksplit, 1), num_sms);
     k_gemm_tc<BN, EK, EPW><<<grid, 32 * (4 + EPW), smem, stream>>>(maps, p);
     return cudaGetLastError();
