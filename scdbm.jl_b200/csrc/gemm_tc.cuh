@@ -610,23 +610,28 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
             }
             if constexpr (EK != 1) {
                 // chunked accumulation: add all but the last chunk in registers, then fold the last one in and put
-                // the total back into the last chunk's TMEM stage (promotion never runs in pair mode)
+                // the total back into the last chunk's TMEM stage
                 const int nch = tc_chunks(khi - klo);
                 if (nch > 1) {
-                    float sum[CW];
+                    float sum[2][CW];      // [row half of a pair-mode work tile][column of the warp's slice]
 #pragma unroll
-                    for (int i = 0; i < CW; ++i) sum[i] = 0.0f;
+                    for (int i = 0; i < CW; ++i) sum[0][i] = sum[1][i] = 0.0f;
                     for (int c = 0; c < nch; ++c) {
                         mbar_wait_epi(smem_u32(&bar_tfull[astage]), aphase);
                         tc_fence_after();
-                        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(astage * BN + slice * CW);
+                        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(astage * halves * BN + slice * CW);
 #pragma unroll
-                        for (int g = 0; g < CW / 16; ++g) {
-                            uint32_t r[16];
-                            tmem_ld16(ta + g * 16, r);
-                            tmem_wait_ld();
+                        for (int h = 0; h < 2; ++h) {
+                            if (h < halves) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) sum[g * 16 + i] += __uint_as_float(r[i]);
+                                for (int g = 0; g < CW / 16; ++g) {
+                                    uint32_t r[16];
+                                    tmem_ld16(ta + h * BN + g * 16, r);
+                                    tmem_wait_ld();
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) sum[h][g * 16 + i] += __uint_as_float(r[i]);
+                                }
+                            }
                         }
                         if (c + 1 < nch) {
                             tc_fence_before();
@@ -635,11 +640,16 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                             if (++astage == ASTAGES) { astage = 0; aphase ^= 1u; }
                         } else {
 #pragma unroll
-                            for (int g = 0; g < CW / 16; ++g) {
-                                uint32_t r[16];
+                            for (int h = 0; h < 2; ++h) {
+                                if (h < halves) {
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(sum[g * 16 + i]);
-                                tmem_st16(ta + g * 16, r);
+                                    for (int g = 0; g < CW / 16; ++g) {
+                                        uint32_t r[16];
+#pragma unroll
+                                        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(sum[h][g * 16 + i]);
+                                        tmem_st16(ta + h * BN + g * 16, r);
+                                    }
+                                }
                             }
                             tmem_wait_st();
                         }
@@ -853,7 +863,8 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
     // every SM busy with pairs; the NB sampling kernel keeps single tiles (its two 224-column stages fill TMEM)
     int max_kb = 0;
     for (int s = 0; s < nsrc; ++s) max_kb += (int)((ops[s].K + TC_BK - 1) / TC_BK) * ((ops[s].a.p1 && ops[s].a.kind == MAT_COUNT) ? 2 : 1);
-    p.pair = (ek != 1 && g.M >= (int64_t)2 * TC_BM * num_sms && tc_chunks(max_kb) == 1) ? 1 : 0;
+    (void)max_kb;
+    p.pair = (ek != 1 && g.M >= (int64_t)2 * TC_BM * num_sms) ? 1 : 0;
     const int rows_per_tile = p.pair ? 2 * TC_BM : TC_BM;
     p.m_tiles = (int)((g.M + rows_per_tile - 1) / rows_per_tile);
     p.n_tiles = (int)((g.N + BN - 1) / BN);

@@ -280,3 +280,18 @@ def test_single_rank_communicator_matches_plain_step(pkg):
     assert res[0][1] == res[1][1]
     for a, b in zip(res[0][0], res[1][0]):
         assert np.array_equal(a, b)
+
+
+def test_pair_mode_with_chunked_accumulation(pkg, auto):
+    """>= 2*128*148 rows (256-row work tiles) AND a contraction longer than 72 k-blocks (chunk-promoted accumulation):
+    the combination the positive phase of C4 runs in (100 000 cells x 20 000 genes).  Ragged rows and width."""
+    n, V, H = 2 * 128 * 148 + 77, 5000, 130
+    dbm = synth.random_dbm([V, H, 16], 9)
+    m = pkg.DeviceModel.from_host(to_pkg_model(pkg, dbm), auto)
+    g = np.random.default_rng(3)
+    x = g.poisson(0.3, (n, V)).astype(float)
+    x[n - 3, 11] = 4000.0
+    e_in = relerr(pkg.hiddeninput(m, x, ctx=auto), om.hiddeninput(dbm[0], x), 1e-6)
+    e_pot = relerr(pkg.hiddenpotential(m, x, 2.0, ctx=auto), om.hiddenpotential(dbm[0], x, 2.0), 1e-7)
+    print(f"[pair + chunks] hiddeninput {e_in:.2e}, hiddenpotential {e_pot:.2e}")
+    assert e_in < RTOL and e_pot < RTOL
