@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 // bits of the word (the uniform uses the top 23) and the last mantissa bit of the accumulator.
                 const EpiParams& e = p.epi;
                 // position of (lane, column c) in the staging tile: lane * CW + c; bit 9 travels in the accumulator's last bit
-#pragma unroll 1
+#pragma unroll 1      // (2-way unrolling: more spills at the 64-register cap, measured 6 % slower)
                 for (int g = 0; g < CW / 4; ++g) {
                     uint32_t r[4];
                     tmem_ld4(taddr + g * 4, r);
@@ -913,7 +913,7 @@ struct TcGradParams {
     int64_t V, H;
     int32_t kblocks[2];
     int32_t nA[2], nB[2];
-    uint32_t combos[2];
+    uint32_t combos[2];    // bit (pa * 2 + pb): plane product A_pa x B_pb is contracted
     const uint32_t* a_hiflag[2];
     float scale[2];
     float* out;
@@ -922,7 +922,7 @@ struct TcGradParams {
 };
 constexpr int TG_BN = 128, TG_THREADS = 32 * (4 + 16);
 constexpr int TG_PLANE = 128 * TC_BK * 2;           // 16 KB: [2 unit blocks][64 samples][64 units] fp16
-constexpr int TG_STAGE = 4 * TG_PLANE;              // up to 2 A planes + 2 B planes
+__host__ __device__ constexpr int tg_stage_bytes(int halves) { return (halves + 2) * TG_PLANE; }   // one A plane (all row halves) + 2 B planes
 
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
     uint64_t d = 0;
@@ -934,10 +934,21 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
     return d;
 }
 
+// HALVES: 128-row halves of a work tile (1 or 2).  Two halves share every B (hidden-state) tile load: 64 instead of 96
+// B/clk/SM of L2 -> shared-memory operand traffic, which bounds this kernel at the C4 shapes.
+// A k-block (64 samples) is contracted in one or two PASSES through one shared-memory stage: pass pa stages A plane pa
+// (all row halves) and the B planes it multiplies.  Pass 1 runs only where it is needed: a COUNT operand's hi plane where
+// the 128-sample block is flagged, a REAL operand's lo plane always.
+// The sample axis is contracted in chunks of <= TC_CHUNK_KB k-blocks, chunks never straddle the positive / negative
+// source, each chunk goes into a fresh TMEM stage (2 stages x HALVES x 128 columns) and the epilogue warps add
+// scale[source] x chunk in registers (fp32 promotion: tcgen05.mma's own accumulation truncates, see tc_chunks).
+template <int HALVES>
 __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant__ TcGradMaps maps, const __grid_constant__ TcGradParams p) {
     constexpr uint32_t IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(TG_BN >> 3) << 17) |
                                ((uint32_t)(TC_BM >> 4) << 24);   // c = F32, a = b = F16, both MN-major
-    constexpr uint32_t TG_TMEM = 512;   // 2 chunk stages x {positive, negative} accumulator x 128 columns
+    constexpr uint32_t TG_TMEM = 2 * HALVES * TG_BN;             // 256 or 512 columns
+    constexpr int STAGE = tg_stage_bytes(HALVES);
+    constexpr int ROWS = HALVES * TC_BM;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_holder;
@@ -965,17 +976,11 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
         lo = (int)((int64_t)p.kblocks[s] * sp / p.splits);
         hi = (int)((int64_t)p.kblocks[s] * (sp + 1) / p.splits);
     };
-    // The contraction runs over the samples (K = 100 000 at BASELINE config C4): accumulated in chunks of <= TC_CHUNK_KB
-    // k-blocks, each into a fresh pair of TMEM accumulators, combined and summed in registers by the epilogue warps
-    // (round-to-nearest fp32; tcgen05.mma's own accumulation truncates -- see tc_chunks).
-    auto chunking = [&](int sp, int& n0, int& tkb, int& nch, int& per) {
-        int lo0, hi0, lo1, hi1;
-        kb_range(0, sp, lo0, hi0);
-        kb_range(1, sp, lo1, hi1);
-        n0 = hi0 - lo0;
-        tkb = n0 + (hi1 - lo1);
-        nch = tkb > 0 ? (tkb + TC_CHUNK_KB - 1) / TC_CHUNK_KB : 1;
-        per = (tkb + nch - 1) / nch;
+    // B-plane masks of the two passes of k-block kb of source s (0: pass not run)
+    auto pass_masks = [&](int s, int kb, uint32_t& m0, uint32_t& m1) {
+        m0 = p.combos[s] & 3u;
+        m1 = (p.combos[s] >> 2) & 3u;
+        if (p.a_hiflag[s] && (p.a_hiflag[s][kb / 2] & 1u) == 0u) m1 = 0u;      // COUNT operand: hi plane unused in this 128-sample block
     };
 
     if (svc == 0) {
@@ -984,23 +989,27 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
             uint32_t phase = 0;
             for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
                 const int tile = w / p.splits, sp = w % p.splits;
-                const int m0 = (tile / p.n_tiles) * TC_BM, n0 = (tile % p.n_tiles) * TG_BN;
+                const int m0 = (tile / p.n_tiles) * ROWS, n0 = (tile % p.n_tiles) * TG_BN;
                 for (int s = 0; s < 2; ++s) {
                     int lo, hi;
                     kb_range(s, sp, lo, hi);
                     for (int kb = lo; kb < hi; ++kb) {
-                        const int nA = (p.a_hiflag[s] && p.nA[s] == 2 && (p.a_hiflag[s][kb / 2] & 1u) == 0u) ? 1 : p.nA[s];
-                        mbar_wait_parked(smem_u32(&bar_empty[stage]), phase ^ 1u);
-                        const uint32_t full = smem_u32(&bar_full[stage]);
-                        const uint32_t sa = smem_base + (uint32_t)stage * TG_STAGE, sb = sa + 2 * TG_PLANE;
-                        mbar_expect_tx(full, (uint32_t)((nA + p.nB[s]) * TG_PLANE));
-                        for (int pa = 0; pa < nA; ++pa)
-                            for (int blk = 0; blk < 2; ++blk)
-                                tma_load_2d(sa + pa * TG_PLANE + blk * 8192, &maps.a[s][pa], full, m0 + blk * 64, kb * TC_BK);
-                        for (int pb = 0; pb < p.nB[s]; ++pb)
-                            for (int blk = 0; blk < 2; ++blk)
-                                tma_load_2d(sb + pb * TG_PLANE + blk * 8192, &maps.b[s][pb], full, n0 + blk * 64, kb * TC_BK);
-                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                        uint32_t pm[2];
+                        pass_masks(s, kb, pm[0], pm[1]);
+                        for (int pa = 0; pa < 2; ++pa) {
+                            if (!pm[pa]) continue;
+                            const int nb = (pm[pa] & 2u) ? 2 : 1;
+                            mbar_wait_parked(smem_u32(&bar_empty[stage]), phase ^ 1u);
+                            const uint32_t full = smem_u32(&bar_full[stage]);
+                            const uint32_t sa = smem_base + (uint32_t)stage * STAGE, sb = sa + HALVES * TG_PLANE;
+                            mbar_expect_tx(full, (uint32_t)((HALVES + nb) * TG_PLANE));
+                            for (int blk = 0; blk < 2 * HALVES; ++blk)
+                                tma_load_2d(sa + blk * 8192, &maps.a[s][pa], full, m0 + blk * 64, kb * TC_BK);
+                            for (int pb = 0; pb < nb; ++pb)
+                                for (int blk = 0; blk < 2; ++blk)
+                                    tma_load_2d(sb + pb * TG_PLANE + blk * 8192, &maps.b[s][pb], full, n0 + blk * 64, kb * TC_BK);
+                            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                        }
                     }
                 }
             }
@@ -1011,46 +1020,47 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
             uint32_t phase = 0, aphase = 0;
             for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
                 const int sp = w % p.splits;
-                int n0, tkb, nch, per;
-                chunking(sp, n0, tkb, nch, per);
-                if (tkb == 0) {   // nothing to contract in this split: hand the epilogue an (ignored) stage so the protocol stays in step
-                    mbar_wait_parked(smem_u32(&bar_tempty[astage]), aphase ^ 1u);
-                    tc_commit(smem_u32(&bar_tfull[astage]));
-                    if (++astage == 2) { astage = 0; aphase ^= 1u; }
-                    continue;
-                }
-                int done = 0, in_chunk = 0;
-                uint32_t acc_used = 0;      // bit s: accumulator s has been written in this chunk
                 for (int s = 0; s < 2; ++s) {
                     int lo, hi;
                     kb_range(s, sp, lo, hi);
+                    const int n = hi - lo;
+                    if (n <= 0) continue;
+                    const int nch = (n + TC_CHUNK_KB - 1) / TC_CHUNK_KB, per = (n + nch - 1) / nch;
+                    int in_chunk = 0;
+                    uint32_t accumulate = 0;
                     for (int kb = lo; kb < hi; ++kb) {
                         if (in_chunk == 0) {
                             mbar_wait_parked(smem_u32(&bar_tempty[astage]), aphase ^ 1u);
                             tc_fence_after();
-                            acc_used = 0;
+                            accumulate = 0;
                         }
-                        const uint32_t tmem_d = tmem_base + (uint32_t)(astage * 2 + s) * TG_BN;
-                        const uint32_t combos = (p.a_hiflag[s] && p.nA[s] == 2 && (p.a_hiflag[s][kb / 2] & 1u) == 0u) ? (p.combos[s] & 0x3u) : p.combos[s];
-                        mbar_wait_parked(smem_u32(&bar_full[stage]), phase);
-                        tc_fence_after();
-                        const uint32_t sa = smem_base + (uint32_t)stage * TG_STAGE, sb = sa + 2 * TG_PLANE;
-                        uint32_t accumulate = (acc_used >> s) & 1u;
+                        const uint32_t tmem_d = tmem_base + (uint32_t)(astage * HALVES) * TG_BN;
+                        uint32_t pm[2];
+                        pass_masks(s, kb, pm[0], pm[1]);
+                        for (int pa = 0; pa < 2; ++pa) {
+                            if (!pm[pa]) continue;
+                            mbar_wait_parked(smem_u32(&bar_full[stage]), phase);
+                            tc_fence_after();
+                            const uint32_t sa = smem_base + (uint32_t)stage * STAGE, sb = sa + HALVES * TG_PLANE;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            if (!((combos >> c) & 1u)) continue;
-                            const uint32_t a0 = sa + (c >> 1) * TG_PLANE, b0 = sb + (c & 1) * TG_PLANE;
+                            for (int h = 0; h < HALVES; ++h) {
+                                uint32_t acc_h = accumulate;
 #pragma unroll
-                            for (int k = 0; k < TC_BK / 16; ++k) {   // 16 samples = two 8-sample groups = 2 KB
-                                tc_mma_f16(tmem_d, umma_desc_mn_sw128(a0 + k * 2048), umma_desc_mn_sw128(b0 + k * 2048), IDESC, accumulate);
-                                accumulate = 1;
+                                for (int pb = 0; pb < 2; ++pb) {
+                                    if (!((pm[pa] >> pb) & 1u)) continue;
+#pragma unroll
+                                    for (int k = 0; k < TC_BK / 16; ++k) {   // 16 samples = two 8-sample groups = 2 KB
+                                        tc_mma_f16(tmem_d + h * TG_BN, umma_desc_mn_sw128(sa + h * TG_PLANE + k * 2048),
+                                                   umma_desc_mn_sw128(sb + pb * TG_PLANE + k * 2048), IDESC, acc_h);
+                                        acc_h = 1;
+                                    }
+                                }
                             }
+                            accumulate = 1;
+                            tc_commit(smem_u32(&bar_empty[stage]));
+                            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                         }
-                        acc_used |= 1u << s;
-                        tc_commit(smem_u32(&bar_empty[stage]));
-                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-                        ++done;
-                        if (++in_chunk == per || done == tkb) {
+                        if (++in_chunk == per || kb + 1 == hi) {
                             tc_commit(smem_u32(&bar_tfull[astage]));
                             if (++astage == 2) { astage = 0; aphase ^= 1u; }
                             in_chunk = 0;
@@ -1065,49 +1075,55 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
         uint32_t aphase = 0;
         for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
             const int tile = w / p.splits, sp = w % p.splits;
-            const int64_t m0 = (int64_t)(tile / p.n_tiles) * TC_BM, nn0 = (int64_t)(tile % p.n_tiles) * TG_BN;
-            int n0, tkb, nch, per;
-            chunking(sp, n0, tkb, nch, per);
-            float sum[32];
+            const int64_t m0 = (int64_t)(tile / p.n_tiles) * ROWS, nn0 = (int64_t)(tile % p.n_tiles) * TG_BN;
+            float sum[HALVES][32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) sum[i] = 0.0f;
-            for (int c = 0; c < nch; ++c) {
-                mbar_wait_epi(smem_u32(&bar_tfull[astage]), aphase);
-                tc_fence_after();
-                // which accumulators did this chunk write?  flattened k-blocks [c per, min((c+1) per, tkb)); source 0 owns [0, n0)
-                const int c_lo = c * per, c_hi = min((c + 1) * per, tkb);
-                const bool use0 = tkb > 0 && c_lo < n0, use1 = tkb > 0 && c_hi > n0;
-                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(astage * 2) * TG_BN + (uint32_t)(slice * 32);
+            for (int h = 0; h < HALVES; ++h)
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    uint32_t r0[16], r1[16];
-                    tmem_ld16(ta + g * 16, r0);
-                    tmem_ld16(ta + TG_BN + g * 16, r1);
-                    tmem_wait_ld();
+                for (int i = 0; i < 32; ++i) sum[h][i] = 0.0f;
+            for (int s = 0; s < 2; ++s) {
+                int lo, hi;
+                kb_range(s, sp, lo, hi);
+                const int n = hi - lo;
+                if (n <= 0) continue;
+                const int nch = (n + TC_CHUNK_KB - 1) / TC_CHUNK_KB;
+                const float sc = p.scale[s];
+                for (int c = 0; c < nch; ++c) {
+                    mbar_wait_epi(smem_u32(&bar_tfull[astage]), aphase);
+                    tc_fence_after();
+                    const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(astage * HALVES) * TG_BN + (uint32_t)(slice * 32);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float a0 = use0 ? __uint_as_float(r0[i]) : 0.0f;
-                        const float a1 = use1 ? __uint_as_float(r1[i]) : 0.0f;
-                        sum[g * 16 + i] += fmaf(p.scale[0], a0, p.scale[1] * a1);
-                    }
+                    for (int h = 0; h < HALVES; ++h)
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            uint32_t r[16];
+                            tmem_ld16(ta + h * TG_BN + g * 16, r);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) sum[h][g * 16 + i] = fmaf(sc, __uint_as_float(r[i]), sum[h][g * 16 + i]);
+                        }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[astage]));
+                    if (++astage == 2) { astage = 0; aphase ^= 1u; }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[astage]));
-                if (++astage == 2) { astage = 0; aphase ^= 1u; }
             }
-            const int64_t row = m0 + q * 32 + lane;
             float* dst = (p.splits > 1 ? p.partial + (int64_t)sp * p.V * p.H : p.out);
-            if (row < p.V) {
-                const int64_t c0 = nn0 + slice * 32;
-                float* d = dst + row * p.H + c0;
-                if (c0 + 32 <= p.H && (p.H & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0u) {
+            const int64_t c0 = nn0 + slice * 32;
+            const bool vec = c0 + 32 <= p.H && (p.H & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0u;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(d + i) = make_float4(sum[i], sum[i + 1], sum[i + 2], sum[i + 3]);
-                } else {
+            for (int h = 0; h < HALVES; ++h) {
+                const int64_t row = m0 + h * TC_BM + q * 32 + lane;
+                if (row < p.V) {
+                    float* d = dst + row * p.H + c0;
+                    if (vec) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c0 + i < p.H) d[i] = sum[i];
+                        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(d + i) = make_float4(sum[h][i], sum[h][i + 1], sum[h][i + 2], sum[h][i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c0 + i < p.H) d[i] = sum[h][i];
+                    }
                 }
             }
         }
@@ -1138,8 +1154,14 @@ inline bool tc_grad_supported(const TcGradArgs& a) {
 }
 
 // number of K splits that fills the GPU when there are few output tiles
+// 256-row work tiles when they still fill the GPU
+inline int tc_grad_halves(const TcGradArgs& a, int num_sms) {
+    const int64_t tiles2 = ((a.V + 2 * TC_BM - 1) / (2 * TC_BM)) * ((a.H + TG_BN - 1) / TG_BN);
+    return tiles2 >= num_sms ? 2 : 1;
+}
 inline int tc_grad_splits(const TcGradArgs& a, int num_sms) {
-    const int tiles = (int)((a.V + TC_BM - 1) / TC_BM) * (int)((a.H + TG_BN - 1) / TG_BN);
+    const int rows = tc_grad_halves(a, num_sms) * TC_BM;
+    const int tiles = (int)((a.V + rows - 1) / rows) * (int)((a.H + TG_BN - 1) / TG_BN);
     const int kb = (int)((a.v.rows + TC_BK - 1) / TC_BK);
     if (tiles >= num_sms) return 1;
     return std::max(1, std::min({(num_sms + tiles - 1) / tiles, kb / 4 + 1, 16}));
@@ -1150,9 +1172,10 @@ inline cudaError_t launch_grad_tc(TcContext& t, const TcGradArgs& a, int num_sms
     TcGradMaps maps;
     TcGradParams p;
     memset(&p, 0, sizeof(p));
+    const int halves = tc_grad_halves(a, num_sms);
     p.V = a.V; p.H = a.H;
     p.out = a.out; p.partial = a.partial; p.splits = std::max(1, a.splits);
-    p.m_tiles = (int)((a.V + TC_BM - 1) / TC_BM);
+    p.m_tiles = (int)((a.V + halves * TC_BM - 1) / (halves * TC_BM));
     p.n_tiles = (int)((a.H + TG_BN - 1) / TG_BN);
     p.scale[0] = a.pos_scale; p.scale[1] = a.neg_scale;
     const MatView* av[2] = {&a.v, &a.vm};
@@ -1176,15 +1199,18 @@ inline cudaError_t launch_grad_tc(TcContext& t, const TcGradArgs& a, int num_sms
         ok = ok && tc_make_map_mn(t, &maps.b[s][1], B.p1 ? B.p1 : B.p0, B.rows, a.H, B.ld);
         if (!ok) return cudaErrorInvalidValue;
     }
-    p.stages = 3;
-    const int smem = p.stages * TG_STAGE + 1024;
-    if (!t.attr_set[15]) {
-        cudaError_t e = cudaFuncSetAttribute(k_grad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    p.stages = halves == 2 ? 3 : 4;
+    const int smem = p.stages * tg_stage_bytes(halves) + 1024;
+    const int slot = halves == 2 ? 15 : 14;
+    if (!t.attr_set[slot]) {
+        cudaError_t e = halves == 2 ? cudaFuncSetAttribute(k_grad_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                                    : cudaFuncSetAttribute(k_grad_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        t.attr_set[15] = true;
+        t.attr_set[slot] = true;
     }
     const int nwork = p.m_tiles * p.n_tiles * p.splits;
-    k_grad_tc<<<std::min(nwork, num_sms), TG_THREADS, smem, stream>>>(maps, p);
+    if (halves == 2) k_grad_tc<2><<<std::min(nwork, num_sms), TG_THREADS, smem, stream>>>(maps, p);
+    else k_grad_tc<1><<<std::min(nwork, num_sms), TG_THREADS, smem, stream>>>(maps, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || p.splits == 1) return e;
     const int64_t n = a.V * a.H;
