@@ -119,7 +119,7 @@ static void ctx_release(scdbm_ctx* c) {
 struct Layer {
     int V = 0, H = 0, kind = SCDBM_VIS_BERNOULLI;
     float *W = nullptr, *a = nullptr, *b = nullptr, *r = nullptr;
-    __nv_bfloat16 *w0 = nullptr, *w1 = nullptr, *t0 = nullptr, *t1 = nullptr;  // W[V x ldh], Wt[H x ldv] hi/lo
+    plane_t *w0 = nullptr, *w1 = nullptr, *t0 = nullptr, *t1 = nullptr;  // W[V x ldh], Wt[H x ldv] hi/lo
     float4* nbc = nullptr;  // NB layer: per-gene {a, r, 1e-6/r, r-1}
     uint32_t* nbT = nullptr;   // NB layer: per-gene Philox-word threshold of the zero shortcut, padded with 0xFFFFFFFF
     float nbL_mu = -1.0f;   // mu_inv_max the bound was computed for
@@ -144,8 +144,8 @@ static void model_free(scdbm_model* m) {
     for (auto& L : m->L) {
         float* f[] = {L.W, L.a, L.b, L.r};
         for (float* p : f) if (p) cudaFreeAsync(p, st);
-        __nv_bfloat16* h[] = {L.w0, L.w1, L.t0, L.t1};
-        for (__nv_bfloat16* p : h) if (p) cudaFreeAsync(p, st);
+        plane_t* h[] = {L.w0, L.w1, L.t0, L.t1};
+        for (plane_t* p : h) if (p) cudaFreeAsync(p, st);
         if (L.nbc) cudaFreeAsync(L.nbc, st);
         if (L.nbT) cudaFreeAsync(L.nbT, st);
     }
@@ -234,7 +234,7 @@ static scdbm_mat* mat_new(scdbm_ctx* ctx, int64_t rows, int64_t cols, int kind) 
     m->v.cols = cols;
     m->v.ld = round_up(std::max<int64_t>(cols, 1), 64);
     m->v.kind = kind;
-    const size_t bytes = (size_t)std::max<int64_t>(rows, 1) * m->v.ld * sizeof(__nv_bfloat16);
+    const size_t bytes = (size_t)std::max<int64_t>(rows, 1) * m->v.ld * sizeof(plane_t);
     // stream-ordered pool allocations: repeated samples()/particles calls re-use the same memory
     CK(cudaMallocAsync(&m->v.p0, bytes, ctx->stream));
     CK(cudaMemsetAsync(m->v.p0, 0, bytes, ctx->stream));
@@ -689,7 +689,7 @@ int32_t scdbm_model_create(scdbm_ctx* c, int32_t nrbms, const int32_t* units, in
         CK(cudaMemsetAsync(L.a, 0, (size_t)L.V * sizeof(float), c->stream));
         CK(cudaMemsetAsync(L.b, 0, (size_t)L.H * sizeof(float), c->stream));
         k_fill_f32<<<grid1d(L.V), 256, 0, c->stream>>>(L.r, L.V, 1.0f);
-        const size_t wb = (size_t)L.V * L.ldh * sizeof(__nv_bfloat16), tb = (size_t)L.H * L.ldv * sizeof(__nv_bfloat16);
+        const size_t wb = (size_t)L.V * L.ldh * sizeof(plane_t), tb = (size_t)L.H * L.ldv * sizeof(plane_t);
         CK(cudaMallocAsync(&L.w0, wb, c->stream)); CK(cudaMallocAsync(&L.w1, wb, c->stream));
         CK(cudaMallocAsync(&L.t0, tb, c->stream)); CK(cudaMallocAsync(&L.t1, tb, c->stream));
         CK(cudaMemsetAsync(L.w0, 0, wb, c->stream)); CK(cudaMemsetAsync(L.w1, 0, wb, c->stream));
@@ -1024,7 +1024,7 @@ int32_t scdbm_mat_upload_compressed(scdbm_mat* m, int32_t major, const int64_t* 
     for (int64_t i = 0; i < nmajor; ++i) REQUIRE(ptr[i] <= ptr[i + 1], "pointer array must be non-decreasing");
     REQUIRE(nnz == 0 || (idx && val), "NULL index/value array");
     if (m->v.rows == 0 || m->v.cols == 0) return SCDBM_OK;
-    const size_t plane = (size_t)m->v.rows * m->v.ld * sizeof(__nv_bfloat16);
+    const size_t plane = (size_t)m->v.rows * m->v.ld * sizeof(plane_t);
     CK(cudaMemsetAsync(m->v.p0, 0, plane, c->stream));
     if (m->v.p1) CK(cudaMemsetAsync(m->v.p1, 0, plane, c->stream));
     if (m->v.f) CK(cudaMemsetAsync(m->v.f, 0, plane * 2, c->stream));

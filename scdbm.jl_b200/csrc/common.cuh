@@ -12,18 +12,19 @@ namespace scdbm {
 // ---- device state matrix: [rows x cols], row = chain/cell, unit-contiguous.
 // Stored as one or two FP16 "planes" whose SUM is the value, so that every state is directly a tcgen05
 // kind::f16 operand without conversion (A and B operands must share one 16-bit format; FP16 holds
-// integers to 2048 exactly, which keeps the second count plane empty for counts < 2048).  The plane
-// pointers are typed __nv_bfloat16 for historical reasons; the 16-bit words are IEEE fp16 everywhere.
+// integers to 2048 exactly, which keeps the second count plane empty for counts < 2048).
 //   BINARY : p0 in {0,1}                                   (exact)
 //   COUNT  : p0 = v mod 2048, p1 = v - p0 (multiple of 2048) -- exact to 65535, p1 != 0 only for counts >= 2048
 //   REAL   : p0 = fp16(v),   p1 = fp16(v - p0)             (22 significant bits in fp16's normal range)
 //            plus an fp32 master copy `f` (what downloads, mean-field deltas and the
 //            CUDA-core engine read; the planes are the tensor-core operands)
+using plane_t = __half;   // one 16-bit word of a state / weight plane: IEEE fp16
+
 enum MatKind : int32_t { MAT_BINARY = 0, MAT_COUNT = 1, MAT_REAL = 2 };
 
 struct MatView {
-    __nv_bfloat16* p0;
-    __nv_bfloat16* p1;     // nullptr for BINARY
+    plane_t* p0;
+    plane_t* p1;     // nullptr for BINARY
     float* f;              // fp32 master copy, REAL only (else nullptr)
     uint32_t* hiflag;      // COUNT only, per 128-row tile: bit 0 = the p1 (hi) plane may hold a non-zero entry (consumers read it),
                            // bit 1 = it may hold stale non-zeros (the NB sampling kernel zero-fills it before patching); 0 = all zero
@@ -83,8 +84,8 @@ struct EpiParams {
 // p0 + p1 (bf16 planes) or f (fp32).  `scale` multiplies the A operand of a
 // source (gradient: +1/n_pos, -1/n_neg).
 struct Operand {
-    const __nv_bfloat16* p0;
-    const __nv_bfloat16* p1;
+    const plane_t* p0;
+    const plane_t* p1;
     const float* f;
     int64_t s_mn, s_k;
     int32_t kind;          // MatKind of the planes

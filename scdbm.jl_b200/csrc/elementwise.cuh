@@ -20,12 +20,12 @@ __global__ void k_upload_f64(const double* __restrict__ src, int64_t lds, MatVie
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         const int64_t r = r0 + j, c = c0 + threadIdx.x;
         if (r < dst.rows && c < dst.cols) {
-            __nv_bfloat16 a, b;
+            plane_t a, b;
             split_value(dst.kind, t[threadIdx.x][j], a, b);
             dst.p0[r * dst.ld + c] = a;
             if (dst.p1) dst.p1[r * dst.ld + c] = b;
             if (dst.f) dst.f[r * dst.ld + c] = t[threadIdx.x][j];
-            if (dst.hiflag && (__bfloat16_as_ushort(b) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 3u;
+            if (dst.hiflag && (__half_as_ushort(b) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 3u;
         }
     }
 }
@@ -112,8 +112,8 @@ __global__ void k_weight_scale(const unsigned int* __restrict__ max_bits, float*
     scale[0] = exp2f((float)e);
     scale[1] = exp2f((float)-e);
 }
-__global__ void k_refresh_operands(const float* __restrict__ W, int V, int H, const float* __restrict__ scale, __nv_bfloat16* w0,
-                                   __nv_bfloat16* w1, int64_t ldh, __nv_bfloat16* t0, __nv_bfloat16* t1, int64_t ldv) {
+__global__ void k_refresh_operands(const float* __restrict__ W, int V, int H, const float* __restrict__ scale, plane_t* w0,
+                                   plane_t* w1, int64_t ldh, plane_t* t0, plane_t* t1, int64_t ldv) {
     __shared__ float t[32][33];
     const float s = scale[0];
     const int v0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
@@ -122,7 +122,7 @@ __global__ void k_refresh_operands(const float* __restrict__ W, int V, int H, co
         float x = 0.0f;
         if (v < V && h < H) {
             x = s * W[(int64_t)v * H + h];
-            const __nv_bfloat16 a = plane_encode(x);
+            const plane_t a = plane_encode(x);
             w0[(int64_t)v * ldh + h] = a;
             w1[(int64_t)v * ldh + h] = plane_encode(x - plane_decode(a));
         }
@@ -133,7 +133,7 @@ __global__ void k_refresh_operands(const float* __restrict__ W, int V, int H, co
         const int h = h0 + j, v = v0 + threadIdx.x;
         if (v < V && h < H) {
             const float x = t[threadIdx.x][j];
-            const __nv_bfloat16 a = plane_encode(x);
+            const plane_t a = plane_encode(x);
             t0[(int64_t)h * ldv + v] = a;
             t1[(int64_t)h * ldv + v] = plane_encode(x - plane_decode(a));
         }
@@ -192,8 +192,8 @@ __global__ void k_det_finish(const float* __restrict__ ws, int S, int64_t stride
 // grad: the layer's block {dW [V x H] row-major, da [V], db [H]}.
 __global__ void k_update_layer(float* __restrict__ W, float* __restrict__ a, float* __restrict__ b, const float* __restrict__ r,
                                const float* __restrict__ gW, const float* __restrict__ ga, const float* __restrict__ gb, int V, int H,
-                               float lr, int nb, const float* __restrict__ scale, __nv_bfloat16* w0, __nv_bfloat16* w1, int64_t ldh,
-                               __nv_bfloat16* t0, __nv_bfloat16* t1, int64_t ldv, unsigned int* __restrict__ wmax, float mu_inv_max,
+                               float lr, int nb, const float* __restrict__ scale, plane_t* w0, plane_t* w1, int64_t ldh,
+                               plane_t* t0, plane_t* t1, int64_t ldv, unsigned int* __restrict__ wmax, float mu_inv_max,
                                float4* __restrict__ nbc, uint32_t* __restrict__ nbT) {
     __shared__ float t[32][33];
     __shared__ float red[8];
@@ -210,7 +210,7 @@ __global__ void k_update_layer(float* __restrict__ W, float* __restrict__ a, flo
             W[i] = w;
             m = fmaxf(m, fabsf(w));
             x = s * w;
-            const __nv_bfloat16 hi = plane_encode(x);
+            const plane_t hi = plane_encode(x);
             w0[(int64_t)v * ldh + h] = hi;
             w1[(int64_t)v * ldh + h] = plane_encode(x - plane_decode(hi));
         }
@@ -221,7 +221,7 @@ __global__ void k_update_layer(float* __restrict__ W, float* __restrict__ a, flo
         const int h = h0 + j, v = v0 + threadIdx.x;
         if (v < V && h < H) {
             const float x = t[threadIdx.x][j];
-            const __nv_bfloat16 hi = plane_encode(x);
+            const plane_t hi = plane_encode(x);
             t0[(int64_t)h * ldv + v] = hi;
             t1[(int64_t)h * ldv + v] = plane_encode(x - plane_decode(hi));
         }
@@ -389,7 +389,7 @@ __global__ void k_gather_rows(MatView src, const int32_t* __restrict__ idx, MatV
     if (dst.hiflag && threadIdx.x == 0 && (r & 127) == 0) dst.hiflag[r >> 7] = any_hi ? *any_hi : 3u;
     for (int64_t c = threadIdx.x; c < dst.ld; c += blockDim.x) {
         dst.p0[r * dst.ld + c] = src.p0[s * src.ld + c];
-        if (dst.p1) dst.p1[r * dst.ld + c] = src.p1 ? src.p1[s * src.ld + c] : __ushort_as_bfloat16(0);
+        if (dst.p1) dst.p1[r * dst.ld + c] = src.p1 ? src.p1[s * src.ld + c] : __ushort_as_half(0);
         if (dst.f) dst.f[r * dst.ld + c] = src.f ? src.f[s * src.ld + c] : (c < src.cols ? mat_load(src, s, c) : 0.0f);
     }
 }
@@ -399,7 +399,7 @@ __global__ void k_copy_rows(MatView src, MatView dst, int64_t rows) {
     if (r >= rows) return;
     for (int64_t c = threadIdx.x; c < dst.ld; c += blockDim.x) {
         dst.p0[r * dst.ld + c] = src.p0[r * src.ld + c];
-        if (dst.p1) dst.p1[r * dst.ld + c] = src.p1 ? src.p1[r * src.ld + c] : __ushort_as_bfloat16(0);
+        if (dst.p1) dst.p1[r * dst.ld + c] = src.p1 ? src.p1[r * src.ld + c] : __ushort_as_half(0);
         if (dst.f) dst.f[r * dst.ld + c] = src.f ? src.f[r * src.ld + c] : (c < src.cols ? mat_load(src, r, c) : 0.0f);
     }
 }
@@ -502,7 +502,7 @@ __global__ void k_restore_cols(MatView dst, MatView orig, const int32_t* __restr
         const int64_t r = i / ncols, c = cols[i % ncols], j = r * dst.ld + c;
         dst.p0[j] = orig.p0[j];
         if (dst.p1) dst.p1[j] = orig.p1[j];
-        if (dst.hiflag && dst.p1 && (__bfloat16_as_ushort(orig.p1[j]) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 3u;
+        if (dst.hiflag && dst.p1 && (__half_as_ushort(orig.p1[j]) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 3u;
     }
 }
 __global__ void k_restore_mask(MatView dst, MatView orig, const uint8_t* __restrict__ mask) {   // mask row-major [rows x cols]
@@ -512,7 +512,7 @@ __global__ void k_restore_mask(MatView dst, MatView orig, const uint8_t* __restr
         const int64_t r = i / dst.cols, j = r * dst.ld + i % dst.cols;
         dst.p0[j] = orig.p0[j];
         if (dst.p1) dst.p1[j] = orig.p1[j];
-        if (dst.hiflag && dst.p1 && (__bfloat16_as_ushort(orig.p1[j]) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 3u;
+        if (dst.hiflag && dst.p1 && (__half_as_ushort(orig.p1[j]) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 3u;
     }
 }
 

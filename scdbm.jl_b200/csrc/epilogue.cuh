@@ -8,9 +8,9 @@
 namespace scdbm {
 
 // 16-bit plane word <-> float (IEEE fp16, saturating so that no plane ever holds Inf)
-__device__ __forceinline__ float plane_decode(__nv_bfloat16 w) { return __half2float(__ushort_as_half(__bfloat16_as_ushort(w))); }
-__device__ __forceinline__ __nv_bfloat16 plane_encode(float v) {
-    return __ushort_as_bfloat16(__half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f))));
+__device__ __forceinline__ float plane_decode(plane_t w) { return __half2float(w); }
+__device__ __forceinline__ plane_t plane_encode(float v) {
+    return __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
 }
 
 __device__ __forceinline__ float mat_load(const MatView& m, int64_t row, int64_t col) {
@@ -21,7 +21,7 @@ __device__ __forceinline__ float mat_load(const MatView& m, int64_t row, int64_t
     return v;
 }
 
-__device__ __forceinline__ void split_value(int kind, float v, __nv_bfloat16& a, __nv_bfloat16& b) {
+__device__ __forceinline__ void split_value(int kind, float v, plane_t& a, plane_t& b) {
     if (kind == MAT_COUNT) {
         const float hi = floorf(v * (1.0f / COUNT_BASE)) * COUNT_BASE;
         a = plane_encode(v - hi);
@@ -34,7 +34,7 @@ __device__ __forceinline__ void split_value(int kind, float v, __nv_bfloat16& a,
 
 // write up to 4 consecutive values; 8-byte vector store when all 4 are in range
 __device__ __forceinline__ void mat_store4(const MatView& m, int64_t row, int64_t col0, const float (&v)[4], int nvalid) {
-    __nv_bfloat16 a[4], b[4];
+    plane_t a[4], b[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) split_value(m.kind, v[j], a[j], b[j]);
     const int64_t i = row * m.ld + col0;
@@ -44,12 +44,12 @@ __device__ __forceinline__ void mat_store4(const MatView& m, int64_t row, int64_
     }
     if (nvalid == 4) {
         uint2 pa, pb;
-        pa.x = (uint32_t)__bfloat16_as_ushort(a[0]) | ((uint32_t)__bfloat16_as_ushort(a[1]) << 16);
-        pa.y = (uint32_t)__bfloat16_as_ushort(a[2]) | ((uint32_t)__bfloat16_as_ushort(a[3]) << 16);
+        pa.x = (uint32_t)__half_as_ushort(a[0]) | ((uint32_t)__half_as_ushort(a[1]) << 16);
+        pa.y = (uint32_t)__half_as_ushort(a[2]) | ((uint32_t)__half_as_ushort(a[3]) << 16);
         *reinterpret_cast<uint2*>(m.p0 + i) = pa;
         if (m.p1) {
-            pb.x = (uint32_t)__bfloat16_as_ushort(b[0]) | ((uint32_t)__bfloat16_as_ushort(b[1]) << 16);
-            pb.y = (uint32_t)__bfloat16_as_ushort(b[2]) | ((uint32_t)__bfloat16_as_ushort(b[3]) << 16);
+            pb.x = (uint32_t)__half_as_ushort(b[0]) | ((uint32_t)__half_as_ushort(b[1]) << 16);
+            pb.y = (uint32_t)__half_as_ushort(b[2]) | ((uint32_t)__half_as_ushort(b[3]) << 16);
             *reinterpret_cast<uint2*>(m.p1 + i) = pb;
         }
     } else {

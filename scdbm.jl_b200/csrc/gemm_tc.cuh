@@ -52,7 +52,7 @@ struct TcContext {
 
 struct TcOperandPlanes {
     MatView a;                       // state (1 or 2 planes)
-    const __nv_bfloat16 *b0, *b1;    // weight planes [N x ldb]
+    const plane_t *b0, *b1;    // weight planes [N x ldb]
     int64_t ldb, N, K;
 };
 

@@ -25,13 +25,13 @@ __global__ void k_scatter_compressed(const int64_t* __restrict__ ptr, const int3
             const bool ok = dst.kind == MAT_COUNT ? (v >= 0.0f && v <= 65535.0f && v == floorf(v))
                           : dst.kind == MAT_BINARY ? (v == 0.0f || v == 1.0f) : isfinite(v);
             if (!ok) { atomicOr(err, 2u); continue; }
-            __nv_bfloat16 a, hb;
+            plane_t a, hb;
             split_value(dst.kind, v, a, hb);
             const int64_t j = r * dst.ld + c;
             dst.p0[j] = a;
             if (dst.p1) dst.p1[j] = hb;
             if (dst.f) dst.f[j] = v;
-            if (dst.hiflag && (__bfloat16_as_ushort(hb) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 3u;
+            if (dst.hiflag && (__half_as_ushort(hb) & 0x7FFFu) != 0) dst.hiflag[r / 128] = 3u;
         }
     }
 }
