@@ -441,9 +441,9 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
         uint16_t* s_lo = reinterpret_cast<uint16_t*>(S + TC_SCAP);                  // [32][CW] fp16 staging tile, 16 B aligned
         float4* sN = reinterpret_cast<float4*>(s_lo + 32 * CW);                     // the slice's {a, r, 1e-6/r, r-1}
         uint32_t* sT = reinterpret_cast<uint32_t*>(sN + CW);                        // the slice's pass-A thresholds
-        int64_t flag_m0 = -1;
+        int32_t flag_tile = -1;
         bool dirty = true;
-        int64_t cur_m0 = 0;
+        uint32_t cur_m0 = 0;      // (the NB class addresses rows with 32 bits: M < 2^31)
         uint32_t cur_c0 = 0;                                                        // global column of the warp's slice
         const uint32_t lt = (1u << lane) - 1u;
         const float acc_scale = p.epi.acc_scale ? __ldg(p.epi.acc_scale) : 1.0f;   // 1/s of the fp16 weight planes
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
         auto put_big = [&](float k, int idx) {
             const EpiParams& e = p.epi;
             const float hi = floorf(k * (1.0f / COUNT_BASE)) * COUNT_BASE;
-            const int64_t r2 = cur_m0 + q * 32 + idx / CW, c2 = (int64_t)cur_c0 + idx % CW;
+            const int64_t r2 = (int64_t)cur_m0 + q * 32 + idx / CW, c2 = (int64_t)cur_c0 + idx % CW;
             if (r2 < p.M && c2 < p.N) {
                 e.out.p1[r2 * e.out.ld + c2] = plane_encode(hi);
                 if (e.out.hiflag) e.out.hiflag[r2 / TC_BM] = 3u;
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     if (x > -0.125f)
                         om = -x * fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, 1.0f / 720.0f, 1.0f / 120.0f), 1.0f / 24.0f), 1.0f / 6.0f), 0.5f), 1.0f);
                     if (c.y * E > mu_lim * om) {                                      // mean above mu_inv_max: gamma-Poisson, out of line
-                        const RngAddr g{e.k0, e.k1, (uint32_t)(cur_m0 + q * 32 + idx / CW) + e.row_offset, col, e.tick, e.stream & 0xFFu};
+                        const RngAddr g{e.k0, e.k1, cur_m0 + (uint32_t)(q * 32 + idx / CW) + e.row_offset, col, e.tick, e.stream & 0xFFu};
                         put(nb_draw_slow(x, c.y, u, e.pshift, e.mu_inv_max, g), idx);
                     } else {
                         const float pp = om * fast_rcp(fmaf(c.z, om, 1.0f)) - e.pshift;
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 // lo count plane: staged in the warp's shared-memory tile (zeroed here, patched by pass B, written
                 // out coalesced at the end of the tile).  hi plane (counts >= 2048, rare): coalesced zero-fill now where
                 // the row tile is marked (full 32 B sectors: 4 lanes x 16 B per row, 8 rows per store), scattered patches from pass B.
-                cur_m0 = m0; cur_c0 = (uint32_t)n0 + (uint32_t)(slice * CW);
+                cur_m0 = (uint32_t)m0; cur_c0 = (uint32_t)n0 + (uint32_t)(slice * CW);
                 const MatView& o = p.epi.out;
                 // per-gene constants of this slice (both tables are padded past the last tile): loads issued now, parked in
                 // shared memory after the zero-fill
@@ -584,8 +584,8 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 if (lane < CW) { cn = __ldg(p.epi.nbc + cur_c0 + lane); ct = __ldg(p.epi.nbT + cur_c0 + lane); }
                 // the hi plane of a row tile is all zero unless its flag says otherwise (bit 1: stale entries of an earlier
                 // sweep); read once per row tile -- a flag raised by this launch marks entries written into a clean plane
-                if (m0 != flag_m0) {
-                    flag_m0 = m0;
+                if (tile / p.n_tiles != flag_tile) {
+                    flag_tile = tile / p.n_tiles;
                     dirty = !o.hiflag || (*reinterpret_cast<const volatile uint32_t*>(o.hiflag + m0 / TC_BM) & 2u) != 0u;
                 }
 #pragma unroll
