@@ -218,6 +218,34 @@ def gibbssample_dbm(particles, dbm, rng, nsteps=5, temperature=1.0, mu_inv_max=s
     return particles
 
 
+def sampleparticles_native(dbm, nparticles, gen, burnin=10):
+    """TIMING twin of `sampleparticles` for a DBM (bench.py's CPU baseline): the same operation sequence as the
+    reference (src/gibbssampling.jl:646-650,153-182,512-531,810-820) -- dgemm, NB mean, one `NegativeBinomial(r, p)`
+    draw per visible element, `rand() < p` per hidden unit -- with the draws taken from NumPy's own compiled samplers
+    (`Generator.negative_binomial`, what Distributions.jl's samplers are to the reference) instead of the
+    Philox-addressed inversion the parity tests need.  Never used as a checker."""
+    first = dbm[0]
+    r = first.inversedispersion[None, :]
+    V = first.weights.shape[0]
+    v0 = gen.negative_binomial(1.0, 0.5, (nparticles, V)).astype(float)                    # :515
+    mu0 = v0 + 1e-6
+    parts = [gen.negative_binomial(np.broadcast_to(r, mu0.shape), np.clip(r / (mu0 + r) - 1e-6, 1e-12, 1.0)).astype(float)]
+    for rbm in dbm:
+        parts.append((gen.random((nparticles, rbm.weights.shape[1])) < 0.5).astype(float))  # :428
+    L = len(parts)
+    for _ in range(burnin):
+        new = [None] * L
+        mu = visiblepotential(first, parts[1])                                               # :1018
+        new[0] = gen.negative_binomial(np.broadcast_to(r, mu.shape), r / (mu + r)).astype(float)   # :814-818
+        for i in range(1, L - 1):
+            p = sigm(dbm_layer_input(dbm, parts, i))
+            new[i] = (gen.random(p.shape) < p).astype(float)
+        p = hiddenpotential(dbm[-1], parts[L - 2])
+        new[L - 1] = (gen.random(p.shape) < p).astype(float)
+        parts = new
+    return parts
+
+
 def _annealed(rbm, temperature):
     r = copy.copy(rbm)
     r.weights = rbm.weights * temperature
