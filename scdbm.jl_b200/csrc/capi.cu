@@ -4,6 +4,7 @@
 #include "elementwise.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 #include "sparse.cuh"
 #include "comm.cuh"
 
@@ -67,6 +68,7 @@ struct scdbm_ctx {
     int64_t launches = 0;
     int64_t tc_launches = 0;
     int num_sms = 148;
+    bool use_cg2 = true;    // two-SM (cta_group::2) sweep kernel for the L2-operand-bound Bernoulli / deterministic sweeps
     TcContext tc;
     float* scratch = nullptr;   // reduction workspace (column-sum partials)
     int64_t scratch_cap = 0;
@@ -370,6 +372,8 @@ static void run_gemm(scdbm_ctx* ctx, GemmArgs& g, const SweepSrc* srcs, int nsrc
             k_det_finish<<<(unsigned)((nthreads + 127) / 128), 128, 0, ctx->stream>>>(ctx->scratch, S, stride, ldw, g.epi, g.M, g.N);
             CK(cudaGetLastError());
             ctx->launches++;
+        } else if (ctx->use_cg2 && tc_cg2_eligible(g, ops, nsrc, ctx->num_sms)) {
+            CK(launch_gemm_cg2(ctx->tc, ops, nsrc, g, ctx->num_sms, ctx->stream));
         } else {
             CK(launch_gemm_tc(ctx->tc, ops, nsrc, g, ctx->num_sms, ctx->stream));
         }
@@ -559,6 +563,7 @@ int32_t scdbm_ctx_create(int32_t device, uint64_t seed, void* stream, scdbm_ctx*
     c->device = device;
     c->seed = seed;
     c->num_sms = prop.multiProcessorCount;
+    if (const char* v = getenv("SCDBM_CG2")) c->use_cg2 = v[0] == '1';
     if (stream) c->stream = (cudaStream_t)stream;
     else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     CK(cudaEventCreate(&c->ev0));
@@ -605,6 +610,7 @@ int32_t scdbm_ctx_set_option(scdbm_ctx* c, const char* name, double value) {
     else if (n == "mu_inv_max") c->mu_inv_max = (float)value;
     else if (n == "nb_pshift") c->nb_pshift = (float)value;
     else if (n == "seed") c->seed = (uint64_t)value;
+    else if (n == "two_sm") c->use_cg2 = value != 0.0;
     else throw Err(SCDBM_EINVAL, "unknown option: " + n);
     API_END
 }
@@ -617,6 +623,7 @@ int32_t scdbm_ctx_get_option(scdbm_ctx* c, const char* name, double* value) {
     else if (n == "mu_inv_max") *value = c->mu_inv_max;
     else if (n == "nb_pshift") *value = c->nb_pshift;
     else if (n == "seed") *value = (double)c->seed;
+    else if (n == "two_sm") *value = c->use_cg2 ? 1.0 : 0.0;
     else if (n == "num_sms") *value = c->num_sms;
     else if (n == "tc_launches") *value = (double)c->tc_launches;
     else if (n == "comm_rank") *value = c->rank;

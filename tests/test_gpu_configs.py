@@ -295,3 +295,60 @@ def test_pair_mode_with_chunked_accumulation(pkg, auto):
     e_pot = relerr(pkg.hiddenpotential(m, x, 2.0, ctx=auto), om.hiddenpotential(dbm[0], x, 2.0), 1e-7)
     print(f"[pair + chunks] hiddeninput {e_in:.2e}, hiddenpotential {e_pot:.2e}")
     assert e_in < RTOL and e_pot < RTOL
+
+
+# ------------------------------------------------------------ two-SM (cta_group::2) sweep kernel
+@pytest.fixture()
+def two_sm(pkg):
+    """A context whose wide Bernoulli / deterministic sweeps run the cta_group::2 kernel (csrc/gemm_tc2.cuh)."""
+    c = pkg.Context(0, SEED)
+    c.set("two_sm", 1)
+    assert c.get("two_sm") == 1.0
+    return c
+
+
+def test_two_sm_deterministic_sweeps(pkg, two_sm):
+    """256 x 256 cluster tiles, ragged in rows and width, count data with a >= 2048 entry in the LAST row tile
+    (hi-plane pass of one cluster tile only), K long enough for chunk-promoted accumulation; dual-source DBM layer."""
+    n, V, H, H2 = 256 * 40 + 77, 5000, 300, 40
+    dbm = synth.random_dbm([V, H, H2], 13)
+    m = pkg.DeviceModel.from_host(to_pkg_model(pkg, dbm), two_sm)
+    g = np.random.default_rng(5)
+    x = g.poisson(0.3, (n, V)).astype(float)
+    x[n - 3, 11] = 4000.0
+    x[300, 4999] = 2049.0
+    before = two_sm.get("tc_launches")
+    e_in = relerr(pkg.hiddeninput(m, x, ctx=two_sm), om.hiddeninput(dbm[0], x), 1e-6)
+    e_pot = relerr(pkg.hiddenpotential(m, x, 2.0, ctx=two_sm), om.hiddenpotential(dbm[0], x, 2.0), 1e-7)
+    assert two_sm.get("tc_launches") - before == 2
+    h2 = (g.random((n, H2)) < 0.5).astype(float)
+    xin = om.dbm_layer_input(dbm, [x, None, h2], 1)
+    e_dbm = relerr(pkg.dbmlayer(m, 1, x, h2, what=pkg.OUT_INPUT, ctx=two_sm), xin, 0.05 * np.abs(xin).max())
+    e_dbp = relerr(pkg.dbmlayer(m, 1, x, h2, ctx=two_sm), osp.sigm(xin), 1e-7)
+    print(f"[two-SM] hiddeninput {e_in:.2e}, hiddenpotential {e_pot:.2e}, dbm layer input {e_dbm:.2e}, potential {e_dbp:.2e}")
+    assert max(e_in, e_pot, e_dbm, e_dbp) < RTOL
+
+
+def test_two_sm_bernoulli_draws_match_single_sm(pkg, two_sm, auto):
+    """Same seed, same tick: the two-SM kernel and the single-SM kernel consume the same Philox words against the same
+    potentials -- identical samples up to potentials that differ in the last bit next to a uniform (gate G2), and the
+    samples match the oracle's draws from the same uniforms."""
+    n, V, H, H2 = 256 * 38 + 5, 700, 520, 64
+    dbm = synth.random_dbm([V, H, H2], 17)
+    g = np.random.default_rng(7)
+    x = g.poisson(0.5, (n, V)).astype(float)
+    h2 = (g.random((n, H2)) < 0.5).astype(float)
+    outs = []
+    for c in (two_sm, auto):
+        c.set("seed", SEED)
+        m = pkg.DeviceModel.from_host(to_pkg_model(pkg, dbm), c)
+        outs.append((pkg.samplehidden(m, x, 1.0, tick=77, ctx=c), pkg.dbmlayer(m, 1, x, h2, what=pkg.OUT_SAMPLE, tick=78, ctx=c)))
+    for a, b in zip(*outs):
+        assert set(np.unique(a)) <= {0.0, 1.0}
+        mism = float(np.mean(a != b))
+        print(f"[two-SM] Bernoulli draws differing from the single-SM kernel: {mism:.2e}")
+        assert mism < 1e-5
+    # statistics against the potential (gate G3): per-unit mean within 5 sigma
+    pot = om.hiddenpotential(dbm[0], x)
+    z = (outs[0][0].mean(0) - pot.mean(0)) / np.sqrt((pot * (1 - pot)).mean(0) / n + 1e-12)
+    assert np.abs(z).max() < 5.0
