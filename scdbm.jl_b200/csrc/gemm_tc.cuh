@@ -79,7 +79,17 @@ constexpr int TC_MAX_STAGES = 8;
 #define SCDBM_NB_EPW 28
 #endif
 constexpr int TC_QCAP = 192, TC_SCAP = 64, TC_NB_STEPS = SCDBM_NB_STEPS;
-constexpr int TC_NB_EPW = SCDBM_NB_EPW, TC_NB_BN = 8 * TC_NB_EPW;
+#ifndef SCDBM_NB_DYN      // 1: the epilogue warps of a row quadrant claim (tile, slice) items dynamically
+#define SCDBM_NB_DYN 1
+#endif
+#ifndef SCDBM_NB_CW       // columns per epilogue warp and tile of the wide NB kernel (16 or 32)
+#define SCDBM_NB_CW 32
+#endif
+#ifndef SCDBM_NB_ASTAGES  // its TMEM accumulator stages (stages x tile width <= 512 columns)
+#define SCDBM_NB_ASTAGES 2
+#endif
+constexpr int TC_NB_EPW = SCDBM_NB_EPW, TC_NB_BN = (SCDBM_NB_CW / 4) * TC_NB_EPW;
+static_assert(SCDBM_NB_ASTAGES * TC_NB_BN <= 512, "NB kernel: accumulator stages exceed TMEM");
 // ... and the slice's per-gene constants (nbc: 16 B, threshold: 4 B per column): with the shared-memory carve-out at its
 // maximum the L1 is too small to keep the per-gene tables, and every gather from them was an L2 round trip
 __host__ __device__ constexpr int tc_epi_smem(int cw) { return TC_QCAP * 8 + TC_SCAP * 16 + 32 * cw * 2 + cw * 20; }
@@ -293,14 +303,15 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
     constexpr int NS = EPW / 4;          // column slices per tile
     constexpr int CW = BN / NS;          // columns per epilogue warp per tile (16 or 32)
     constexpr int B_TILE = BN * TC_BK * 2;
-    constexpr int ASTAGES = 2;    // TMEM accumulator stages (4 x 128 = all 512 columns; 4 x 64 = 256)
+    constexpr int ASTAGES = (EK == 1 && BN == TC_NB_BN) ? SCDBM_NB_ASTAGES : 2;    // TMEM accumulator stages
     constexpr uint32_t TMEM_COLS = (EK == 1) ? ((ASTAGES * BN <= 256) ? 256 : 512) : ((2 * ASTAGES * BN <= 256) ? 256 : 512);
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // c = F32, a = b = F16, K-major
     static_assert(CW == 16 || CW == 32, "epilogue slice must be 16 or 32 columns");
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_tfull[2], bar_tempty[2];
+    __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_tfull[4], bar_tempty[4];
     __shared__ uint32_t tmem_holder;
+    __shared__ int dyn_item[4];     // EK == 1: next (tile, slice) item of each row quadrant
     if constexpr (EK == 0 || EK == 3) {
         if (p.epi.skip && *p.epi.skip) return;   // speculatively launched mean-field iteration after convergence (whole grid)
     }
@@ -321,6 +332,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
             mbar_init(smem_u32(&bar_tfull[i]), 1);
             mbar_init(smem_u32(&bar_tempty[i]), EPW);
         }
+        for (int i = 0; i < 4; ++i) dyn_item[i] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     } else if (svc == 2) {
@@ -564,13 +576,30 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
             if (sn > 0) { stage2(0, sn); sn = 0; }
             __syncwarp();
         };
-        for (int it = 0, work; (work = tc_tile(p, it)) >= 0; ++it) {
+        for (int it0 = 0;; ++it0) {
+            int it = it0, dyn_slice = 0;
+            if constexpr (EK == 1 && SCDBM_NB_DYN) {
+                // NB draw: the cost of a 32-row x CW-gene block follows its genes (zero fraction, search length), so a static
+                // warp -> slice map leaves warps waiting for the slowest one of their tile (20 % of the warp samples in capture
+                // prof_r02c sat in the accumulator wait).  The NS warps of a row quadrant instead claim (tile, slice) items in
+                // order from a shared counter.  A warp claiming an item of tile `it` implies an item of tile it-1 was finished
+                // (NS items, NS-1 other warps), hence every earlier phase of this TMEM stage's barrier has completed.
+                int item = 0;
+                if (lane == 0) item = atomicAdd(&dyn_item[q], 1);
+                item = __shfl_sync(0xffffffffu, item, 0);
+                it = item / NS;
+                dyn_slice = item % NS;
+                astage = it % ASTAGES;
+                aphase = (uint32_t)(it / ASTAGES) & 1u;
+            }
+            const int work = tc_tile(p, it);
+            if (work < 0) break;
             int tile, klo, khi;
             tc_split_range(p, work, EK == 1 ? 0 : tc_tile_kblocks(p, (p.ksplit > 1 ? work / p.ksplit : work) / p.n_tiles), tile, klo, khi);
             const int64_t row_shift = p.ksplit > 1 ? (int64_t)(work % p.ksplit) * p.M : 0;    // split-K: slab of raw partial sums
             const int halves = (EK != 1 && p.pair) ? 2 : 1;
             const int64_t m0 = (int64_t)(tile / p.n_tiles) * (TC_BM * halves), n0 = (int64_t)(tile % p.n_tiles) * BN;
-            slice = ((warp >> 2) + it) % NS;
+            slice = (EK == 1 && SCDBM_NB_DYN) ? dyn_slice : ((warp >> 2) + it) % NS;
             if constexpr (EK == 1) {
                 // lo count plane: staged in the warp's shared-memory tile (zeroed here, patched by pass B, written
                 // out coalesced at the end of the tile).  hi plane (counts >= 2048, rare): coalesced zero-fill now where
