@@ -46,11 +46,11 @@ def kernel(r):
 
 
 out = {"capture": os.path.basename(a.report), "commit": a.commit, "kernel_source_sha": bench.kernel_source_hash(), "chains": a.chains,
-       "command": f"ncu --set full --clock-control none --import-source on -k regex:k_gemm_tc -s 6 -c 3 python profiles/prof_visible.py --chains {a.chains} --sweeps 3",
+       "command": f"ncu --set full --clock-control none --import-source on -k regex:k_gemm_ -s 6 -c 3 python profiles/prof_visible.py --chains {a.chains} --sweeps 3",
        "note": "counters of ONE capture, cold-cache and serialised under ncu; not measured by the bench run that quotes them"}
 for r in rows[2:]:
     name = r[ix["Kernel Name"]]
-    key = "nb_downsweep" if "224, 1, 28" in name else "upsweep" if "128, 2, 16" in name else "top_layer" if "64, 2, 16" in name else None
+    key = "nb_downsweep" if "224, 1, 28" in name else "upsweep" if ("k_gemm_cg2<2>" in name.replace("(int)", "") or "128, 2, 16" in name) else "top_layer" if "64, 2, 16" in name else None
     if key and key not in out:
         out[key] = kernel(r)
         if key == "nb_downsweep":

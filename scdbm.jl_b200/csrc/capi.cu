@@ -222,8 +222,8 @@ static void colsum(scdbm_ctx* c, const MatView& m, float scale, float* out, bool
         c->scratch_cap = need;
     }
     dim3 grid((unsigned)((m.cols + 31) / 32), (unsigned)nslabs), block(32, 8);
-    k_colsum_partial<<<grid, block, 0, c->stream>>>(m, c->scratch);
-    k_colsum_final<<<(unsigned)((m.cols + 127) / 128), 128, 0, c->stream>>>(c->scratch, nslabs, m.cols, scale, out, accumulate ? 1 : 0);
+    CK(launch_pdl(k_colsum_partial, dim3(grid), dim3(block), 0, c->stream, m, c->scratch));
+    CK(launch_pdl(k_colsum_final, dim3((unsigned)((m.cols + 127) / 128)), dim3(128), 0, c->stream, c->scratch, nslabs, m.cols, scale, out, accumulate ? 1 : 0));
     c->launches += 2;
 }
 
@@ -345,7 +345,7 @@ static void run_gemm(scdbm_ctx* ctx, GemmArgs& g, const SweepSrc* srcs, int nsrc
         // other writer of a COUNT matrix marks all row tiles as "hi plane possibly in use"
         if (tc_epilogue_class(g, ops, nsrc) == 1 && g.epi.out.hiflag) {
             const int64_t nt = (std::max<int64_t>(g.epi.out.rows, 1) + 127) / 128;
-            k_flags_advance<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(g.epi.out.hiflag, nt);
+            CK(launch_pdl(k_flags_advance, dim3((unsigned)((nt + 255) / 256)), dim3(256), 0, ctx->stream, g.epi.out.hiflag, nt));
             ctx->launches++;
         } else {
             set_hiflags(ctx, g.epi.out, true);
@@ -369,7 +369,7 @@ static void run_gemm(scdbm_ctx* ctx, GemmArgs& g, const SweepSrc* srcs, int nsrc
             gp.epi.bias0 = gp.epi.bias1 = nullptr;
             CK(launch_gemm_tc(ctx->tc, ops, nsrc, gp, ctx->num_sms, ctx->stream, S));
             const int64_t nthreads = g.M * ((g.N + 3) / 4);
-            k_det_finish<<<(unsigned)((nthreads + 127) / 128), 128, 0, ctx->stream>>>(ctx->scratch, S, stride, ldw, g.epi, g.M, g.N);
+            CK(launch_pdl(k_det_finish, dim3((unsigned)((nthreads + 127) / 128)), dim3(128), 0, ctx->stream, ctx->scratch, S, stride, ldw, g.epi, g.M, g.N));
             CK(cudaGetLastError());
             ctx->launches++;
         } else if (ctx->use_cg2 && tc_cg2_eligible(g, ops, nsrc, ctx->num_sms)) {
@@ -1166,7 +1166,7 @@ int32_t scdbm_mat_copy(scdbm_mat* dst, const scdbm_mat* src) {
     REQUIRE(dst->v.kind == src->v.kind, "kinds differ");
     if (dst->v.rows == 0) return SCDBM_OK;
     set_hiflags(dst->ctx, dst->v, true);
-    k_copy_rows<<<(unsigned)dst->v.rows, 128, 0, dst->ctx->stream>>>(src->v, dst->v, dst->v.rows);
+    CK(launch_pdl(k_copy_rows, dim3((unsigned)dst->v.rows), dim3(128), 0, dst->ctx->stream, src->v, dst->v, dst->v.rows));
     CK(cudaGetLastError());
     dst->ctx->launches++;
     API_END
@@ -1403,6 +1403,8 @@ int32_t scdbm_particles_visible_potential(scdbm_model* m, scdbm_particles* p, sc
 // after one mean-field iteration: fold this iteration's max |change| into the convergence state.  One thread.
 //   st[0] delta bits of the iteration (reset), st[1] converged flag, st[2] iterations run, st[3] delta bits of the last one
 __global__ void k_mf_check(unsigned int* st, float eps, unsigned int* host_mirror) {
+    pdl_trigger();
+    pdl_wait();
     if (st[1] == 0u) {
         const float delta = __uint_as_float(st[0]);
         st[2] += 1u;
@@ -1522,7 +1524,7 @@ static void meanfield_impl(scdbm_model* m, const scdbm_mat* x, double eps, int m
             }
             // non-negative floats order like their bit patterns: max over ranks of the uint32 word
             if (global_delta) nccl_check(nccl_api().AllReduce(c->d_mf, c->d_mf, 1, ncclUint32, ncclMax, c->comm, c->stream), "ncclAllReduce(max delta)");
-            k_mf_check<<<1, 1, 0, c->stream>>>(c->d_mf, (float)eps, c->d_hmf);
+            CK(launch_pdl(k_mf_check, dim3(1), dim3(1), 0, c->stream, c->d_mf, (float)eps, c->d_hmf));
             c->launches++;
         }
         launched += group;
@@ -1647,7 +1649,7 @@ static void gradient_biases(scdbm_opt* o, int l, const MatView& v, const MatView
     float* ga = o->buf + o->offA[l];
     float* gb = o->buf + o->offB[l];
     if (std::max(v.rows, vm.rows) <= 2048) {
-        k_bias_grad<<<(unsigned)((L.V + L.H + 31) / 32), dim3(32, 32), 0, c->stream>>>(v, vm, h, hm, pos_scale, neg_scale, ga, gb);
+        CK(launch_pdl(k_bias_grad, dim3((unsigned)((L.V + L.H + 31) / 32)), dim3(32, 32), 0, c->stream, v, vm, h, hm, pos_scale, neg_scale, ga, gb));
         CK(cudaGetLastError());
         c->launches++;
         return;
@@ -1749,14 +1751,14 @@ static void update_layer(scdbm_model* m, scdbm_opt* o, int l, float lr) {
 // orientations, NB sampling constants) after a one-thread kernel that fixes the round's weight scale
 static void update_all_layers(scdbm_model* m, scdbm_opt* o, float lr) {
     scdbm_ctx* c = m->ctx;
-    k_weight_scale_next<<<1, 1, 0, c->stream>>>(m->d_wmax, m->d_scale);
+    CK(launch_pdl(k_weight_scale_next, dim3(1), dim3(1), 0, c->stream, m->d_wmax, m->d_scale));
     for (int l = 0; l < (int)m->L.size(); ++l) {
         Layer& L = m->L[l];
         const bool nb = L.kind == SCDBM_VIS_NEGBIN;
         dim3 grid((L.V + 31) / 32, (L.H + 31) / 32), block(32, 8);
-        k_update_layer<<<grid, block, 0, c->stream>>>(L.W, L.a, L.b, L.r, o->buf + o->offW[l], o->buf + o->offA[l], o->buf + o->offB[l], L.V, L.H,
+        CK(launch_pdl(k_update_layer, dim3(grid), dim3(block), 0, c->stream, L.W, L.a, L.b, L.r, o->buf + o->offW[l], o->buf + o->offA[l], o->buf + o->offB[l], L.V, L.H,
                                                      lr, nb ? 1 : 0, m->d_scale, L.w0, L.w1, L.ldh, L.t0, L.t1, L.ldv, m->d_wmax, c->mu_inv_max,
-                                                     L.nbc, L.nbT);
+                                                     L.nbc, L.nbT));
         if (nb) L.nbL_mu = c->mu_inv_max;
     }
     CK(cudaGetLastError());
@@ -1897,14 +1899,14 @@ int32_t scdbm_rbm_train_epoch(scdbm_trainer* t, const scdbm_mat* x, const int32_
         const int64_t thisb = std::min<int64_t>(B, n - s);
         const int64_t mrows = t->pcd ? B : thisb;  // PCD keeps the full chain (rbmtraining.jl:548-553)
         MatView v = rows_view(t->v->v, thisb), h = rows_view(t->h->v, thisb);
-        k_gather_rows<<<(unsigned)thisb, 128, 0, c->stream>>>(x->v, t->d_perm + s, v, x->v.hiflag ? t->d_anyhi : nullptr);   // sets the hi-plane flags of v
+        CK(launch_pdl(k_gather_rows, dim3((unsigned)thisb), dim3(128), 0, c->stream, x->v, t->d_perm + s, v, x->v.hiflag ? t->d_anyhi : nullptr));   // sets the hi-plane flags of v
         c->launches++;
         DrawCfg d;
         op_hidden(m, t->l, v, h, up, SCDBM_OUT_POTENTIAL, d);                         // :556
         MatView prob = t->pcd ? t->chain->v : h;                                       // :561-565
         MatView hs = rows_view(t->hs->v, mrows);
         DrawAddr da{(uint32_t)c->seed, (uint32_t)(c->seed >> 32), (uint32_t)t->clock, stream_id(1), 0u, nullptr, 0};
-        k_bernoulli<<<grid1d(mrows * ((L.H + 3) / 4)), 256, 0, c->stream>>>(rows_view(prob, mrows), hs, da);  // :567
+        CK(launch_pdl(k_bernoulli, dim3(grid1d(mrows * ((L.H + 3) / 4))), dim3(256), 0, c->stream, rows_view(prob, mrows), hs, da));  // :567
         c->launches++;
         t->clock++;
         MatView vs = rows_view(t->vs->v, mrows);
@@ -1923,7 +1925,7 @@ int32_t scdbm_rbm_train_epoch(scdbm_trainer* t, const scdbm_mat* x, const int32_
             MatView dstv = t->est->v;
             dstv.p0 += s * dstv.ld; dstv.p1 += s * dstv.ld; dstv.f += s * dstv.ld;
             dstv.rows = cnt;
-            k_copy_rows<<<(unsigned)cnt, 128, 0, c->stream>>>(vm, dstv, cnt);
+            CK(launch_pdl(k_copy_rows, dim3((unsigned)cnt), dim3(128), 0, c->stream, vm, dstv, cnt));
             c->launches++;
         }
         MatView hm = t->pcd ? t->chain->v : rows_view(t->hm->v, mrows);
@@ -2109,7 +2111,7 @@ int32_t scdbm_gibbs_cond(scdbm_model* m, scdbm_particles* p, const uint8_t* mask
     uint8_t* d_mask = nullptr;
     int ncols = 0;
     try {
-        k_copy_rows<<<(unsigned)p->n, 128, 0, c->stream>>>(p->cur[0]->v, orig->v, p->n);
+        CK(launch_pdl(k_copy_rows, dim3((unsigned)p->n), dim3(128), 0, c->stream, p->cur[0]->v, orig->v, p->n));
         c->launches++;
         if (mask_rows == 0) {
             std::vector<int32_t> cols;

@@ -5,6 +5,8 @@
 #include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <utility>
 #include <string>
 
 namespace scdbm {
@@ -31,6 +33,34 @@ struct MatView {
     int64_t rows, cols, ld; // ld (elements) is a multiple of 64
     int32_t kind;
 };
+
+// ---- programmatic dependent launch.  The latency-bound training loops (BASELINE configs C1 / C2) are chains of ~10 small
+// dependent kernels per minibatch; a plain stream launch leaves the GPU idle for the launch latency between each pair.
+// Kernels launched through launch_pdl may become resident while their predecessor still runs: they set up (barriers,
+// TMEM), call pdl_wait() -- which returns once the predecessor grid has completed and its writes are visible -- and only then
+// touch global memory.  pdl_trigger() lets the successor start its own set-up; it is issued only after this CTA holds every
+// resource it needs (TMEM), so a successor can never starve a predecessor.  Both are no-ops in a plainly launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool& pdl_enabled() {
+    static bool on = [] { const char* v = getenv("SCDBM_PDL"); return !(v && v[0] == '0'); }();
+    return on;
+}
+// launch `kernel` with programmatic stream serialization; the kernel MUST call pdl_wait() before its first global access
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 constexpr float COUNT_BASE = 2048.0f;   // COUNT planes: p0 = v mod 2048, p1 = v - p0
 

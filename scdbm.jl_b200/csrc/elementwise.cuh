@@ -154,6 +154,8 @@ __global__ void k_update(float* __restrict__ theta, const float* __restrict__ gr
 // slabs of raw fp32 partial sums in fixed order, adds the biases, applies the deterministic activation and writes the
 // state planes.  One thread per 4 consecutive columns of a row.
 __global__ void k_det_finish(const float* __restrict__ ws, int S, int64_t stride, int64_t ldw, EpiParams e, int64_t M, int64_t N) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t groups = (N + 3) / 4;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M * groups) return;
@@ -195,6 +197,8 @@ __global__ void k_update_layer(float* __restrict__ W, float* __restrict__ a, flo
                                float lr, int nb, const float* __restrict__ scale, plane_t* w0, plane_t* w1, int64_t ldh,
                                plane_t* t0, plane_t* t1, int64_t ldv, unsigned int* __restrict__ wmax, float mu_inv_max,
                                float4* __restrict__ nbc, uint32_t* __restrict__ nbT) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float t[32][33];
     __shared__ float red[8];
     const float s = scale[0];
@@ -260,6 +264,8 @@ __global__ void k_update_layer(float* __restrict__ W, float* __restrict__ a, flo
 }
 // scale of the coming update round from the max |W| the previous round left behind (one thread); resets the running max
 __global__ void k_weight_scale_next(unsigned int* __restrict__ max_bits, float* __restrict__ scale) {
+    pdl_trigger();
+    pdl_wait();
     const float m = __uint_as_float(*max_bits);
     int e = 0;
     if (m > 0.0f && isfinite(m)) e = 10 - (int)ceilf(log2f(m));      // |s W| <= 2^10
@@ -272,6 +278,8 @@ __global__ void k_weight_scale_next(unsigned int* __restrict__ max_bits, float* 
 // ---- bias gradients of one RBM in one launch (small batches; the two-pass column sums below serve large ones):
 //   da[c] = ps sum_rows v - ns sum_rows vm   (c < V),   db[c - V] = ps sum_rows h - ns sum_rows hm.   Deterministic.
 __global__ void k_bias_grad(MatView v, MatView vm, MatView h, MatView hm, float ps, float ns, float* __restrict__ da, float* __restrict__ db) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[32][33];
     const int64_t V = v.cols, H = h.cols;
     const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
@@ -297,6 +305,8 @@ __global__ void k_bias_grad(MatView v, MatView vm, MatView h, MatView hm, float 
 // ---- column sums of a state matrix, deterministic (no float atomics):
 // pass 1: partial[slab][c] = sum over the slab's rows; pass 2: out[c] (+)= scale * sum_slabs (fixed order)
 __global__ void k_colsum_partial(MatView m, float* __restrict__ partial) {
+    pdl_trigger();
+    pdl_wait();
     // block = 32 columns x 8 row-lanes; grid.x over column blocks, grid.y over row slabs
     __shared__ float red[8][33];
     const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
@@ -322,6 +332,8 @@ __global__ void k_colsum_partial(MatView m, float* __restrict__ partial) {
 }
 __global__ void k_colsum_final(const float* __restrict__ partial, int nslabs, int64_t cols, float scale,
                                float* __restrict__ out, int accumulate) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
     float tot = 0.0f;
@@ -366,6 +378,8 @@ __global__ void k_fill_nbc_pad(float4* nbc, int64_t n) {
 // before an NB sampling launch into `flags`' matrix: tiles whose hi plane was in use (or marked) must be zero-filled
 // by this launch (-> 2); tiles that were zero-filled by the previous launch and got no new entry are clean (-> 0)
 __global__ void k_flags_advance(uint32_t* __restrict__ flags, int64_t n) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) flags[i] = (flags[i] & 1u) ? 2u : 0u;
 }
@@ -384,6 +398,8 @@ __global__ void k_any_flag(const uint32_t* __restrict__ flags, int64_t n, uint32
 }
 // any_hi: device word written by k_any_flag for `src` (nullptr: assume counts >= 2048 may occur)
 __global__ void k_gather_rows(MatView src, const int32_t* __restrict__ idx, MatView dst, const uint32_t* __restrict__ any_hi) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t r = blockIdx.x;
     const int64_t s = idx[r];
     if (dst.hiflag && threadIdx.x == 0 && (r & 127) == 0) dst.hiflag[r >> 7] = any_hi ? *any_hi : 3u;
@@ -395,6 +411,8 @@ __global__ void k_gather_rows(MatView src, const int32_t* __restrict__ idx, MatV
 }
 
 __global__ void k_copy_rows(MatView src, MatView dst, int64_t rows) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t r = blockIdx.x;
     if (r >= rows) return;
     for (int64_t c = threadIdx.x; c < dst.ld; c += blockDim.x) {
@@ -412,6 +430,8 @@ struct DrawAddr {
     int64_t ldu;
 };
 __global__ void k_bernoulli(MatView prob, MatView dst, DrawAddr d) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t groups = (prob.cols + 3) / 4;
     const int64_t n = prob.rows * groups;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {

@@ -18,6 +18,8 @@ __device__ __forceinline__ float operand_load(const Operand& o, int64_t mn, int6
 }
 
 __global__ void __launch_bounds__(ST_THREADS) k_gemm_simt(const GemmArgs g) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float As[ST_K][ST_M + 4];
     __shared__ float Bs[ST_K][ST_N + 4];
     if (g.epi.skip && *g.epi.skip) return;   // speculatively launched mean-field iteration after convergence
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_gemm_simt(const GemmArgs g) {
 
 inline cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
     dim3 grid((unsigned)((g.N + ST_N - 1) / ST_N), (unsigned)((g.M + ST_M - 1) / ST_M));
-    k_gemm_simt<<<grid, ST_THREADS, 0, stream>>>(g);
+    { cudaError_t le = launch_pdl(k_gemm_simt, dim3(grid), dim3(ST_THREADS), 0, stream, g); if (le != cudaSuccess) return le; }
     return cudaGetLastError();
 }
 

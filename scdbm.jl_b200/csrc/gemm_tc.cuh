@@ -313,7 +313,10 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
     __shared__ uint32_t tmem_holder;
     __shared__ int dyn_item[4];     // EK == 1: next (tile, slice) item of each row quadrant
     if constexpr (EK == 0 || EK == 3) {
-        if (p.epi.skip && *p.epi.skip) return;   // speculatively launched mean-field iteration after convergence (whole grid)
+        if (p.epi.skip) {      // speculatively launched mean-field iteration after convergence (whole grid)
+            pdl_wait();        // the flag is written by the preceding launch
+            if (*p.epi.skip) return;
+        }
     }
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -345,6 +348,8 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_holder;
+    pdl_trigger();      // this CTA holds its TMEM columns: the next launch may start setting up
+    pdl_wait();         // operands and bias / flag tables come from the preceding launches
 
     if (svc == 0) {
         if (lane == 0) {
@@ -846,8 +851,7 @@ inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, i
     p.sched = (EK == 1 && p.m_tiles >= num_sms && p.ksplit <= 1) ? 1 : 0;
 #endif
     const int grid = p.sched ? std::min(p.m_tiles, num_sms) : std::min(p.m_tiles * p.n_tiles * std::max(p.ksplit, 1), num_sms);
-    k_gemm_tc<BN, EK, EPW><<<grid, 32 * (4 + EPW), smem, stream>>>(maps, p);
-    return cudaGetLastError();
+    return launch_pdl(k_gemm_tc<BN, EK, EPW>, dim3(grid), dim3(32 * (4 + EPW)), (size_t)smem, stream, maps, p);
 }
 
 // epilogue class: the fast sampling kernels need Philox-fed draws into the canonical plane layout
@@ -999,6 +1003,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_holder;
+    pdl_trigger();      // this CTA holds its TMEM columns: the next launch may start setting up
+    pdl_wait();         // operands and bias / flag tables come from the preceding launches
 
     // k-block range of source s for split `sp`
     auto kb_range = [&](int s, int sp, int& lo, int& hi) {
@@ -1167,6 +1173,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
 
 // out[i] = sum over splits (fixed order) of partial[s][i]
 __global__ void k_grad_reduce(const float* __restrict__ partial, int splits, int64_t n, float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float t = 0.0f;
         for (int s = 0; s < splits; ++s) t += partial[(int64_t)s * n + i];
@@ -1238,12 +1246,15 @@ inline cudaError_t launch_grad_tc(TcContext& t, const TcGradArgs& a, int num_sms
         t.attr_set[slot] = true;
     }
     const int nwork = p.m_tiles * p.n_tiles * p.splits;
-    if (halves == 2) k_grad_tc<2><<<std::min(nwork, num_sms), TG_THREADS, smem, stream>>>(maps, p);
-    else k_grad_tc<1><<<std::min(nwork, num_sms), TG_THREADS, smem, stream>>>(maps, p);
+    cudaError_t le;
+    if (halves == 2) le = launch_pdl(k_grad_tc<2>, dim3(std::min(nwork, num_sms)), dim3(TG_THREADS), (size_t)smem, stream, maps, p);
+    else le = launch_pdl(k_grad_tc<1>, dim3(std::min(nwork, num_sms)), dim3(TG_THREADS), (size_t)smem, stream, maps, p);
+    if (le != cudaSuccess) return le;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || p.splits == 1) return e;
     const int64_t n = a.V * a.H;
-    k_grad_reduce<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, stream>>>(a.partial, p.splits, n, a.out);
+    le = launch_pdl(k_grad_reduce, dim3((unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8)), dim3(256), 0, stream, a.partial, p.splits, n, a.out);
+    if (le != cudaSuccess) return le;
     return cudaGetLastError();
 }
 
