@@ -135,7 +135,8 @@ struct scdbm_model {
     int64_t live = 0;
     bool closed = false;
     float* d_scale = nullptr;          // {s, 1/s}
-    unsigned int* d_wmax = nullptr;    // max |W| over all layers (float bits)
+    unsigned int* d_wmax = nullptr;    // 3 slots of max |W| over all layers (float bits); slot wmax_round holds the current maximum,
+    int wmax_round = 0;                //   the fused update kernel (k_update_layer) rotates them
     int units(int layer) const { return layer == 0 ? L[0].V : L[layer - 1].H; }
     int nlayers() const { return (int)L.size() + 1; }
 };
@@ -201,6 +202,7 @@ struct scdbm_trainer {
     scdbm_opt* opt = nullptr;
     int32_t* d_perm = nullptr;
     int64_t perm_cap = 0;
+    int64_t v_groups = 0;          // minibatches gathered per launch into `v` (rows: v_groups x round_up(B, 128))
     uint32_t* d_anyhi = nullptr;   // does the data matrix of this epoch hold counts >= 2048 anywhere?
     bool track_mean = false;      // record `estimatedmean` (model means in minibatch order) each epoch
     scdbm_mat* est = nullptr;
@@ -287,6 +289,17 @@ static scdbm_mat* mat_view_of(scdbm_mat* of) {
 static MatView rows_view(const MatView& v, int64_t rows) {
     MatView r = v;
     r.rows = std::min(rows, v.rows);
+    return r;
+}
+
+// rows [r0, r0 + rows) of a matrix; r0 is a multiple of 128 (the hi-plane flags are per 128-row tile)
+static MatView rows_at(const MatView& v, int64_t r0, int64_t rows) {
+    MatView r = v;
+    r.p0 += r0 * v.ld;
+    if (r.p1) r.p1 += r0 * v.ld;
+    if (r.f) r.f += r0 * v.ld;
+    if (r.hiflag) r.hiflag += r0 / 128;
+    r.rows = std::min(rows, v.rows - r0);
     return r;
 }
 
@@ -444,7 +457,8 @@ static void refresh_nbc(scdbm_ctx* ctx, Layer& L, unsigned int* invalid = nullpt
 // scale -> fp16 hi/lo planes of every layer.  Called whenever any fp32 master weight changed.
 static void refresh_operands(scdbm_model* m) {
     scdbm_ctx* ctx = m->ctx;
-    CK(cudaMemsetAsync(m->d_wmax, 0, sizeof(unsigned int), ctx->stream));
+    CK(cudaMemsetAsync(m->d_wmax, 0, 3 * sizeof(unsigned int), ctx->stream));
+    m->wmax_round = 0;
     for (auto& L : m->L) {
         const int64_t n = (int64_t)L.V * L.H;
         k_absmax<<<grid1d(n), 256, 0, ctx->stream>>>(L.W, n, m->d_wmax);
@@ -664,8 +678,8 @@ int32_t scdbm_model_create(scdbm_ctx* c, int32_t nrbms, const int32_t* units, in
     auto* m = new scdbm_model{c, {}};
     ctx_retain(c);
     CK(cudaMallocAsync(&m->d_scale, 2 * sizeof(float), c->stream));
-    CK(cudaMallocAsync(&m->d_wmax, sizeof(unsigned int), c->stream));
-    CK(cudaMemsetAsync(m->d_wmax, 0, sizeof(unsigned int), c->stream));
+    CK(cudaMallocAsync(&m->d_wmax, 3 * sizeof(unsigned int), c->stream));
+    CK(cudaMemsetAsync(m->d_wmax, 0, 3 * sizeof(unsigned int), c->stream));
     {
         const float one[2] = {1.0f, 1.0f};
         CK(cudaMemcpyAsync(m->d_scale, one, sizeof(one), cudaMemcpyHostToDevice, c->stream));
@@ -1578,8 +1592,9 @@ int32_t scdbm_opt_destroy(scdbm_opt* o) {
 }
 
 // dW rows [v0, v0 + vn) of layer l:  pos_scale * v'h - neg_scale * vm'hm  (vn < 0: all rows)
-static void gradient_weights(scdbm_opt* o, int l, const MatView& v_, const MatView& vm_, const MatView& h, const MatView& hm,
-                             float pos_scale, float neg_scale, int64_t v0 = 0, int64_t vn = -1) {
+// fuse_bias: also produce da, db in the same launch when the batch is small (returns whether it did)
+static bool gradient_weights(scdbm_opt* o, int l, const MatView& v_, const MatView& vm_, const MatView& h, const MatView& hm,
+                             float pos_scale, float neg_scale, int64_t v0 = 0, int64_t vn = -1, bool fuse_bias = false) {
     scdbm_model* m = o->model;
     scdbm_ctx* c = m->ctx;
     Layer& L = m->L[l];
@@ -1613,12 +1628,17 @@ static void gradient_weights(scdbm_opt* o, int l, const MatView& v_, const MatVi
     g.epi.mode = EPI_RAW_F32;
     g.epi.out_f32 = o->buf + o->offW[l] + v0 * L.H;
     g.epi.ldo = L.H;
-    bool done = false;
+    bool done = false, fused = false;
     const double work = (double)vn * (double)L.H * (double)(v.rows + vm.rows);
     if (c->engine == SCDBM_ENGINE_TC || (c->engine == SCDBM_ENGINE_AUTO && work >= (double)(1 << 24))) {
         TcGradArgs ga{v, h, vm, hm, pos_scale, -neg_scale, g.epi.out_f32, vn, L.H, nullptr, 1};
         if (tc_grad_supported(ga)) {
             ga.splits = tc_grad_splits(ga, c->num_sms);
+            if (fuse_bias && v0 == 0 && vn == L.V && std::max(v.rows, vm.rows) <= 2048) {
+                ga.da = o->buf + o->offA[l];
+                ga.db = o->buf + o->offB[l];
+                fused = true;
+            }
             if (ga.splits > 1) {
                 const int64_t need = (int64_t)ga.splits * vn * L.H;
                 if (c->scratch_cap < need) {
@@ -1638,6 +1658,7 @@ static void gradient_weights(scdbm_opt* o, int l, const MatView& v_, const MatVi
     }
     if (!done) CK(launch_gemm_simt(g, c->stream));
     c->launches++;
+    return done && fused;
 }
 
 // da, db of layer l from column sums (deterministic two-pass reduction)
@@ -1664,8 +1685,7 @@ static void gradient_biases(scdbm_opt* o, int l, const MatView& v, const MatView
 
 static void gradient_layer(scdbm_opt* o, int l, const MatView& v, const MatView& vm, const MatView& h, const MatView& hm,
                            float pos_scale, float neg_scale) {
-    gradient_weights(o, l, v, vm, h, hm, pos_scale, neg_scale);
-    gradient_biases(o, l, v, vm, h, hm, pos_scale, neg_scale);
+    if (!gradient_weights(o, l, v, vm, h, hm, pos_scale, neg_scale, 0, -1, true)) gradient_biases(o, l, v, vm, h, hm, pos_scale, neg_scale);
 }
 
 // ---- data-parallel exchange: allreduce(sum) of gradient ranges on the communication stream, ordered behind the work
@@ -1748,21 +1768,21 @@ static void update_layer(scdbm_model* m, scdbm_opt* o, int l, float lr) {
 }
 
 // K6: update of ALL layers of the model, one fused kernel per layer (parameters, clamps, fp16 operand planes in both
-// orientations, NB sampling constants) after a one-thread kernel that fixes the round's weight scale
+// orientations, NB sampling constants, the round's weight scale and the next round's max |W|)
 static void update_all_layers(scdbm_model* m, scdbm_opt* o, float lr) {
     scdbm_ctx* c = m->ctx;
-    CK(launch_pdl(k_weight_scale_next, dim3(1), dim3(1), 0, c->stream, m->d_wmax, m->d_scale));
     for (int l = 0; l < (int)m->L.size(); ++l) {
         Layer& L = m->L[l];
         const bool nb = L.kind == SCDBM_VIS_NEGBIN;
         dim3 grid((L.V + 31) / 32, (L.H + 31) / 32), block(32, 8);
         CK(launch_pdl(k_update_layer, dim3(grid), dim3(block), 0, c->stream, L.W, L.a, L.b, L.r, o->buf + o->offW[l], o->buf + o->offA[l], o->buf + o->offB[l], L.V, L.H,
-                                                     lr, nb ? 1 : 0, m->d_scale, L.w0, L.w1, L.ldh, L.t0, L.t1, L.ldv, m->d_wmax, c->mu_inv_max,
+                                                     lr, nb ? 1 : 0, m->d_scale, L.w0, L.w1, L.ldh, L.t0, L.t1, L.ldv, m->d_wmax, m->wmax_round, l == 0 ? 1 : 0, c->mu_inv_max,
                                                      L.nbc, L.nbT));
         if (nb) L.nbL_mu = c->mu_inv_max;
     }
+    m->wmax_round = (m->wmax_round + 1) % 3;
     CK(cudaGetLastError());
-    c->launches += 1 + (int64_t)m->L.size();
+    c->launches += (int64_t)m->L.size();
 }
 
 int32_t scdbm_update_parameters(scdbm_model* m, scdbm_opt* o, int32_t l, double lr) {
@@ -1814,7 +1834,8 @@ int32_t scdbm_trainer_create(scdbm_model* m, int32_t l, int32_t B, int32_t pcd, 
     auto* t = new scdbm_trainer{m, l, B, pcd, 1};
     model_retain(m);
     const int vkind = L.kind == SCDBM_VIS_NEGBIN ? MAT_COUNT : MAT_REAL;  // upper layers train on potentials
-    t->v = mat_new(c, B, L.V, vkind);
+    t->v = mat_new(c, round_up(B, 128), L.V, vkind);
+    t->v_groups = 1;
     t->h = mat_new(c, B, L.H, MAT_REAL);
     t->hm = mat_new(c, B, L.H, MAT_REAL);
     t->hs = mat_new(c, B, L.H, MAT_BINARY);
@@ -1895,12 +1916,27 @@ int32_t scdbm_rbm_train_epoch(scdbm_trainer* t, const scdbm_mat* x, const int32_
         t->est = mat_new(c, n, L.V, MAT_REAL);
     }
     const float up = (float)upfactor, down = (float)downfactor;
-    for (int64_t s = 0; s < n; s += B) {
+    // minibatches are gathered a run at a time (one launch per <= 64 MB of rows), each on its own 128-row tiles
+    const int64_t Bpad = round_up(B, 128);
+    const int64_t G = std::max<int64_t>(1, std::min<int64_t>((n + B - 1) / B, ((int64_t)64 << 20) / (Bpad * t->v->v.ld * 8)));
+    if (t->v_groups != G) {
+        const int vkind = t->v->v.kind;
+        mat_free(t->v);
+        t->v = nullptr;
+        t->v = mat_new(c, G * Bpad, L.V, vkind);
+        t->v_groups = G;
+    }
+    for (int64_t s = 0, mb = 0; s < n; s += B, ++mb) {
         const int64_t thisb = std::min<int64_t>(B, n - s);
         const int64_t mrows = t->pcd ? B : thisb;  // PCD keeps the full chain (rbmtraining.jl:548-553)
-        MatView v = rows_view(t->v->v, thisb), h = rows_view(t->h->v, thisb);
-        CK(launch_pdl(k_gather_rows, dim3((unsigned)thisb), dim3(128), 0, c->stream, x->v, t->d_perm + s, v, x->v.hiflag ? t->d_anyhi : nullptr));   // sets the hi-plane flags of v
-        c->launches++;
+        const int64_t grp = mb % G;
+        if (grp == 0) {
+            const int64_t cnt = std::min<int64_t>(n - s, G * B);
+            CK(launch_pdl(k_gather_rows, dim3((unsigned)cnt), dim3(128), 0, c->stream, x->v, t->d_perm + s, t->v->v,
+                          x->v.hiflag ? t->d_anyhi : nullptr, B, (int)Bpad));   // sets the hi-plane flags of the gathered tiles
+            c->launches++;
+        }
+        MatView v = rows_at(t->v->v, grp * Bpad, thisb), h = rows_view(t->h->v, thisb);
         DrawCfg d;
         op_hidden(m, t->l, v, h, up, SCDBM_OUT_POTENTIAL, d);                         // :556
         MatView prob = t->pcd ? t->chain->v : h;                                       // :561-565

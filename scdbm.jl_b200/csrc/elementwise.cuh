@@ -104,11 +104,14 @@ __global__ void k_absmax(const float* __restrict__ W, int64_t n, unsigned int* _
     for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
     if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out_bits, __float_as_uint(m));
 }
-__global__ void k_weight_scale(const unsigned int* __restrict__ max_bits, float* __restrict__ scale) {
-    const float m = __uint_as_float(*max_bits);
+// exponent e of the power-of-two scale s = 2^e for a model whose largest |W| is m:  |s W| <= 2^10
+__device__ __forceinline__ int weight_scale_exp(float m) {
     int e = 0;
-    if (m > 0.0f && isfinite(m)) e = 10 - (int)ceilf(log2f(m));      // |s W| <= 2^10
-    e = max(-20, min(20, e));
+    if (m > 0.0f && isfinite(m)) e = 10 - (int)ceilf(log2f(m));
+    return max(-20, min(20, e));
+}
+__global__ void k_weight_scale(const unsigned int* __restrict__ max_bits, float* __restrict__ scale) {
+    const int e = weight_scale_exp(__uint_as_float(*max_bits));
     scale[0] = exp2f((float)e);
     scale[1] = exp2f((float)-e);
 }
@@ -194,14 +197,24 @@ __global__ void k_det_finish(const float* __restrict__ ws, int S, int64_t stride
 // grad: the layer's block {dW [V x H] row-major, da [V], db [H]}.
 __global__ void k_update_layer(float* __restrict__ W, float* __restrict__ a, float* __restrict__ b, const float* __restrict__ r,
                                const float* __restrict__ gW, const float* __restrict__ ga, const float* __restrict__ gb, int V, int H,
-                               float lr, int nb, const float* __restrict__ scale, plane_t* w0, plane_t* w1, int64_t ldh,
-                               plane_t* t0, plane_t* t1, int64_t ldv, unsigned int* __restrict__ wmax, float mu_inv_max,
+                               float lr, int nb, float* __restrict__ scale, plane_t* w0, plane_t* w1, int64_t ldh,
+                               plane_t* t0, plane_t* t1, int64_t ldv, unsigned int* __restrict__ wmax3, int round, int first, float mu_inv_max,
                                float4* __restrict__ nbc, uint32_t* __restrict__ nbT) {
     pdl_trigger();
     pdl_wait();
     __shared__ float t[32][33];
     __shared__ float red[8];
-    const float s = scale[0];
+    // The round's weight scale follows from the max |W| the previous round left in wmax3[round % 3] (weight_scale_exp;
+    // every thread derives it: no extra launch, no block-level broadcast).  This round's maximum goes to the next slot;
+    // the slot after that is cleared for the round after (three slots: no block reads a slot another block writes).
+    const int e2 = weight_scale_exp(__uint_as_float(wmax3[round % 3]));
+    const float s = exp2f((float)e2);
+    unsigned int* wmax = wmax3 + (round + 1) % 3;
+    if (first && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) {
+        scale[0] = s;
+        scale[1] = exp2f((float)-e2);
+        wmax3[(round + 2) % 3] = 0u;
+    }
     const int v0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
     float m = 0.0f;
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -262,19 +275,6 @@ __global__ void k_update_layer(float* __restrict__ W, float* __restrict__ a, flo
         if (h < H) b[h] = fmaf(lr, gb[h], b[h]);
     }
 }
-// scale of the coming update round from the max |W| the previous round left behind (one thread); resets the running max
-__global__ void k_weight_scale_next(unsigned int* __restrict__ max_bits, float* __restrict__ scale) {
-    pdl_trigger();
-    pdl_wait();
-    const float m = __uint_as_float(*max_bits);
-    int e = 0;
-    if (m > 0.0f && isfinite(m)) e = 10 - (int)ceilf(log2f(m));      // |s W| <= 2^10
-    e = max(-20, min(20, e));
-    scale[0] = exp2f((float)e);
-    scale[1] = exp2f((float)-e);
-    *max_bits = 0u;
-}
-
 // ---- bias gradients of one RBM in one launch (small batches; the two-pass column sums below serve large ones):
 //   da[c] = ps sum_rows v - ns sum_rows vm   (c < V),   db[c - V] = ps sum_rows h - ns sum_rows hm.   Deterministic.
 __global__ void k_bias_grad(MatView v, MatView vm, MatView h, MatView hm, float ps, float ns, float* __restrict__ da, float* __restrict__ db) {
@@ -397,12 +397,36 @@ __global__ void k_any_flag(const uint32_t* __restrict__ flags, int64_t n, uint32
     if (threadIdx.x == 0) *out = any ? 3u : 0u;
 }
 // any_hi: device word written by k_any_flag for `src` (nullptr: assume counts >= 2048 may occur)
-__global__ void k_gather_rows(MatView src, const int32_t* __restrict__ idx, MatView dst, const uint32_t* __restrict__ any_hi) {
+// One launch gathers a run of minibatches: dst row (j * Bpad + i) = src row idx[j * B + i]; Bpad (a multiple of 128)
+// keeps every minibatch on its own hi-plane flag tiles.  Rows are copied 16 bytes at a time (ld is a multiple of 64).
+__global__ void k_gather_rows(MatView src, const int32_t* __restrict__ idx, MatView dst, const uint32_t* __restrict__ any_hi, int B, int Bpad) {
     pdl_trigger();
     pdl_wait();
-    const int64_t r = blockIdx.x;
-    const int64_t s = idx[r];
-    if (dst.hiflag && threadIdx.x == 0 && (r & 127) == 0) dst.hiflag[r >> 7] = any_hi ? *any_hi : 3u;
+    const int64_t j = blockIdx.x / B, i = blockIdx.x % B;
+    const int64_t r = j * Bpad + i;
+    const int64_t s = idx[blockIdx.x];
+    if (dst.hiflag && threadIdx.x == 0 && (i & 127) == 0) dst.hiflag[r >> 7] = any_hi ? *any_hi : 3u;
+    if (src.ld == dst.ld && (!dst.f || src.f)) {
+        const int64_t n16 = dst.ld / 8;       // 16-byte chunks of one plane row
+        const uint4* s0 = reinterpret_cast<const uint4*>(src.p0 + s * src.ld);
+        uint4* d0 = reinterpret_cast<uint4*>(dst.p0 + r * dst.ld);
+        for (int64_t c = threadIdx.x; c < n16; c += blockDim.x) d0[c] = s0[c];
+        if (dst.p1) {
+            uint4* d1 = reinterpret_cast<uint4*>(dst.p1 + r * dst.ld);
+            if (src.p1) {
+                const uint4* s1 = reinterpret_cast<const uint4*>(src.p1 + s * src.ld);
+                for (int64_t c = threadIdx.x; c < n16; c += blockDim.x) d1[c] = s1[c];
+            } else {
+                for (int64_t c = threadIdx.x; c < n16; c += blockDim.x) d1[c] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        if (dst.f) {
+            const float4* sf = reinterpret_cast<const float4*>(src.f + s * src.ld);
+            float4* df = reinterpret_cast<float4*>(dst.f + r * dst.ld);
+            for (int64_t c = threadIdx.x; c < dst.ld / 4; c += blockDim.x) df[c] = sf[c];
+        }
+        return;
+    }
     for (int64_t c = threadIdx.x; c < dst.ld; c += blockDim.x) {
         dst.p0[r * dst.ld + c] = src.p0[s * src.ld + c];
         if (dst.p1) dst.p1[r * dst.ld + c] = src.p1 ? src.p1[s * src.ld + c] : __ushort_as_half(0);

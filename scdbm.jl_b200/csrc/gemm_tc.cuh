@@ -63,6 +63,8 @@ struct TcGradArgs {
     int64_t V, H;
     float* partial;               // split-K workspace [splits][V][H] (nullptr: splits == 1)
     int32_t splits;
+    float* da = nullptr;          // non-null (small batches): trailing CTAs of the same launch also produce the bias gradients
+    float* db = nullptr;          //   da[V] = pos_scale colsum(v) + neg_scale colsum(vm),  db[H] likewise from h, hm
 };
 
 constexpr int TC_BM = 128, TC_BK = 64;
@@ -885,7 +887,9 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
                                   cudaStream_t stream, int ksplit = 1) {
     if (!t.encode) return cudaErrorNotSupported;
     const int ek = tc_epilogue_class(g, ops, nsrc);
-    const int BN = g.N <= 64 ? 64 : (ek == 1 && g.N >= TC_NB_BN) ? TC_NB_BN : 128;
+    // latency-bound launches (a handful of tiles): 64-column tiles halve each epilogue warp's serial work and double the CTAs
+    const bool few_tiles = ek != 1 && ((g.M + TC_BM - 1) / TC_BM) * ((g.N + 127) / 128) * std::max(ksplit, 1) * 4 <= num_sms;
+    const int BN = (g.N <= 64 || few_tiles) ? 64 : (ek == 1 && g.N >= TC_NB_BN) ? TC_NB_BN : 128;
     TcMaps maps;
     TcParams p;
     memset(&p, 0, sizeof(p));
@@ -952,6 +956,10 @@ struct TcGradParams {
     float* out;
     float* partial;
     int32_t m_tiles, n_tiles, splits, stages;
+    int32_t nbias;         // trailing CTAs that compute bias gradients (32 columns each), 0: none
+    MatView bv, bh, bvm, bhm;
+    float* da;
+    float* db;
 };
 constexpr int TG_BN = 128, TG_THREADS = 32 * (4 + 16);
 constexpr int TG_PLANE = 128 * TC_BK * 2;           // 16 KB: [2 unit blocks][64 samples][64 units] fp16
@@ -965,6 +973,32 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
+}
+
+// Bias gradients of a small batch by one trailing CTA of the gradient launch (the launch is latency-bound: a separate
+// kernel costs more than these few loads): 32 columns x 20 row lanes, fixed summation order.
+__device__ __noinline__ void grad_bias_cta(const TcGradParams& p, int blk) {
+    __shared__ float red[20][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int64_t V = p.bv.cols, H = p.bh.cols;
+    const int64_t c = (int64_t)blk * 32 + cx;
+    const bool vis = c < V;
+    const MatView& P = vis ? p.bv : p.bh;
+    const MatView& N = vis ? p.bvm : p.bhm;
+    const int64_t cc = vis ? c : c - V;
+    float sp = 0.0f, sn = 0.0f;
+    if (c < V + H) {
+        for (int64_t r = ry; r < P.rows; r += 20) sp += mat_load(P, r, cc);
+        for (int64_t r = ry; r < N.rows; r += 20) sn += mat_load(N, r, cc);
+    }
+    red[ry][cx] = p.scale[0] * sp + p.scale[1] * sn;
+    __syncthreads();
+    if (ry == 0 && c < V + H) {
+        float tot = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 20; ++j) tot += red[j][cx];
+        (vis ? p.da : p.db)[cc] = tot;
+    }
 }
 
 // HALVES: 128-row halves of a work tile (1 or 2).  Two halves share every B (hidden-state) tile load: 64 instead of 96
@@ -989,6 +1023,13 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int svc = warp - 16;    // epilogue warps 0-15, service warps above them (see k_gemm_tc)
     const int nwork = p.m_tiles * p.n_tiles * p.splits;
+    const int ngemm = (int)gridDim.x - p.nbias;
+    if ((int)blockIdx.x >= ngemm) {
+        pdl_trigger();
+        pdl_wait();
+        grad_bias_cta(p, (int)blockIdx.x - ngemm);
+        return;
+    }
 
     if (svc == 1 && lane == 0) {
         for (int i = 0; i < p.stages; ++i) { mbar_init(smem_u32(&bar_full[i]), 1); mbar_init(smem_u32(&bar_empty[i]), 1); }
@@ -1022,7 +1063,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+            for (int w = blockIdx.x; w < nwork; w += ngemm) {
                 const int tile = w / p.splits, sp = w % p.splits;
                 const int m0 = (tile / p.n_tiles) * ROWS, n0 = (tile % p.n_tiles) * TG_BN;
                 for (int s = 0; s < 2; ++s) {
@@ -1053,7 +1094,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
         if (lane == 0) {
             int stage = 0, astage = 0;
             uint32_t phase = 0, aphase = 0;
-            for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+            for (int w = blockIdx.x; w < nwork; w += ngemm) {
                 const int sp = w % p.splits;
                 for (int s = 0; s < 2; ++s) {
                     int lo, hi;
@@ -1108,7 +1149,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
         const int q = warp & 3, slice = warp >> 2;
         int astage = 0;
         uint32_t aphase = 0;
-        for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        for (int w = blockIdx.x; w < nwork; w += ngemm) {
             const int tile = w / p.splits, sp = w % p.splits;
             const int64_t m0 = (int64_t)(tile / p.n_tiles) * ROWS, nn0 = (int64_t)(tile % p.n_tiles) * TG_BN;
             float sum[HALVES][32];
@@ -1215,6 +1256,9 @@ inline cudaError_t launch_grad_tc(TcContext& t, const TcGradArgs& a, int num_sms
     p.m_tiles = (int)((a.V + halves * TC_BM - 1) / (halves * TC_BM));
     p.n_tiles = (int)((a.H + TG_BN - 1) / TG_BN);
     p.scale[0] = a.pos_scale; p.scale[1] = a.neg_scale;
+    p.nbias = (a.da && a.db) ? (int)((a.v.cols + a.h.cols + 31) / 32) : 0;
+    p.bv = a.v; p.bh = a.h; p.bvm = a.vm; p.bhm = a.hm;
+    p.da = a.da; p.db = a.db;
     const MatView* av[2] = {&a.v, &a.vm};
     const MatView* bv[2] = {&a.h, &a.hm};
     for (int s = 0; s < 2; ++s) {
@@ -1247,8 +1291,8 @@ inline cudaError_t launch_grad_tc(TcContext& t, const TcGradArgs& a, int num_sms
     }
     const int nwork = p.m_tiles * p.n_tiles * p.splits;
     cudaError_t le;
-    if (halves == 2) le = launch_pdl(k_grad_tc<2>, dim3(std::min(nwork, num_sms)), dim3(TG_THREADS), (size_t)smem, stream, maps, p);
-    else le = launch_pdl(k_grad_tc<1>, dim3(std::min(nwork, num_sms)), dim3(TG_THREADS), (size_t)smem, stream, maps, p);
+    if (halves == 2) le = launch_pdl(k_grad_tc<2>, dim3(std::min(nwork, num_sms) + p.nbias), dim3(TG_THREADS), (size_t)smem, stream, maps, p);
+    else le = launch_pdl(k_grad_tc<1>, dim3(std::min(nwork, num_sms) + p.nbias), dim3(TG_THREADS), (size_t)smem, stream, maps, p);
     if (le != cudaSuccess) return le;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || p.splits == 1) return e;
