@@ -1,15 +1,18 @@
 """Launch counts and CUDA-event timings of the small-problem training paths (BASELINE configs C1 and C2)."""
-import os, sys
+import argparse, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as g
 import bench
+ap = argparse.ArgumentParser()
+ap.add_argument("--only", default="", help="c1 | c2 | ops (default: all)")
+a = ap.parse_args()
 pkg = g.load_package()
 ctx = pkg.Context(0, bench.SEED)
 x1 = bench.synth_counts(500, 1000, seed=1)
 xm = pkg.Mat.from_host(ctx, x1, pkg.MAT_COUNT)
 m = pkg.DeviceModel(ctx, [1000, 128], pkg.VIS_NEGBIN)
 m.init_layer(0, xm, seed=bench.SEED)
-for pcd in (False, True):
+for pcd in ((False, True) if a.only in ("", "c1") else ()):
     tr = pkg.RBMTrainer(m, 100, pcd=pcd)
     for _ in range(3):
         pkg.trainrbm_(m, xm, tr, 1e-4, 1)
@@ -21,19 +24,24 @@ for pcd in (False, True):
             pkg.trainrbm_(m, xm, tr, 1e-4, 1)
         best = min(best, ctx.timer_stop())
     print(f"C1 pcd={pcd}: {20 / best * 1e3:.0f} epochs/s, {best / 100 * 1e3:.1f} us per minibatch, {ctx.launch_count() / 300:.1f} launches per minibatch")
+if a.only not in ("", "c2", "ops"):
+    sys.exit(0)
 x2 = bench.synth_counts(5000, 2000, seed=2)
 L = bench.make_model()
 dm = pkg.DeviceModel.from_host([pkg.NegativeBinomialBernoulliRBM(**L[0]), pkg.BernoulliRBM(**L[1])], ctx)
 x2m = pkg.Mat.from_host(ctx, x2, pkg.MAT_COUNT)
 p = pkg.DeviceParticles(dm, 100).init(False)
-pkg.traindbm_(dm, x2m, epochs=3, particles=p, learningrate=1e-4, device=True, ctx=ctx)
-ctx.sync(); ctx.launch_count(reset=True)
-best = 1e30
-for _ in range(3):
-    ctx.sync(); ctx.timer_start()
-    pkg.traindbm_(dm, x2m, epochs=20, particles=p, learningrate=1e-4, device=True, ctx=ctx)
-    best = min(best, ctx.timer_stop())
-print(f"C2: {20 / best * 1e3:.0f} steps/s, {best / 20 * 1e3:.0f} us per step, {ctx.launch_count() / 60:.1f} launches per step")
+if a.only in ("", "c2"):
+    pkg.traindbm_(dm, x2m, epochs=3, particles=p, learningrate=1e-4, device=True, ctx=ctx)
+    ctx.sync(); ctx.launch_count(reset=True)
+    best = 1e30
+    for _ in range(3):
+        ctx.sync(); ctx.timer_start()
+        pkg.traindbm_(dm, x2m, epochs=20, particles=p, learningrate=1e-4, device=True, ctx=ctx)
+        best = min(best, ctx.timer_stop())
+    print(f"C2: {20 / best * 1e3:.0f} steps/s, {best / 20 * 1e3:.0f} us per step, {ctx.launch_count() / 60:.1f} launches per step")
+if a.only not in ("", "ops"):
+    sys.exit(0)
 # per-operator GPU time at the C1 minibatch shape (back-to-back launches, CUDA events)
 import numpy as np
 lib, ck = pkg.lib(), pkg._lib.check

@@ -335,10 +335,11 @@ static void run_gemm(scdbm_ctx* ctx, GemmArgs& g, const SweepSrc* srcs, int nsrc
     bool use_tc = false;
     if (ctx->engine != SCDBM_ENGINE_SIMT && srcs) {
         use_tc = tc_supported(g, nsrc);
-        // AUTO: tiny problems are launch-latency-bound; the FFMA kernel has no descriptor set-up cost
+        // AUTO: only toy shapes go to the FFMA kernel (no descriptor set-up, fp32 operands).  A one-tile tcgen05 launch
+        // costs ~11 us; the FFMA kernel needs 75 us for 100 x 256 -> 64 (C2's top layer, measured)
         double work = 0.0;
         for (int s = 0; s < nsrc; ++s) work += (double)g.M * (double)g.N * (double)g.src[s].K;
-        if (ctx->engine == SCDBM_ENGINE_AUTO && work < (double)(1 << 22)) use_tc = false;
+        if (ctx->engine == SCDBM_ENGINE_AUTO && work < (double)(1 << 17)) use_tc = false;
     }
     if (ctx->engine == SCDBM_ENGINE_TC && !use_tc && srcs)
         throw Err(SCDBM_EUNSUP, "engine=tc requested but the shape is not tiled by the tcgen05 kernel");
@@ -1630,11 +1631,11 @@ static bool gradient_weights(scdbm_opt* o, int l, const MatView& v_, const MatVi
     g.epi.ldo = L.H;
     bool done = false, fused = false;
     const double work = (double)vn * (double)L.H * (double)(v.rows + vm.rows);
-    if (c->engine == SCDBM_ENGINE_TC || (c->engine == SCDBM_ENGINE_AUTO && work >= (double)(1 << 24))) {
+    if (c->engine == SCDBM_ENGINE_TC || (c->engine == SCDBM_ENGINE_AUTO && work >= (double)(1 << 20))) {
         TcGradArgs ga{v, h, vm, hm, pos_scale, -neg_scale, g.epi.out_f32, vn, L.H, nullptr, 1};
         if (tc_grad_supported(ga)) {
             ga.splits = tc_grad_splits(ga, c->num_sms);
-            if (fuse_bias && v0 == 0 && vn == L.V && std::max(v.rows, vm.rows) <= 2048) {
+            if (fuse_bias && v0 == 0 && vn == L.V && std::max(v.rows, vm.rows) <= 16384) {
                 ga.da = o->buf + o->offA[l];
                 ga.db = o->buf + o->offB[l];
                 fused = true;
@@ -1714,12 +1715,13 @@ static void gradient_dbm(scdbm_opt* o, scdbm_model* m, scdbm_particles* mu, scdb
         const int64_t nW = (int64_t)L.V * L.H;
         const int nblk = (c->comm && nW >= (int64_t)(4 << 20)) ? 4 : 1;
         const int64_t step = round_up((L.V + nblk - 1) / nblk, 128);
+        bool bias_done = false;
         for (int64_t v0 = 0; v0 < L.V; v0 += step) {
             const int64_t vn = std::min<int64_t>(step, L.V - v0);
-            gradient_weights(o, l, v, vm, h, hm, ps, ns, v0, vn);
+            bias_done = gradient_weights(o, l, v, vm, h, hm, ps, ns, v0, vn, nblk == 1);
             comm_allreduce_range(c, o->buf + o->offW[l] + v0 * L.H, vn * L.H);
         }
-        gradient_biases(o, l, v, vm, h, hm, ps, ns);
+        if (!bias_done) gradient_biases(o, l, v, vm, h, hm, ps, ns);
         comm_allreduce_range(c, o->buf + o->offA[l], L.V + L.H);
     }
     comm_join(c);
