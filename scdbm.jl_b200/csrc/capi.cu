@@ -223,7 +223,7 @@ static void colsum(scdbm_ctx* c, const MatView& m, float scale, float* out, bool
         if (cudaMalloc(&c->scratch, need * sizeof(float)) != cudaSuccess) throw Err(SCDBM_ENOMEM, "column-sum workspace");
         c->scratch_cap = need;
     }
-    dim3 grid((unsigned)((m.cols + 31) / 32), (unsigned)nslabs), block(32, 8);
+    dim3 grid((unsigned)((m.cols + 255) / 256), (unsigned)nslabs), block(32, 8);
     CK(launch_pdl(k_colsum_partial, dim3(grid), dim3(block), 0, c->stream, m, c->scratch));
     CK(launch_pdl(k_colsum_final, dim3((unsigned)((m.cols + 127) / 128)), dim3(128), 0, c->stream, c->scratch, nslabs, m.cols, scale, out, accumulate ? 1 : 0));
     c->launches += 2;

@@ -307,26 +307,43 @@ __global__ void k_bias_grad(MatView v, MatView vm, MatView h, MatView hm, float 
 __global__ void k_colsum_partial(MatView m, float* __restrict__ partial) {
     pdl_trigger();
     pdl_wait();
-    // block = 32 columns x 8 row-lanes; grid.x over column blocks, grid.y over row slabs
-    __shared__ float red[8][33];
-    const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
-    float s = 0.0f;
-    if (c < m.cols) {
-        if (m.kind == MAT_COUNT && m.hiflag) {      // hi count plane only where the row tile uses it (half the HBM reads)
-            for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < m.rows; r += (int64_t)gridDim.y * 8) {
-                float v = plane_decode(m.p0[r * m.ld + c]);
-                if (m.hiflag[r >> 7] & 1u) v += plane_decode(m.p1[r * m.ld + c]);
-                s += v;
+    // block = 32 chunks of 8 columns x 8 row lanes (16-byte plane loads: rows are padded to multiples of 64 columns);
+    // grid.x over 256-column blocks, grid.y over row slabs
+    __shared__ float red[8][32][9];
+    const int64_t c0 = ((int64_t)blockIdx.x * 32 + threadIdx.x) * 8;
+    float s[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    auto add8 = [&](const plane_t* p) {
+        const uint4 v = *reinterpret_cast<const uint4*>(p);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 t = __half22float2(h[j]);
+            s[2 * j] += t.x;
+            s[2 * j + 1] += t.y;
+        }
+    };
+    if (c0 < m.ld) {
+        for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < m.rows; r += (int64_t)gridDim.y * 8) {
+            const int64_t i = r * m.ld + c0;
+            if (m.f) {
+                const float4 x = *reinterpret_cast<const float4*>(m.f + i), y = *reinterpret_cast<const float4*>(m.f + i + 4);
+                s[0] += x.x; s[1] += x.y; s[2] += x.z; s[3] += x.w; s[4] += y.x; s[5] += y.y; s[6] += y.z; s[7] += y.w;
+            } else {
+                add8(m.p0 + i);
+                // hi count plane only where the row tile uses it (half the HBM reads)
+                if (m.p1 && !(m.kind == MAT_COUNT && m.hiflag && !(m.hiflag[r >> 7] & 1u))) add8(m.p1 + i);
             }
-        } else {
-            for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < m.rows; r += (int64_t)gridDim.y * 8) s += mat_load(m, r, c);
         }
     }
-    red[threadIdx.y][threadIdx.x] = s;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = s[j];
     __syncthreads();
-    if (threadIdx.y == 0 && c < m.cols) {
+    // 256 columns of the block, one per thread: fixed summation order over the 8 row lanes
+    const int t = threadIdx.y * 32 + threadIdx.x;
+    const int64_t c = (int64_t)blockIdx.x * 256 + t;
+    if (c < m.cols) {
         float tot = 0.0f;
-        for (int j = 0; j < 8; ++j) tot += red[j][threadIdx.x];
+        for (int j = 0; j < 8; ++j) tot += red[j][t >> 3][t & 7];
         partial[(int64_t)blockIdx.y * m.cols + c] = tot;
     }
 }

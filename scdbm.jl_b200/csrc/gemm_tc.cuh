@@ -92,6 +92,11 @@ constexpr int TC_QCAP = 192, TC_SCAP = 64, TC_NB_STEPS = SCDBM_NB_STEPS;
 #endif
 constexpr int TC_NB_EPW = SCDBM_NB_EPW, TC_NB_BN = (SCDBM_NB_CW / 4) * TC_NB_EPW;
 static_assert(SCDBM_NB_ASTAGES * TC_NB_BN <= 512, "NB kernel: accumulator stages exceed TMEM");
+// Long contractions (K >= 512: the 1 024-unit hidden layer of configs C4 / C5): the 28 epilogue warps' queues leave room for ONE
+// 73 KB operand stage, so every k-block's load -> MMA round trip (~2 us) is exposed: 16 of them per tile, 3x the
+// epilogue's time.  There the NB class runs 20 epilogue warps on 160-column tiles: two operand stages fit, and three
+// accumulator stages (480 TMEM columns).
+constexpr int TC_NBK_EPW = 20, TC_NBK_BN = 8 * TC_NBK_EPW, TC_NBK_MIN_KB = 8;
 // ... and the slice's per-gene constants (nbc: 16 B, threshold: 4 B per column): with the shared-memory carve-out at its
 // maximum the L1 is too small to keep the per-gene tables, and every gather from them was an L2 round trip
 __host__ __device__ constexpr int tc_epi_smem(int cw) { return TC_QCAP * 8 + TC_SCAP * 16 + 32 * cw * 2 + cw * 20; }
@@ -120,6 +125,8 @@ struct TcParams {
                           //      a slice of the k-blocks and stores raw fp32 partial sums (EPI_RAW_F32) into its own slab
     int32_t sched;        // 1: a CTA owns whole m-tiles and walks all n-tiles (balanced over genes, A re-used
                           //    back-to-back); 0: flat round-robin over (m, n) tiles, n fastest (few m-tiles)
+    int32_t mfast;        // flat order with the ROW tile fastest: the concurrently running CTAs share one weight tile and
+                          //    re-stream the (smaller) state operand instead of all weight planes
     EpiParams epi;
 };
 
@@ -224,6 +231,22 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Mean-field extras of the deterministic class: the hoisted addend and the previous value are read once, straight from
+// HBM, by a loop with one 16-byte load per array in flight per thread.  Each lane asks L2 for its row's part of the
+// warp's block (CW floats) while the warp still waits for the accumulator.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void epi_prefetch_extras(const EpiParams& e, int64_t row, int64_t M, int64_t col, int64_t N, int cw) {
+    if (row >= M || col >= N) return;
+    if (e.addend) {
+        const float* a = e.addend + row * e.ld_add + col;
+        for (int b = 0; b < cw; b += 32) prefetch_l2(a + b);
+    }
+    if (e.prev.f) {
+        const float* o = e.prev.f + row * e.prev.ld + col;
+        for (int b = 0; b < cw; b += 32) prefetch_l2(o + b);
+    }
+}
+
 // pass A of the NB epilogue for one element: `word >= T` (the draw is not decided by the zero shortcut) -> append the
 // 8-byte entry {x, y} to the warp's queue at shared address qbase + 8 * slot.  One compare feeds the ballot and
 // predicates the store; no branch.
@@ -253,7 +276,9 @@ __device__ __forceinline__ int tc_tile(const TcParams& p, int it) {
         return m < p.m_tiles ? m * p.n_tiles + it % p.n_tiles : -1;
     }
     const int t = (int)blockIdx.x + it * (int)gridDim.x;
-    return t < p.m_tiles * p.n_tiles * max(p.ksplit, 1) ? t : -1;     // split-K: t is a work item, see tc_split_range
+    if (t >= p.m_tiles * p.n_tiles * max(p.ksplit, 1)) return -1;     // split-K: t is a work item, see tc_split_range
+    if (p.mfast) return (t % p.m_tiles) * p.n_tiles + t / p.m_tiles;   // row tile fastest: the CTAs share a weight tile
+    return t;
 }
 
 // split-K: work item id -> (tile, split) and the split's range of the tile's flattened k-block sequence
@@ -305,7 +330,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
     constexpr int NS = EPW / 4;          // column slices per tile
     constexpr int CW = BN / NS;          // columns per epilogue warp per tile (16 or 32)
     constexpr int B_TILE = BN * TC_BK * 2;
-    constexpr int ASTAGES = (EK == 1 && BN == TC_NB_BN) ? SCDBM_NB_ASTAGES : 2;    // TMEM accumulator stages
+    constexpr int ASTAGES = (EK == 1 && BN == TC_NB_BN) ? SCDBM_NB_ASTAGES : (EK == 1 && BN == TC_NBK_BN) ? 3 : 2;    // TMEM accumulator stages
     constexpr uint32_t TMEM_COLS = (EK == 1) ? ((ASTAGES * BN <= 256) ? 256 : 512) : ((2 * ASTAGES * BN <= 256) ? 256 : 512);
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // c = F32, a = b = F16, K-major
     static_assert(CW == 16 || CW == 32, "epilogue slice must be 16 or 32 columns");
@@ -644,6 +669,9 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     if (p.epi.r && (p.epi.mode == EPI_NBMEAN || p.epi.mode == EPI_NB_DRAW)) r_l = __ldg(p.epi.r + cl);
                 }
             }
+            if constexpr (EK == 3) {
+                for (int h = 0; h < halves; ++h) epi_prefetch_extras(p.epi, m0 + h * TC_BM + q * 32 + lane, p.M, n0 + slice * CW, p.N, CW);
+            }
             if constexpr (EK != 1) {
                 // chunked accumulation: add all but the last chunk in registers, then fold the last one in and put
                 // the total back into the last chunk's TMEM stage
@@ -829,7 +857,7 @@ inline bool tc_supported(const GemmArgs& g, int nsrc) {
 
 template <int BN, int EK, int EPW>
 inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, int num_sms, cudaStream_t stream) {
-    const int slot = (BN == 64 ? 0 : BN == 128 ? 4 : 8) + EK;   // wide NB kernel: slot 9
+    const int slot = BN == TC_NBK_BN ? 10 : (BN == 64 ? 0 : BN == 128 ? 4 : 8) + EK;   // wide NB kernel: slot 9
     constexpr int B_TILE = BN * TC_BK * 2;
     const int qbytes = (EK == 1) ? EPW * tc_epi_smem(BN / (EPW / 4)) : 0;
     p.a_tiles = std::max(p.split_hi[0] ? 1 : p.nA[0], p.nsrc > 1 ? (p.split_hi[1] ? 1 : p.nA[1]) : 1);
@@ -852,6 +880,11 @@ inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, i
 #else
     p.sched = (EK == 1 && p.m_tiles >= num_sms && p.ksplit <= 1) ? 1 : 0;
 #endif
+    // Flat order, which operand is re-streamed from L2 / HBM?  Column tile fastest: the ~#SM concurrent tiles span all
+    // weight tiles of one or two row tiles, so the weight planes are streamed once per row-tile group (AIS / PCD Gibbs at
+    // C4: 16 384 x 20 000 x 1 024 read 3.3 GB of the 82 MB weight planes from HBM, ncu capture prof_r02_aisnb).  Row tile
+    // fastest re-streams the state operand instead: chosen when that one is the smaller.
+    p.mfast = (!p.sched && p.ksplit <= 1 && p.m_tiles > 1 && p.n_tiles > 1 && p.M * (int64_t)p.a_tiles < p.N * 2) ? 1 : 0;
     const int grid = p.sched ? std::min(p.m_tiles, num_sms) : std::min(p.m_tiles * p.n_tiles * std::max(p.ksplit, 1), num_sms);
     return launch_pdl(k_gemm_tc<BN, EK, EPW>, dim3(grid), dim3(32 * (4 + EPW)), (size_t)smem, stream, maps, p);
 }
@@ -889,7 +922,8 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
     const int ek = tc_epilogue_class(g, ops, nsrc);
     // latency-bound launches (a handful of tiles): 64-column tiles halve each epilogue warp's serial work and double the CTAs
     const bool few_tiles = ek != 1 && ((g.M + TC_BM - 1) / TC_BM) * ((g.N + 127) / 128) * std::max(ksplit, 1) * 4 <= num_sms;
-    const int BN = (g.N <= 64 || few_tiles) ? 64 : (ek == 1 && g.N >= TC_NB_BN) ? TC_NB_BN : 128;
+    const bool long_k = ek == 1 && g.N >= TC_NBK_BN && (ops[0].K + TC_BK - 1) / TC_BK >= TC_NBK_MIN_KB;
+    const int BN = (g.N <= 64 || few_tiles) ? 64 : long_k ? TC_NBK_BN : (ek == 1 && g.N >= TC_NB_BN) ? TC_NB_BN : 128;
     TcMaps maps;
     TcParams p;
     memset(&p, 0, sizeof(p));
@@ -928,6 +962,7 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
         if (ek == 3) return tc_launch_bn<64, 3, 16>(t, maps, p, num_sms, stream);
         return tc_launch_bn<64, 0, 16>(t, maps, p, num_sms, stream);
     }
+    if (BN == TC_NBK_BN && ek == 1) return tc_launch_bn<TC_NBK_BN, 1, TC_NBK_EPW>(t, maps, p, num_sms, stream);
     if (BN == TC_NB_BN && ek == 1) return tc_launch_bn<TC_NB_BN, 1, TC_NB_EPW>(t, maps, p, num_sms, stream);
     if (ek == 1) return tc_launch_bn<128, 1, 16>(t, maps, p, num_sms, stream);
     if (ek == 2) return tc_launch_bn<128, 2, 16>(t, maps, p, num_sms, stream);

@@ -196,6 +196,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 + C2_EPW), 1
                     if (p.epi.r && p.epi.mode == EPI_NBMEAN) r_l[t] = __ldg(p.epi.r + c);
                 }
             }
+            if constexpr (EK == 3) epi_prefetch_extras(p.epi, m0 + q * 32 + lane, p.M, n0 + slice * C2_CW, p.N, C2_CW);
             const int nch = tc_chunks(tc_tile_kblocks(p, mt));
             if (nch > 1) {   // chunked accumulation with fp32 promotion (see tc_chunks)
                 float sum[C2_CW];
