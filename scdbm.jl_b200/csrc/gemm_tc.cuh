@@ -46,7 +46,7 @@ struct TcMapKeyHash {
 };
 struct TcContext {
     PFN_tmapEncodeTiled encode = nullptr;
-    bool attr_set[16] = {};
+    bool attr_set[24] = {};
     std::unordered_map<TcMapKey, CUtensorMap, TcMapKeyHash> maps;
 };
 
@@ -1266,6 +1266,15 @@ inline bool tc_grad_supported(const TcGradArgs& a) {
     return a.V >= 1 && a.H >= 1 && a.v.rows >= 1 && a.vm.rows >= 1 && a.v.p0 && a.h.p0 && a.vm.p0 && a.hm.p0;
 }
 
+// two-SM variant (gemm_tc2.cuh)
+inline bool tc_grad_cg2_eligible(const TcGradArgs& a, int num_sms);
+inline int tc_grad_cg2_splits(const TcGradArgs& a, int num_sms);
+inline cudaError_t launch_grad_cg2(TcContext& t, const TcGradMaps& maps, TcGradParams& p, int num_sms, cudaStream_t stream);
+inline bool& tc_grad_cg2_enabled() {
+    static bool on = [] { const char* v = getenv("SCDBM_GRAD_CG2"); return !(v && v[0] == '0'); }();
+    return on;
+}
+
 // number of K splits that fills the GPU when there are few output tiles
 // 256-row work tiles when they still fill the GPU
 inline int tc_grad_halves(const TcGradArgs& a, int num_sms) {
@@ -1273,6 +1282,7 @@ inline int tc_grad_halves(const TcGradArgs& a, int num_sms) {
     return tiles2 >= num_sms ? 2 : 1;
 }
 inline int tc_grad_splits(const TcGradArgs& a, int num_sms) {
+    if (tc_grad_cg2_enabled() && tc_grad_cg2_eligible(a, num_sms)) return tc_grad_cg2_splits(a, num_sms);
     const int rows = tc_grad_halves(a, num_sms) * TC_BM;
     const int tiles = (int)((a.V + rows - 1) / rows) * (int)((a.H + TG_BN - 1) / TG_BN);
     const int kb = (int)((a.v.rows + TC_BK - 1) / TC_BK);
@@ -1314,6 +1324,12 @@ inline cudaError_t launch_grad_tc(TcContext& t, const TcGradArgs& a, int num_sms
         ok = ok && tc_make_map_mn(t, &maps.b[s][0], B.p0, B.rows, a.H, B.ld);
         ok = ok && tc_make_map_mn(t, &maps.b[s][1], B.p1 ? B.p1 : B.p0, B.rows, a.H, B.ld);
         if (!ok) return cudaErrorInvalidValue;
+    }
+    if (p.nbias == 0 && tc_grad_cg2_enabled() && tc_grad_cg2_eligible(a, num_sms)) {
+        cudaError_t e = launch_grad_cg2(t, maps, p, num_sms, stream);
+        if (e != cudaSuccess || p.splits == 1) return e;
+        const int64_t n = a.V * a.H;
+        return launch_pdl(k_grad_reduce, dim3((unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8)), dim3(256), 0, stream, a.partial, p.splits, n, a.out);
     }
     p.stages = halves == 2 ? 3 : 4;
     const int smem = p.stages * tg_stage_bytes(halves) + 1024;

@@ -338,4 +338,224 @@ inline cudaError_t launch_gemm_cg2(TcContext& t, const TcOperandPlanes* ops, int
     return cg2_launch<3>(t, maps, p, num_sms, stream);
 }
 
+// =====================================================================================
+// Two-SM gradient GEMM (K5): dW[V x H] = s0 v'h + s1 vm'hm for the large shapes (C4: 20 000 x 1 024 over 108 192 samples).
+// A cluster computes a 256 x 256 tile of dW; each CTA stages its own 128 visible units (one plane per pass) and HALF of the
+// hidden units' planes (128 of 256): 16 KB + 2 x 16 KB per 1 024 MMA cycles = 48 B/clk/SM of operand traffic against 64 for
+// the single-SM kernel with 256-row tiles.  Pass structure, chunked accumulation and scaling as in k_grad_tc; barrier
+// protocol as in k_gemm_cg2.  Each epilogue warp owns 32 visible units x 64 hidden units of its CTA's 128 x 256 block.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1)
+    k_grad_cg2(const __grid_constant__ TcGradMaps maps, const __grid_constant__ TcGradParams p) {
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // F32 acc, F16 MN-major operands, M = N = 256
+    constexpr uint32_t TMEM_COLS = 512;        // 2 accumulator stages x 256 columns
+    constexpr int STAGE = tg_stage_bytes(1);   // 16 KB A plane + 2 x 16 KB B half-planes
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_holder;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int svc = warp - 16;
+    const uint32_t rank = cluster_ctarank();
+    const int ncl = (int)(gridDim.x >> 1), cl = (int)(blockIdx.x >> 1);
+    const int nwork = p.m_tiles * p.n_tiles * p.splits;
+
+    if (svc == 1 && lane == 0) {
+        for (int i = 0; i < p.stages; ++i) { mbar_init(smem_u32(&bar_full[i]), 1); mbar_init(smem_u32(&bar_empty[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bar_tfull[i]), 1); mbar_init(smem_u32(&bar_tempty[i]), 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    } else if (svc == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_holder;
+
+    auto kb_range = [&](int s, int sp, int& lo, int& hi) {
+        lo = (int)((int64_t)p.kblocks[s] * sp / p.splits);
+        hi = (int)((int64_t)p.kblocks[s] * (sp + 1) / p.splits);
+    };
+    auto pass_masks = [&](int s, int kb, uint32_t& m0, uint32_t& m1) {
+        m0 = p.combos[s] & 3u;
+        m1 = (p.combos[s] >> 2) & 3u;
+        if (p.a_hiflag[s] && (p.a_hiflag[s][kb / 2] & 1u) == 0u) m1 = 0u;      // COUNT operand: hi plane unused in this 128-sample block
+    };
+
+    if (svc == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = cl; w < nwork; w += ncl) {
+                const int tile = w / p.splits, sp = w % p.splits;
+                const int m0 = (tile / p.n_tiles) * 256 + (int)rank * 128, n0 = (tile % p.n_tiles) * 256 + (int)rank * 128;
+                for (int s = 0; s < 2; ++s) {
+                    int lo, hi;
+                    kb_range(s, sp, lo, hi);
+                    for (int kb = lo; kb < hi; ++kb) {
+                        uint32_t pm[2];
+                        pass_masks(s, kb, pm[0], pm[1]);
+                        for (int pa = 0; pa < 2; ++pa) {
+                            if (!pm[pa]) continue;
+                            const int nb = (pm[pa] & 2u) ? 2 : 1;
+                            mbar_wait_parked(smem_u32(&bar_empty[stage]), phase ^ 1u);
+                            const uint32_t full_leader = smem_u32(&bar_full[stage]) & C2_PEER_MASK;
+                            const uint32_t sa = smem_base + (uint32_t)stage * STAGE, sb = sa + TG_PLANE;
+                            if (rank == 0) mbar_expect_tx(smem_u32(&bar_full[stage]), 2u * (uint32_t)((1 + nb) * TG_PLANE));
+                            for (int blk = 0; blk < 2; ++blk) tma_load_2d_cg2(sa + blk * 8192, &maps.a[s][pa], full_leader, m0 + blk * 64, kb * TC_BK);
+                            for (int pb = 0; pb < nb; ++pb)
+                                for (int blk = 0; blk < 2; ++blk)
+                                    tma_load_2d_cg2(sb + pb * TG_PLANE + blk * 8192, &maps.b[s][pb], full_leader, n0 + blk * 64, kb * TC_BK);
+                            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (svc == 1) {
+        if (lane == 0 && rank == 0) {
+            int stage = 0, astage = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int w = cl; w < nwork; w += ncl) {
+                const int sp = w % p.splits;
+                for (int s = 0; s < 2; ++s) {
+                    int lo, hi;
+                    kb_range(s, sp, lo, hi);
+                    const int n = hi - lo;
+                    if (n <= 0) continue;
+                    const int nch = (n + TC_CHUNK_KB - 1) / TC_CHUNK_KB, per = (n + nch - 1) / nch;
+                    int in_chunk = 0;
+                    uint32_t accumulate = 0;
+                    for (int kb = lo; kb < hi; ++kb) {
+                        if (in_chunk == 0) {
+                            mbar_wait_parked(smem_u32(&bar_tempty[astage]), aphase ^ 1u);
+                            tc_fence_after();
+                            accumulate = 0;
+                        }
+                        const uint32_t tmem_d = tmem_base + (uint32_t)astage * 256u;
+                        uint32_t pm[2];
+                        pass_masks(s, kb, pm[0], pm[1]);
+                        for (int pa = 0; pa < 2; ++pa) {
+                            if (!pm[pa]) continue;
+                            mbar_wait_parked(smem_u32(&bar_full[stage]), phase);
+                            tc_fence_after();
+                            const uint32_t sa = smem_base + (uint32_t)stage * STAGE, sb = sa + TG_PLANE;
+#pragma unroll
+                            for (int pb = 0; pb < 2; ++pb) {
+                                if (!((pm[pa] >> pb) & 1u)) continue;
+#pragma unroll
+                                for (int k = 0; k < TC_BK / 16; ++k) {
+                                    tc_mma_f16_cg2(tmem_d, umma_desc_mn_sw128(sa + k * 2048), umma_desc_mn_sw128(sb + pb * TG_PLANE + k * 2048), IDESC, accumulate);
+                                    accumulate = 1;
+                                }
+                            }
+                            tc_commit_cg2(smem_u32(&bar_empty[stage]), 3);
+                            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                        }
+                        if (++in_chunk == per || kb + 1 == hi) {
+                            tc_commit_cg2(smem_u32(&bar_tfull[astage]), 3);
+                            if (++astage == 2) { astage = 0; aphase ^= 1u; }
+                            in_chunk = 0;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (svc < 0) {
+        const int q = warp & 3, slice = warp >> 2;
+        int astage = 0;
+        uint32_t aphase = 0;
+        for (int w = cl; w < nwork; w += ncl) {
+            const int tile = w / p.splits, sp = w % p.splits;
+            const int64_t m0 = (int64_t)(tile / p.n_tiles) * 256 + (int64_t)rank * 128, nn0 = (int64_t)(tile % p.n_tiles) * 256;
+            float sum[64];
+#pragma unroll
+            for (int i = 0; i < 64; ++i) sum[i] = 0.0f;
+            for (int s = 0; s < 2; ++s) {
+                int lo, hi;
+                kb_range(s, sp, lo, hi);
+                const int n = hi - lo;
+                if (n <= 0) continue;
+                const int nch = (n + TC_CHUNK_KB - 1) / TC_CHUNK_KB;
+                const float sc = p.scale[s];
+                for (int c = 0; c < nch; ++c) {
+                    mbar_wait_parked(smem_u32(&bar_tfull[astage]), aphase);
+                    tc_fence_after();
+                    const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)astage * 256u + (uint32_t)(slice * 64);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint32_t r[16];
+                        tmem_ld16(ta + g * 16, r);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) sum[g * 16 + i] = fmaf(sc, __uint_as_float(r[i]), sum[g * 16 + i]);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(smem_u32(&bar_tempty[astage]), 0);
+                    if (++astage == 2) { astage = 0; aphase ^= 1u; }
+                }
+            }
+            float* dst = (p.splits > 1 ? p.partial + (int64_t)sp * p.V * p.H : p.out);
+            const int64_t c0 = nn0 + slice * 64;
+            const bool vec = c0 + 64 <= p.H && (p.H & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0u;
+            const int64_t row = m0 + q * 32 + lane;
+            if (row < p.V) {
+                float* d = dst + row * p.H + c0;
+                if (vec) {
+#pragma unroll
+                    for (int i = 0; i < 64; i += 4) *reinterpret_cast<float4*>(d + i) = make_float4(sum[i], sum[i + 1], sum[i + 2], sum[i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i)
+                        if (c0 + i < p.H) d[i] = sum[i];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (svc == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// the two-SM gradient kernel serves shapes with at least two waves of 256 x 256 cluster tiles and many samples
+inline bool tc_grad_cg2_eligible(const TcGradArgs& a, int num_sms) {
+    if (a.V < 256 || a.H < 256 || std::max(a.v.rows, a.vm.rows) <= 16384) return false;
+    return ((a.V + 255) / 256) * ((a.H + 255) / 256) >= num_sms;
+}
+// K splits that even out the last wave of cluster tiles (partial sums are reduced in fixed order by k_grad_reduce)
+inline int tc_grad_cg2_splits(const TcGradArgs& a, int num_sms) {
+    const int64_t tiles = ((a.V + 255) / 256) * ((a.H + 255) / 256);
+    const int ncl = num_sms / 2;
+    int best = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= 4; ++s) {
+        const double waves = (double)(tiles * s) / ncl;
+        const double eff = waves / std::ceil(waves) - 0.01 * (s - 1);     // each extra split costs a slab of traffic
+        if (eff > best_eff) { best_eff = eff; best = s; }
+    }
+    return best;
+}
+
+inline cudaError_t launch_grad_cg2(TcContext& t, const TcGradMaps& maps, TcGradParams& p, int num_sms, cudaStream_t stream) {
+    p.m_tiles = (int)((p.V + 255) / 256);
+    p.n_tiles = (int)((p.H + 255) / 256);
+    p.stages = 4;
+    p.nbias = 0;
+    const int smem = p.stages * tg_stage_bytes(1) + 1024;
+    if (!t.attr_set[16]) {
+        cudaError_t e = cudaFuncSetAttribute(k_grad_cg2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        t.attr_set[16] = true;
+    }
+    const int nwork = p.m_tiles * p.n_tiles * p.splits;
+    const int clusters = std::min(nwork, num_sms / 2);
+    k_grad_cg2<<<2 * clusters, TG_THREADS, smem, stream>>>(maps, p);
+    return cudaGetLastError();
+}
+
 }  // namespace scdbm

@@ -352,3 +352,30 @@ def test_two_sm_bernoulli_draws_match_single_sm(pkg, two_sm, auto):
     pot = om.hiddenpotential(dbm[0], x)
     z = (outs[0][0].mean(0) - pot.mean(0)) / np.sqrt((pot * (1 - pot)).mean(0) / n + 1e-12)
     assert np.abs(z).max() < 5.0
+
+
+def test_two_sm_gradient(pkg, auto):
+    """Two-SM gradient kernel (k_grad_cg2): >= 148 cluster tiles of 256 x 256, ragged in both unit axes, more than 16 384
+    positive samples (chunk-promoted accumulation, split-K evening out the last wave), count x real positive phase with
+    one 128-sample block that uses the hi count plane, count x binary negative phase."""
+    V, H, n, n2 = 3000, 3300, 16384 + 53, 300
+    g = np.random.default_rng(11)
+    v = g.poisson(0.4, (n, V)).astype(float)
+    v[700, 5] = 5000.0
+    h = g.random((n, H))
+    vm = g.poisson(0.4, (n2, V)).astype(float)
+    hm = (g.random((n2, H)) < 0.5).astype(float)
+    m = pkg.DeviceModel(auto, [V, H], pkg.VIS_NEGBIN)
+    opt = pkg.loglikelihoodoptimizer(m, learningrate=0.01)
+    mats = [pkg.Mat.from_host(auto, v, pkg.MAT_COUNT), pkg.Mat.from_host(auto, vm, pkg.MAT_COUNT),
+            pkg.Mat.from_host(auto, h, pkg.MAT_REAL), pkg.Mat.from_host(auto, hm, pkg.MAT_BINARY)]
+    opt.computegradient_(*mats, m)
+    W, a, b = opt.gradient(0)
+    refW = v.T @ h / n - vm.T @ hm / n2
+    refa = v.mean(0) - vm.mean(0)
+    refb = h.mean(0) - hm.mean(0)
+    eW = np.max(np.abs(W - refW)) / np.abs(refW).max()
+    ea = np.max(np.abs(a - refa)) / np.abs(refa).max()
+    eb = np.max(np.abs(b - refb)) / np.abs(refb).max()
+    print(f"[two-SM gradient] dW {eW:.2e}, da {ea:.2e}, db {eb:.2e} (norm-wise)")
+    assert max(eW, ea, eb) < RTOL
