@@ -80,7 +80,7 @@ constexpr int TC_MAX_STAGES = 8;
 #ifndef SCDBM_NB_EPW      // epilogue warps of the wide NB sampling kernel; its tile is 8 * SCDBM_NB_EPW columns
 #define SCDBM_NB_EPW 28
 #endif
-constexpr int TC_QCAP = 192, TC_SCAP = 64, TC_NB_STEPS = SCDBM_NB_STEPS;
+constexpr int TC_QCAP = 176, TC_SCAP = 64, TC_NB_STEPS = SCDBM_NB_STEPS;
 #ifndef SCDBM_NB_DYN      // 1: the epilogue warps of a row quadrant claim (tile, slice) items dynamically
 #define SCDBM_NB_DYN 1
 #endif
@@ -95,8 +95,11 @@ static_assert(SCDBM_NB_ASTAGES * TC_NB_BN <= 512, "NB kernel: accumulator stages
 // Long contractions (K >= 512: the 1 024-unit hidden layer of configs C4 / C5): the 28 epilogue warps' queues leave room for ONE
 // 73 KB operand stage, so every k-block's load -> MMA round trip (~2 us) is exposed: 16 of them per tile, 3x the
 // epilogue's time.  There the NB class runs 20 epilogue warps on 160-column tiles: two operand stages fit, and three
-// accumulator stages (480 TMEM columns).
-constexpr int TC_NBK_EPW = 20, TC_NBK_BN = 8 * TC_NBK_EPW, TC_NBK_MIN_KB = 8;
+// accumulator stages (480 TMEM columns).  (16 warps / 128 columns / three operand stages measured 4 % slower.)
+#ifndef SCDBM_NBK_EPW
+#define SCDBM_NBK_EPW 20
+#endif
+constexpr int TC_NBK_EPW = SCDBM_NBK_EPW, TC_NBK_BN = 8 * TC_NBK_EPW, TC_NBK_MIN_KB = 8;
 // ... and the slice's per-gene constants (nbc: 16 B, threshold: 4 B per column): with the shared-memory carve-out at its
 // maximum the L1 is too small to keep the per-gene tables, and every gather from them was an L2 round trip
 __host__ __device__ constexpr int tc_epi_smem(int cw) { return TC_QCAP * 8 + TC_SCAP * 16 + 32 * cw * 2 + cw * 20; }
@@ -857,12 +860,13 @@ inline bool tc_supported(const GemmArgs& g, int nsrc) {
 
 template <int BN, int EK, int EPW>
 inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, int num_sms, cudaStream_t stream) {
-    const int slot = BN == TC_NBK_BN ? 10 : (BN == 64 ? 0 : BN == 128 ? 4 : 8) + EK;   // wide NB kernel: slot 9
+    const int slot = (EK == 1 && BN == TC_NBK_BN) ? 10 : (BN == 64 ? 0 : BN == 128 ? 4 : 8) + EK;   // wide NB kernel: slot 9
     constexpr int B_TILE = BN * TC_BK * 2;
     const int qbytes = (EK == 1) ? EPW * tc_epi_smem(BN / (EPW / 4)) : 0;
     p.a_tiles = std::max(p.split_hi[0] ? 1 : p.nA[0], p.nsrc > 1 ? (p.split_hi[1] ? 1 : p.nA[1]) : 1);
     p.stage_bytes = p.a_tiles * (p.pair ? 2 : 1) * TC_A_TILE + 2 * B_TILE;
-    p.stages = std::max(1, std::min(TC_MAX_STAGES, (TC_SMEM_BUDGET + 20 * 1024 - qbytes) / p.stage_bytes));
+    // (the NB class takes all 227 KB: its queues leave little room for operand stages)
+    p.stages = std::max(1, std::min(TC_MAX_STAGES, ((EK == 1 ? 225 * 1024 : TC_SMEM_BUDGET + 20 * 1024) - qbytes) / p.stage_bytes));
     // no more stages than k-blocks of a tile: a small shared-memory request keeps latency-bound launches cheap
     p.stages = std::max(1, std::min(p.stages, p.kblocks[0] * (p.split_hi[0] ? 2 : 1) + (p.nsrc > 1 ? p.kblocks[1] * (p.split_hi[1] ? 2 : 1) : 0)));
     const int smem = p.stages * p.stage_bytes + 1024 + qbytes;
