@@ -192,6 +192,49 @@ __device__ __forceinline__ void epi_det4(const EpiParams& e, int64_t row, int64_
     mat_store4(e.out, row, col0, o, nvalid);
 }
 
+// The same class for a TRANSPOSED accumulator (two-SM kernel, lane = output unit, the 4 values are 4 consecutive rows of
+// one column): every global access of a warp is then 32 consecutive units of one row -- coalesced 128-byte segments --
+// where the row-per-lane form touches 32 different lines per instruction (the mean-field sweeps at 100 000 cells were
+// bound by that: 129 M sector transactions for 66 M sectors of data, ncu capture prof_r02_c4mf).
+__device__ __forceinline__ void epi_det4t(const EpiParams& e, int64_t row0, int nrows, int64_t col, const float (&acc)[4],
+                                          float& delta_local, float bias, float r) {
+    float add[4] = {0.0f, 0.0f, 0.0f, 0.0f}, old[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (e.mode == EPI_RAW_F32) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < nrows) e.out_f32[(row0 + j) * e.ldo + col] = acc[j];
+        return;
+    }
+    if (e.addend) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < nrows) add[j] = e.addend[(row0 + j) * e.ld_add + col];
+#pragma unroll 1
+        for (int sp = 1; sp < e.addend_splits; ++sp)
+            for (int j = 0; j < nrows; ++j) add[j] += e.addend[(int64_t)sp * e.addend_stride + (row0 + j) * e.ld_add + col];
+        if (e.addend_scaled)
+            for (int j = 0; j < 4; ++j) add[j] *= e.wscale;
+    }
+    if (e.prev.p0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < nrows) old[j] = e.prev.f ? e.prev.f[(row0 + j) * e.prev.ld + col] : mat_load(e.prev, row0 + j, col);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j >= nrows) continue;
+        const float x = e.factor * fmaf(e.wscale, acc[j], bias + add[j]);
+        const float o = e.mode == EPI_SIGM ? sigmf(x) : e.mode == EPI_NBMEAN ? nb_mean(x, r) : x;
+        if (e.prev.p0) delta_local = fmaxf(delta_local, fabsf(old[j] - o));
+        plane_t a, b;
+        split_value(e.out.kind, o, a, b);
+        const int64_t i = (row0 + j) * e.out.ld + col;
+        if (e.out.f) e.out.f[i] = o;
+        e.out.p0[i] = a;
+        if (e.out.p1) e.out.p1[i] = b;
+    }
+}
+
 // ---- specialised sampling epilogues (tensor-core engine, Philox-fed): 4 consecutive columns
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
     const __half2 v = __floats2half2_rn(lo, hi);

@@ -128,6 +128,8 @@ struct TcParams {
                           //      a slice of the k-blocks and stores raw fp32 partial sums (EPI_RAW_F32) into its own slab
     int32_t sched;        // 1: a CTA owns whole m-tiles and walks all n-tiles (balanced over genes, A re-used
                           //    back-to-back); 0: flat round-robin over (m, n) tiles, n fastest (few m-tiles)
+    int32_t tposed;       // two-SM kernel, deterministic class: the MMA's roles are swapped (weights as the "A" operand), the
+                          //    accumulator holds out^T (lane = output unit) and the epilogue's global accesses are coalesced
     int32_t mfast;        // flat order with the ROW tile fastest: the concurrently running CTAs share one weight tile and
                           //    re-stream the (smaller) state operand instead of all weight planes
     EpiParams epi;

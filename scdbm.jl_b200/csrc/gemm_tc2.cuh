@@ -79,6 +79,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 + C2_EPW), 1
     const uint32_t rank = cluster_ctarank();
     const int ncl = (int)(gridDim.x >> 1), cl = (int)(blockIdx.x >> 1);
     const int nwork = p.m_tiles * p.n_tiles;
+    const bool tposed = EK == 3 && p.tposed != 0;
 
     if (svc == 1 && lane == 0) {
         for (int i = 0; i < p.stages; ++i) {
@@ -158,8 +159,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 + C2_EPW), 1
                             if (!((combos >> c) & 1u)) continue;
                             const uint32_t a0 = sa + (c >> 1) * TC_A_TILE, b0 = sb + (c & 1) * C2_B_TILE;
 #pragma unroll
-                            for (int k = 0; k < TC_BK / 16; ++k)
-                                tc_mma_f16_cg2(tmem_d, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), IDESC,
+                            for (int k = 0; k < TC_BK / 16; ++k)     // tposed: the weight tile is the MMA's "A" (rows of D = output units)
+                                tc_mma_f16_cg2(tmem_d, umma_desc_k_sw128((tposed ? b0 : a0) + k * 32), umma_desc_k_sw128((tposed ? a0 : b0) + k * 32), IDESC,
                                                (accumulate | (uint32_t)(c != __ffs(combos) - 1) | (uint32_t)k) ? 1u : 0u);
                         }
                         accumulate = 1;
@@ -187,6 +188,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 + C2_EPW), 1
             const int64_t m0 = (int64_t)mt * 256 + (int64_t)rank * TC_BM, n0 = (int64_t)nt * C2_BN;
             // this lane's two columns of the warp's slice: summed biases, inverse dispersion
             float bias_l[2] = {0.0f, 0.0f}, r_l[2] = {1.0f, 1.0f};
+            // transposed accumulator: this lane's output unit, its summed biases and inverse dispersion
+            const int64_t unit = n0 + (int64_t)rank * 128 + q * 32 + lane;
+            if (tposed) {
+                if (unit < p.N) {
+                    if (p.epi.bias0) bias_l[0] = __ldg(p.epi.bias0 + unit);
+                    if (p.epi.bias1) bias_l[0] += __ldg(p.epi.bias1 + unit);
+                    if (p.epi.r && p.epi.mode == EPI_NBMEAN) r_l[0] = __ldg(p.epi.r + unit);
+                }
+            } else
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
                 const int64_t c = n0 + slice * C2_CW + t * 32 + lane;
@@ -196,7 +206,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 + C2_EPW), 1
                     if (p.epi.r && p.epi.mode == EPI_NBMEAN) r_l[t] = __ldg(p.epi.r + c);
                 }
             }
-            if constexpr (EK == 3) epi_prefetch_extras(p.epi, m0 + q * 32 + lane, p.M, n0 + slice * C2_CW, p.N, C2_CW);
+            if constexpr (EK == 3) {
+                if (!tposed) epi_prefetch_extras(p.epi, m0 + q * 32 + lane, p.M, n0 + slice * C2_CW, p.N, C2_CW);
+            }
             const int nch = tc_chunks(tc_tile_kblocks(p, mt));
             if (nch > 1) {   // chunked accumulation with fp32 promotion (see tc_chunks)
                 float sum[C2_CW];
@@ -236,6 +248,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 + C2_EPW), 1
             }
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(astage * C2_BN + slice * C2_CW);
             const int64_t row = m0 + q * 32 + lane;
+            if (tposed) {
+                if constexpr (EK == 3) {
+                    // TMEM column = row of the 256-row cluster tile (both CTAs' rows), lane = output unit
+                    const int64_t row0 = (int64_t)mt * 256 + slice * C2_CW;
+#pragma unroll 1
+                    for (int g = 0; g < C2_CW / 4; ++g) {
+                        uint32_t r[4];
+                        tmem_ld4(taddr + g * 4, r);
+                        tmem_wait_ld();
+                        const int nrows = (int)max((int64_t)0, min((int64_t)4, p.M - (row0 + g * 4)));
+                        if (unit < p.N && nrows > 0) {
+                            const float acc[4] = {__uint_as_float(r[0]) * acc_scale, __uint_as_float(r[1]) * acc_scale, __uint_as_float(r[2]) * acc_scale,
+                                                  __uint_as_float(r[3]) * acc_scale};
+                            epi_det4t(p.epi, row0 + g * 4, nrows, unit, acc, delta_local, bias_l[0], r_l[0]);
+                        }
+                    }
+                }
+            } else
 #pragma unroll 1
             for (int g = 0; g < C2_CW / 4; ++g) {
                 uint32_t r[4];
@@ -335,6 +365,8 @@ inline cudaError_t launch_gemm_cg2(TcContext& t, const TcOperandPlanes* ops, int
     }
     if (nsrc == 1) { maps.a[1][0] = maps.a[0][0]; maps.a[1][1] = maps.a[0][1]; maps.b[1][0] = maps.b[0][0]; maps.b[1][1] = maps.b[0][1]; }
     if (ek == 2) return cg2_launch<2>(t, maps, p, num_sms, stream);
+    static const bool tposed_on = [] { const char* v = getenv("SCDBM_CG2T"); return !(v && v[0] == '0'); }();
+    p.tposed = tposed_on ? 1 : 0;
     return cg2_launch<3>(t, maps, p, num_sms, stream);
 }
 

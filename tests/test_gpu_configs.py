@@ -379,3 +379,23 @@ def test_two_sm_gradient(pkg, auto):
     eb = np.max(np.abs(b - refb)) / np.abs(refb).max()
     print(f"[two-SM gradient] dW {eW:.2e}, da {ea:.2e}, db {eb:.2e} (norm-wise)")
     assert max(eW, ea, eb) < RTOL
+
+
+def test_two_sm_meanfield(pkg, two_sm):
+    """Mean-field at a row count where the layer-1 sweep (hoisted addend, previous value, max |change|) runs the two-SM
+    kernel with the transposed accumulator: ragged rows, explicit iteration counts and the stopping rule."""
+    units = [1500, 1024, 256, 64]
+    n = 256 * 19 + 41
+    dbm = synth.random_dbm(units, 23)
+    m = pkg.DeviceModel.from_host(to_pkg_model(pkg, dbm), two_sm)
+    x, _, _ = synth.counts(n, units[0], seed=8)
+    for maxiter in (1, 3):
+        got = pkg.meanfield(m, x, eps=0.0, maxiter=maxiter, ctx=two_sm)
+        ref, _, _ = om.meanfield(dbm, x, eps=0.0, maxiter=maxiter)
+        errs = [relerr(a, b) for a, b in zip(got[1:], ref[1:])]
+        print(f"[two-SM] mean-field, {maxiter} iteration(s): relative error per layer {errs}")
+        assert max(errs) < RTOL
+    got, it, delta = pkg.meanfield(m, x, eps=1e-3, return_info=True, ctx=two_sm)
+    ref, rit, rdelta = om.meanfield(dbm, x, eps=1e-3)
+    print(f"[two-SM] mean-field eps=1e-3: {it} iterations (oracle {rit}), delta {delta:.3e} (oracle {rdelta:.3e})")
+    assert it == rit and abs(delta - rdelta) < 1e-4 * max(rdelta, 1e-6) + 1e-7
