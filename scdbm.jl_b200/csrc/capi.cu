@@ -392,6 +392,17 @@ static void run_gemm(scdbm_ctx* ctx, GemmArgs& g, const SweepSrc* srcs, int nsrc
             CK(launch_gemm_tc(ctx->tc, ops, nsrc, g, ctx->num_sms, ctx->stream));
         }
         ctx->tc_launches++;
+    } else if (!srcs && nsrc == 0 && g.epi.addend && (g.epi.ld_add & 3) == 0 && (reinterpret_cast<uintptr_t>(g.epi.addend) & 15u) == 0u &&
+               !g.epi.prev.p0 && !g.epi.uniforms && !g.epi.skip &&
+               (g.epi.mode == EPI_INPUT || g.epi.mode == EPI_SIGM || g.epi.mode == EPI_NBMEAN)) {
+        // no contraction at all (mean-field initialisation from the hoisted x W1): an elementwise pass, coalesced
+        set_hiflags(ctx, g.epi.out, true);
+        EpiParams e = g.epi;
+        e.wscale = e.addend_scaled ? e.wscale : 1.0f;
+        e.addend = nullptr;
+        const int64_t nthreads = g.M * ((g.N + 3) / 4);
+        CK(launch_pdl(k_det_finish, dim3((unsigned)((nthreads + 127) / 128)), dim3(128), 0, ctx->stream, g.epi.addend, std::max(g.epi.addend_splits, 1),
+                      g.epi.addend_stride, g.epi.ld_add, e, g.M, g.N));
     } else {
         set_hiflags(ctx, g.epi.out, true);
         CK(launch_gemm_simt(g, ctx->stream));
