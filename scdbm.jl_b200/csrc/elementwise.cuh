@@ -185,6 +185,12 @@ __global__ void k_det_finish(const float* __restrict__ ws, int S, int64_t stride
         const float x = e.factor * fmaf(e.wscale, o[j], b);
         o[j] = e.mode == EPI_SIGM ? sigmf(x) : e.mode == EPI_NBMEAN ? nb_mean(x, e.r[col0 + j]) : x;
     }
+    if (e.mode == EPI_SIGM_BERN) {      // Philox-fed Bernoulli draw, the counters of epi_bern4 (o[] holds the inputs)
+        const uint4 w = philox_group_rk(e, (uint32_t)row, (uint32_t)(col0 >> 2));
+        const float u[4] = {u23(w.x), u23(w.y), u23(w.z), u23(w.w)};
+        for (int j = 0; j < nvalid; ++j) e.out.p0[row * e.out.ld + col0 + j] = plane_encode(bern_draw_fast(o[j], u[j]));
+        return;
+    }
     mat_store4(e.out, row, col0, o, nvalid);
 }
 

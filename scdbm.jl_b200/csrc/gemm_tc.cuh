@@ -913,11 +913,15 @@ inline int tc_epilogue_class(const GemmArgs& g, const TcOperandPlanes* ops, int 
 // Returns the number of splits (1: none).
 inline int tc_plan_split(const GemmArgs& g, const TcOperandPlanes* ops, int nsrc, int num_sms) {
     const EpiParams& e = g.epi;
-    if (tc_epilogue_class(g, ops, nsrc) != 3 || e.mode == EPI_RAW_F32 || e.addend || e.prev.p0 || e.skip) return 1;
+    const int ek = tc_epilogue_class(g, ops, nsrc);
+    // deterministic class, or the Philox-fed Bernoulli draw (the finishing launch draws: same counters, same samples up to
+    // the rounding of the partial sums)
+    if ((ek != 3 && ek != 2) || e.mode == EPI_RAW_F32 || e.addend || e.prev.p0 || e.skip) return 1;
     const int64_t tiles = ((g.M + TC_BM - 1) / TC_BM) * ((g.N + 127) / 128);
     if (tiles * 4 > num_sms) return 1;
     int kb = 0;
     for (int s = 0; s < nsrc; ++s) kb += (int)((ops[s].K + TC_BK - 1) / TC_BK);
+    if (ek == 2 && kb < 8) return 1;
     const int S = (int)std::min<int64_t>({16, kb / 2, num_sms / tiles});
     return S >= 2 ? S : 1;
 }

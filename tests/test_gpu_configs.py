@@ -399,3 +399,21 @@ def test_two_sm_meanfield(pkg, two_sm):
     ref, rit, rdelta = om.meanfield(dbm, x, eps=1e-3)
     print(f"[two-SM] mean-field eps=1e-3: {it} iterations (oracle {rit}), delta {delta:.3e} (oracle {rdelta:.3e})")
     assert it == rit and abs(delta - rdelta) < 1e-4 * max(rdelta, 1e-6) + 1e-7
+
+
+def test_c2_gibbs_draws_match_oracle(pkg, auto):
+    """100 particles of the C2 model, same Philox counters as the oracle (gate G2).  At this row count the dual-source
+    up-sweep h1 | v, h2 (K = 2000 + 64) runs split-K with the Bernoulli draw in the finishing launch."""
+    units, P = [2000, 256, 64], 100
+    dbm = synth.random_dbm(units, 3)
+    m = pkg.DeviceModel.from_host(to_pkg_model(pkg, dbm), auto)
+    auto.set("seed", SEED)
+    p = pkg.initparticles(m, P, device=True)
+    ref = om.initparticles(dbm, P, px.Rng(SEED))
+    before = auto.launch_count()
+    pkg.gibbssample_(p, m, 3)
+    print(f"[C2] launches per Gibbs sweep: {(auto.launch_count() - before) / 3:.1f}")
+    om.gibbssample_dbm(ref, dbm, px.Rng(SEED), 3)
+    mism = [float(np.mean(a != b)) for a, b in zip(p.to_host(), ref)]
+    print(f"[C2] fraction of differing entries per layer after 3 sweeps: {mism}")
+    assert max(mism) < 5e-3
