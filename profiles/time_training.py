@@ -40,6 +40,13 @@ if a.only in ("", "c2"):
         pkg.traindbm_(dm, x2m, epochs=20, particles=p, learningrate=1e-4, device=True, ctx=ctx)
         best = min(best, ctx.timer_stop())
     print(f"C2: {20 / best * 1e3:.0f} steps/s, {best / 20 * 1e3:.0f} us per step, {ctx.launch_count() / 60:.1f} launches per step")
+    # how many mean-field iterations does a step run at this point of training?  (launched in groups of 4)
+    import ctypes as C
+    mu = pkg.DeviceParticles(dm, x2m.rows, real_valued=True)
+    opt2 = pkg.LoglikelihoodOptimizer().initialized(dm)
+    it = C.c_int32()
+    pkg._lib.check(pkg.lib().scdbm_dbm_pcd_step(dm.h, x2m.h, p.h, mu.h, opt2.h, 1e-4, 5, 0.001, C.byref(it)))
+    print(f"    mean-field iterations in the next step: {it.value}")
 if a.only not in ("", "ops"):
     sys.exit(0)
 # per-operator GPU time at the C1 minibatch shape (back-to-back launches, CUDA events)

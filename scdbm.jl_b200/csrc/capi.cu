@@ -9,6 +9,7 @@
 #include "comm.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
@@ -81,7 +82,8 @@ struct scdbm_ctx {
     // mean-field convergence state {delta bits, converged, iterations, last delta bits} on the device, mirrored into mapped
     // pinned host memory by k_mf_check so that the host reads it without a copy
     unsigned int* d_mf = nullptr;
-    unsigned int *h_mf = nullptr, *d_hmf = nullptr;
+    unsigned int *h_mf = nullptr, *d_hmf = nullptr;   // mapped mirror of the state: two 64-bit words, see k_mf_check
+    unsigned int mf_gen = 0;                          // generation tag of the current mean-field call
     // data-parallel communicator (scdbm_comm_init): NCCL over NVLink, collectives ordered on the context's streams
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
@@ -598,8 +600,9 @@ int32_t scdbm_ctx_create(int32_t device, uint64_t seed, void* stream, scdbm_ctx*
     CK(cudaHostAlloc(&c->h_flag, sizeof(unsigned int), cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer(&c->d_flag, c->h_flag, 0));
     *c->h_flag = 0u;
-    CK(cudaMalloc(&c->d_mf, 4 * sizeof(unsigned int)));
+    CK(cudaMalloc(&c->d_mf, 8 * sizeof(unsigned int)));
     CK(cudaHostAlloc(&c->h_mf, 4 * sizeof(unsigned int), cudaHostAllocMapped));
+    memset(c->h_mf, 0, 4 * sizeof(unsigned int));
     CK(cudaHostGetDevicePointer(&c->d_hmf, c->h_mf, 0));
     {   // keep freed state matrices in the device's default memory pool instead of returning them to the driver
         cudaMemPool_t pool;
@@ -1427,8 +1430,14 @@ int32_t scdbm_particles_visible_potential(scdbm_model* m, scdbm_particles* p, sc
 
 // -------------------------------------------------------------- mean-field
 // after one mean-field iteration: fold this iteration's max |change| into the convergence state.  One thread.
-//   st[0] delta bits of the iteration (reset), st[1] converged flag, st[2] iterations run, st[3] delta bits of the last one
-__global__ void k_mf_check(unsigned int* st, float eps, unsigned int* host_mirror) {
+//   st[0] delta bits of the iteration (reset), st[1] converged flag, st[2] iterations run, st[3] delta bits of the last one,
+//   st[4] number of checks executed in this mean-field call (skipped iterations included)
+// The state is mirrored into mapped host memory as two 64-bit words: {iterations, delta bits} first, then -- after a
+// system-wide fence -- {generation of the call, checks executed, converged}.  The host polls the second word instead of
+// synchronising the stream: it can move on the moment convergence is visible while the speculatively launched
+// iterations behind it drain as no-ops; the generation tag keeps a late check of the previous call from being
+// mistaken for this one's.
+__global__ void k_mf_check(unsigned int* st, float eps, unsigned long long* host_mirror, unsigned int gen) {
     pdl_trigger();
     pdl_wait();
     if (st[1] == 0u) {
@@ -1438,9 +1447,11 @@ __global__ void k_mf_check(unsigned int* st, float eps, unsigned int* host_mirro
         if (!(delta > eps)) st[1] = 1u;
     }
     st[0] = 0u;
-    host_mirror[1] = st[1];
-    host_mirror[2] = st[2];
-    host_mirror[3] = st[3];
+    st[4] += 1u;
+    volatile unsigned long long* hm = host_mirror;
+    hm[1] = ((unsigned long long)st[2] << 32) | (unsigned long long)st[3];
+    __threadfence_system();
+    hm[0] = ((unsigned long long)(gen & 0xFFFFu) << 48) | ((unsigned long long)st[4] << 8) | (unsigned long long)(st[1] & 1u);
 }
 
 static void nccl_check(ncclResult_t r, const char* what) {
@@ -1502,8 +1513,10 @@ static void meanfield_impl(scdbm_model* m, const scdbm_mat* x, double eps, int m
     // sweeps and report the delta reached (the caller sees delta > eps).
     const int MF_ITER_CAP = 10000, MF_GROUP = 4;
     const int cap = maxiter > 0 ? maxiter : MF_ITER_CAP;
-    CK(cudaMemsetAsync(c->d_mf, 0, 4 * sizeof(unsigned int), c->stream));
-    c->h_mf[1] = c->h_mf[2] = c->h_mf[3] = 0u;
+    CK(cudaMemsetAsync(c->d_mf, 0, 8 * sizeof(unsigned int), c->stream));
+    const unsigned int gen = (c->mf_gen = (c->mf_gen % 0xFFFFu) + 1u);     // 1 .. 65535
+    volatile unsigned long long* hm = reinterpret_cast<volatile unsigned long long*>(c->h_mf);
+    unsigned long long state = 0ull;
     skip = c->d_mf + 1;
     int launched = 0;
     bool done = !(1.0 > eps);   // `delta = 1.0; while delta > eps` (dbmtraining.jl:194)
@@ -1550,15 +1563,27 @@ static void meanfield_impl(scdbm_model* m, const scdbm_mat* x, double eps, int m
             }
             // non-negative floats order like their bit patterns: max over ranks of the uint32 word
             if (global_delta) nccl_check(nccl_api().AllReduce(c->d_mf, c->d_mf, 1, ncclUint32, ncclMax, c->comm, c->stream), "ncclAllReduce(max delta)");
-            CK(launch_pdl(k_mf_check, dim3(1), dim3(1), 0, c->stream, c->d_mf, (float)eps, c->d_hmf));
+            CK(launch_pdl(k_mf_check, dim3(1), dim3(1), 0, c->stream, c->d_mf, (float)eps, reinterpret_cast<unsigned long long*>(c->d_hmf), gen));
             c->launches++;
         }
         launched += group;
-        CK(cudaStreamSynchronize(c->stream));
-        done = c->h_mf[1] != 0u;
-        memcpy(&last_delta, &c->h_mf[3], sizeof(float));
+        // poll the mapped state word: converged, or every check of this group executed
+        for (unsigned int spins = 1;; ++spins) {
+            const unsigned long long w = hm[0];
+            if ((w >> 48) == gen && ((w & 1ull) || ((w >> 8) & 0xFFFFFFFFull) >= (unsigned long long)launched)) break;
+            if ((spins & 0x3FFu) == 0u) {      // a failed launch must not hang the host
+                const cudaError_t q = cudaStreamQuery(c->stream);
+                if (q == cudaSuccess) break;   // drained: the word below is final
+                if (q != cudaErrorNotReady) CK(q);
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        done = (hm[0] & 1ull) != 0ull;
+        state = hm[1];
     }
-    if (niter) *niter = (int)c->h_mf[2];
+    const unsigned int delta_bits = (unsigned int)(state & 0xFFFFFFFFull);
+    if (launched > 0) memcpy(&last_delta, &delta_bits, sizeof(float));
+    if (niter) *niter = (int)(state >> 32);
     if (delta_out) *delta_out = last_delta;
 }
 
