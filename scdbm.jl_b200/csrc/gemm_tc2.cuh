@@ -554,10 +554,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TG_THREADS, 1)
     }
 }
 
-// the two-SM gradient kernel serves shapes with at least two waves of 256 x 256 cluster tiles and many samples
+// the two-SM gradient kernel serves shapes with at least one wave of 256 x 256 cluster tiles and many samples
 inline bool tc_grad_cg2_eligible(const TcGradArgs& a, int num_sms) {
     if (a.da || a.V < 256 || a.H < 256 || a.v.rows + a.vm.rows < 32 * TC_BK) return false;
-    return ((a.V + 255) / 256) * ((a.H + 255) / 256) >= num_sms;
+    return ((a.V + 255) / 256) * ((a.H + 255) / 256) >= num_sms / 2;     // one wave of clusters; K splits even out the rest
 }
 // K splits that even out the last wave of cluster tiles (partial sums are reduced in fixed order by k_grad_reduce)
 inline int tc_grad_cg2_splits(const TcGradArgs& a, int num_sms) {
