@@ -79,7 +79,8 @@ int32_t scdbm_ctx_destroy(scdbm_ctx* ctx);
 int32_t scdbm_sync(scdbm_ctx* ctx);
 /* options: "engine" (0/1/2), "mu_inv_max" (NB inversion / gamma-Poisson switch),
  * "nb_pshift" (0 or 1e-6, quirk B5), "seed", "two_sm" (0/1: cta_group::2 sweep kernel
- * for wide Bernoulli / deterministic sweeps; same results) */
+ * for wide Bernoulli / deterministic sweeps; same results),
+ * "pdl" (0/1, process-wide: programmatic dependent launch of the library's kernels; same results) */
 int32_t scdbm_ctx_set_option(scdbm_ctx* ctx, const char* name, double value);
 int32_t scdbm_ctx_get_option(scdbm_ctx* ctx, const char* name, double* value);
 /* CUDA-event timer on the context's stream, and a count of the library's own

@@ -640,6 +640,7 @@ int32_t scdbm_ctx_set_option(scdbm_ctx* c, const char* name, double value) {
     else if (n == "nb_pshift") c->nb_pshift = (float)value;
     else if (n == "seed") c->seed = (uint64_t)value;
     else if (n == "two_sm") c->use_cg2 = value != 0.0;
+    else if (n == "pdl") pdl_enabled() = value != 0.0;          // process-wide: programmatic dependent launch on / off
     else throw Err(SCDBM_EINVAL, "unknown option: " + n);
     API_END
 }
@@ -653,6 +654,7 @@ int32_t scdbm_ctx_get_option(scdbm_ctx* c, const char* name, double* value) {
     else if (n == "nb_pshift") *value = c->nb_pshift;
     else if (n == "seed") *value = (double)c->seed;
     else if (n == "two_sm") *value = c->use_cg2 ? 1.0 : 0.0;
+    else if (n == "pdl") *value = pdl_enabled() ? 1.0 : 0.0;
     else if (n == "num_sms") *value = c->num_sms;
     else if (n == "tc_launches") *value = (double)c->tc_launches;
     else if (n == "comm_rank") *value = c->rank;

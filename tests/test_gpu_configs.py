@@ -354,11 +354,12 @@ def test_two_sm_bernoulli_draws_match_single_sm(pkg, two_sm, auto):
     assert np.abs(z).max() < 5.0
 
 
-def test_two_sm_gradient(pkg, auto):
-    """Two-SM gradient kernel (k_grad_cg2): >= 148 cluster tiles of 256 x 256, ragged in both unit axes, more than 16 384
-    positive samples (chunk-promoted accumulation, split-K evening out the last wave), count x real positive phase with
-    one 128-sample block that uses the hi count plane, count x binary negative phase."""
-    V, H, n, n2 = 3000, 3300, 16384 + 53, 300
+@pytest.mark.parametrize("V,H,n,n2", [(3000, 3300, 16384 + 53, 300), (2000, 2561, 2500, 97)])
+def test_two_sm_gradient(pkg, auto, V, H, n, n2):
+    """Two-SM gradient kernel (k_grad_cg2): one or more waves of 256 x 256 cluster tiles, ragged in both unit axes (the
+    second case has a hidden width that is not a multiple of 4: scalar stores), chunk-promoted accumulation, split-K
+    evening out the last wave, count x real positive phase with one 128-sample block that uses the hi count plane,
+    count x binary negative phase."""
     g = np.random.default_rng(11)
     v = g.poisson(0.4, (n, V)).astype(float)
     v[700, 5] = 5000.0
@@ -417,3 +418,25 @@ def test_c2_gibbs_draws_match_oracle(pkg, auto):
     mism = [float(np.mean(a != b)) for a, b in zip(p.to_host(), ref)]
     print(f"[C2] fraction of differing entries per layer after 3 sweeps: {mism}")
     assert max(mism) < 5e-3
+
+
+def test_programmatic_dependent_launch_changes_nothing(pkg):
+    """The kernels of a training chain are launched with programmatic stream serialization and wait
+    (griddepcontrol.wait) before touching memory: the same epochs with plain launches must give the same bits."""
+    n, V, H, B = 500, 1000, 128, 100
+    x, _, _ = synth.counts(n, V, seed=1)
+    out = []
+    for pdl in (1, 0):
+        c = pkg.Context(0, SEED)
+        c.set("pdl", pdl)
+        assert c.get("pdl") == float(pdl)
+        xm = pkg.Mat.from_host(c, x, pkg.MAT_COUNT)
+        m = pkg.DeviceModel(c, [V, H], pkg.VIS_NEGBIN)
+        m.init_layer(0, xm, seed=SEED)
+        tr = pkg.RBMTrainer(m, B, pcd=True)
+        for _ in range(6):
+            pkg.trainrbm_(m, xm, tr, 1e-3, 1)
+        out.append(m.get_layer(0))
+        c.set("pdl", 1)
+    for f in ("weights", "visbias", "hidbias"):
+        assert np.array_equal(getattr(out[0], f), getattr(out[1], f)), f
