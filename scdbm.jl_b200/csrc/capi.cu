@@ -592,6 +592,7 @@ int32_t scdbm_ctx_create(int32_t device, uint64_t seed, void* stream, scdbm_ctx*
     c->seed = seed;
     c->num_sms = prop.multiProcessorCount;
     if (const char* v = getenv("SCDBM_CG2")) c->use_cg2 = v[0] == '1';
+    c->tc.nb_cg2 = c->use_cg2;
     if (stream) c->stream = (cudaStream_t)stream;
     else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     CK(cudaEventCreate(&c->ev0));
@@ -639,7 +640,7 @@ int32_t scdbm_ctx_set_option(scdbm_ctx* c, const char* name, double value) {
     else if (n == "mu_inv_max") c->mu_inv_max = (float)value;
     else if (n == "nb_pshift") c->nb_pshift = (float)value;
     else if (n == "seed") c->seed = (uint64_t)value;
-    else if (n == "two_sm") c->use_cg2 = value != 0.0;
+    else if (n == "two_sm") { c->use_cg2 = value != 0.0; c->tc.nb_cg2 = c->use_cg2; }
     else if (n == "pdl") pdl_enabled() = value != 0.0;          // process-wide: programmatic dependent launch on / off
     else throw Err(SCDBM_EINVAL, "unknown option: " + n);
     API_END

@@ -47,6 +47,7 @@ struct TcMapKeyHash {
 struct TcContext {
     PFN_tmapEncodeTiled encode = nullptr;
     bool attr_set[24] = {};
+    bool nb_cg2 = true;     // NB class with long contractions: two SMs per 256-row tile (context option "two_sm")
     std::unordered_map<TcMapKey, CUtensorMap, TcMapKeyHash> maps;
 };
 
@@ -155,24 +156,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    uint32_t spins = 0;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (!done && ++spins > (1u << 26)) __trap();  // never hang the GPU: a protocol bug becomes a launch error
-    } while (!done);
-}
-// Waits that may last long (an epilogue warp ahead of the MMA issuer; the issuer waiting for a TMEM stage): the
-// try_wait carries a suspend-time hint, so the hardware parks the warp until the phase completes instead of the warp
-// re-polling -- with the default time limit the 28 epilogue warps of the NB kernel spent 13 % of the SM's issue
-// slots on ~57 polls per tile (ncu capture prof_r02a).
+// Every barrier wait: try_wait with a suspend-time hint (the hardware may park the warp; each mbarrier event of the CTA
+// wakes it, so a waiting warp still polls -- measured harmless: the polls do not take issue slots from working warps),
+// and a bounded number of wake-ups -- a protocol bug becomes a launch error, never a hang.
 #ifndef SCDBM_PARK_NS
 #define SCDBM_PARK_NS 20000
 #endif
@@ -191,8 +177,6 @@ __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) 
         if (++spins > (1u << 22)) __trap();   // never hang the GPU: a protocol bug becomes a launch error
     }
 }
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) { mbar_wait_parked(bar, parity); }
-__device__ __forceinline__ void mbar_wait_epi(uint32_t bar, uint32_t parity) { mbar_wait_parked(bar, parity); }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
@@ -212,6 +196,46 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- cluster / cta_group::2 forms (two-SM kernels)
+constexpr uint32_t C2_PEER_MASK = 0xFEFFFFFFu; // clears the CTA-rank bit of a shared::cluster address -> the leader's copy
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar_leader, int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar_leader), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_cg2(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+        "r"(cta)
+        : "memory");
+}
+
 // K-major, 128B-swizzled operand tile: 8-row groups of 1024 B (SBO), descriptor version 1 (sm_100)
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
     uint64_t d = 0;
@@ -275,12 +299,13 @@ __device__ __forceinline__ void nb_enqueue(uint32_t word, uint32_t T, uint32_t x
 }
 
 // tile schedule shared by the three warp roles: it = 0, 1, ... -> flat tile id m * n_tiles + n, or -1 at the end
-__device__ __forceinline__ int tc_tile(const TcParams& p, int it) {
+// (bid, nb: this CTA's -- or cluster's -- index and their number)
+__device__ __forceinline__ int tc_tile(const TcParams& p, int it, int bid, int nb) {
     if (p.sched) {
-        const int m = (int)blockIdx.x + (it / p.n_tiles) * (int)gridDim.x;
+        const int m = bid + (it / p.n_tiles) * nb;
         return m < p.m_tiles ? m * p.n_tiles + it % p.n_tiles : -1;
     }
-    const int t = (int)blockIdx.x + it * (int)gridDim.x;
+    const int t = bid + it * nb;
     if (t >= p.m_tiles * p.n_tiles * max(p.ksplit, 1)) return -1;     // split-K: t is a work item, see tc_split_range
     if (p.mfast) return (t % p.m_tiles) * p.n_tiles + t / p.m_tiles;   // row tile fastest: the CTAs share a weight tile
     return t;
@@ -330,14 +355,18 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // code small enough for the instruction cache.
 // EPW: number of epilogue warps (4 per column slice).  The sampling epilogue is latency-bound, so the NB
 // kernel runs 24 epilogue warps on 192-column tiles; the others 16 warps on 64/128-column tiles.
-template <int BN, int EK, int EPW>
+// CG2 (NB class with long contractions only): two CTAs of a cluster work on a 256-row tile with one cta_group::2 MMA per
+// k-step, each staging its own 128 rows and half of the weight tile (protocol: see gemm_tc2.cuh); launched with a
+// cluster dimension of 2.
+template <int BN, int EK, int EPW, bool CG2 = false>
 __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
+    static_assert(!CG2 || EK == 1, "the two-SM form of this kernel serves the NB class; see k_gemm_cg2 for the others");
     constexpr int NS = EPW / 4;          // column slices per tile
     constexpr int CW = BN / NS;          // columns per epilogue warp per tile (16 or 32)
-    constexpr int B_TILE = BN * TC_BK * 2;
+    constexpr int B_TILE = (CG2 ? BN / 2 : BN) * TC_BK * 2;     // CG2: this CTA's half of the weight tile
     constexpr int ASTAGES = (EK == 1 && BN == TC_NB_BN) ? SCDBM_NB_ASTAGES : (EK == 1 && BN == TC_NBK_BN) ? 3 : 2;    // TMEM accumulator stages
     constexpr uint32_t TMEM_COLS = (EK == 1) ? ((ASTAGES * BN <= 256) ? 256 : 512) : ((2 * ASTAGES * BN <= 256) ? 256 : 512);
-    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // c = F32, a = b = F16, K-major
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((CG2 ? 2 * TC_BM : TC_BM) >> 4) << 24);   // c = F32, a = b = F16, K-major
     static_assert(CW == 16 || CW == 32, "epilogue slice must be 16 or 32 columns");
 
     extern __shared__ uint8_t smem_raw[];
@@ -357,6 +386,8 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
     // a sub-partition, so the few instructions that keep the tensor pipe fed never queue behind the sampling epilogue.
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int svc = warp - EPW;
+    const uint32_t rank = CG2 ? cluster_ctarank() : 0u;                       // CTA of the pair; 0 = leader
+    const int bid = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, nbid = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (svc == 1 && lane == 0) {
         for (int i = 0; i < p.stages; ++i) {
@@ -365,19 +396,22 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
         }
         for (int i = 0; i < ASTAGES; ++i) {
             mbar_init(smem_u32(&bar_tfull[i]), 1);
-            mbar_init(smem_u32(&bar_tempty[i]), EPW);
+            mbar_init(smem_u32(&bar_tempty[i]), CG2 ? 2 * EPW : EPW);
         }
         for (int i = 0; i < 4; ++i) dyn_item[i] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     } else if (svc == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
-                     "r"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CG2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_holder;
     pdl_trigger();      // this CTA holds its TMEM columns: the next launch may start setting up
@@ -388,12 +422,13 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
             // ===================== TMA producer
             int stage = 0;
             uint32_t phase = 0;
-            for (int it = 0, work; (work = tc_tile(p, it)) >= 0; ++it) {
+            for (int it = 0, work; (work = tc_tile(p, it, bid, nbid)) >= 0; ++it) {
                 const int rows = p.pair ? 2 * TC_BM : TC_BM;
                 const uint32_t a_bytes = (uint32_t)rows * TC_BK * 2;
                 int tile, klo, khi;
                 tc_split_range(p, work, tc_tile_kblocks(p, (p.ksplit > 1 ? work / p.ksplit : work) / p.n_tiles), tile, klo, khi);
-                const int m0 = (tile / p.n_tiles) * rows, n0 = (tile % p.n_tiles) * BN;
+                const int m0 = CG2 ? (tile / p.n_tiles) * 2 * TC_BM + (int)rank * TC_BM : (tile / p.n_tiles) * rows;
+                const int n0 = (tile % p.n_tiles) * BN + (CG2 ? (int)rank * (BN / 2) : 0);
                 int f = 0;      // position in the tile's flattened k-block sequence
                 for (int s = 0; s < p.nsrc; ++s) {
                     // counts >= 2048 are rare: the hi plane of a COUNT operand is contracted only where this row tile has one
@@ -407,21 +442,29 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                             mbar_wait_parked(smem_u32(&bar_empty[stage]), phase ^ 1u);
                             const uint32_t full = smem_u32(&bar_full[stage]);
                             const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
+                            if constexpr (CG2) {     // both CTAs' loads complete on the leader's barrier
+                                const uint32_t full_leader = full & C2_PEER_MASK;
+                                if (rank == 0) mbar_expect_tx(full, 2u * tx);
+                                for (int pa = 0; pa < nA; ++pa) tma_load_2d_cg2(sa + pa * a_bytes, &maps.a[s][pa + pass], full_leader, kb * TC_BK, m0);
+                                for (int pb = 0; pb < 2; ++pb)
+                                    tma_load_2d_cg2(sa + (uint32_t)p.a_tiles * a_bytes + pb * B_TILE, &maps.b[s][pb], full_leader, kb * TC_BK, n0);
+                            } else {
                             mbar_expect_tx(full, tx);
                             for (int pa = 0; pa < nA; ++pa) tma_load_2d(sa + pa * a_bytes, &maps.a[s][pa + pass], full, kb * TC_BK, m0);
                             for (int pb = 0; pb < 2; ++pb)
                                 tma_load_2d(sa + (uint32_t)p.a_tiles * a_bytes + pb * B_TILE, &maps.b[s][pb], full, kb * TC_BK, n0);
+                            }
                             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                         }
                 }
             }
         }
     } else if (svc == 1) {
-        if (lane == 0) {
-            // ===================== MMA issuer
+        if (lane == 0 && rank == 0) {
+            // ===================== MMA issuer (CG2: the leader CTA issues for the pair)
             int stage = 0, astage = 0;
             uint32_t phase = 0, aphase = 0;
-            for (int it = 0, work; (work = tc_tile(p, it)) >= 0; ++it) {
+            for (int it = 0, work; (work = tc_tile(p, it, bid, nbid)) >= 0; ++it) {
                 int tile, klo, khi;
                 tc_split_range(p, work, tc_tile_kblocks(p, (p.ksplit > 1 ? work / p.ksplit : work) / p.n_tiles), tile, klo, khi);
                 const int m_blk = tile / p.n_tiles;
@@ -440,7 +483,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                     for (int kb = 0; kb < nkb; ++kb, ++f) {
                         if (f < klo || f >= khi) continue;
                         if (in_chunk == 0) {
-                            mbar_wait_backoff(smem_u32(&bar_tempty[astage]), aphase ^ 1u);
+                            mbar_wait_parked(smem_u32(&bar_tempty[astage]), aphase ^ 1u);
                             tc_fence_after();
                             tmem_d = tmem_base + (uint32_t)(astage * halves) * BN;
                             accumulate = 0;
@@ -456,16 +499,22 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                                 const uint32_t a0 = sa + (c >> 1) * a_bytes + h * TC_A_TILE, b0 = sb + (c & 1) * B_TILE;
 #pragma unroll
                                 for (int k = 0; k < TC_BK / 16; ++k)
+                                    if constexpr (CG2)
+                                        tc_mma_f16_cg2(tmem_d + h * BN, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), IDESC,
+                                                       (accumulate | (uint32_t)(c != __ffs(combos) - 1) | (uint32_t)k) ? 1u : 0u);
+                                    else
                                     tc_mma_f16(tmem_d + h * BN, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), IDESC,
                                                (accumulate | (uint32_t)(c != __ffs(combos) - 1) | (uint32_t)k) ? 1u : 0u);
                             }
                         }
                         accumulate = 1;
-                        tc_commit(smem_u32(&bar_empty[stage]));   // smem slot is free once these MMAs retire
+                        if constexpr (CG2) tc_commit_cg2(smem_u32(&bar_empty[stage]), 3);
+                        else tc_commit(smem_u32(&bar_empty[stage]));   // smem slot is free once these MMAs retire
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                         ++done;
                         if (++in_chunk == per || done == tkb) {
-                            tc_commit(smem_u32(&bar_tfull[astage]));      // chunk (or whole accumulator) ready for the epilogue warps
+                            if constexpr (CG2) tc_commit_cg2(smem_u32(&bar_tfull[astage]), 3);
+                            else tc_commit(smem_u32(&bar_tfull[astage]));      // chunk (or whole accumulator) ready for the epilogue warps
                             if (++astage == ASTAGES) { astage = 0; aphase ^= 1u; }
                             in_chunk = 0;
                         }
@@ -629,13 +678,14 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 astage = it % ASTAGES;
                 aphase = (uint32_t)(it / ASTAGES) & 1u;
             }
-            const int work = tc_tile(p, it);
+            const int work = tc_tile(p, it, bid, nbid);
             if (work < 0) break;
             int tile, klo, khi;
             tc_split_range(p, work, EK == 1 ? 0 : tc_tile_kblocks(p, (p.ksplit > 1 ? work / p.ksplit : work) / p.n_tiles), tile, klo, khi);
             const int64_t row_shift = p.ksplit > 1 ? (int64_t)(work % p.ksplit) * p.M : 0;    // split-K: slab of raw partial sums
             const int halves = (EK != 1 && p.pair) ? 2 : 1;
-            const int64_t m0 = (int64_t)(tile / p.n_tiles) * (TC_BM * halves), n0 = (int64_t)(tile % p.n_tiles) * BN;
+            const int64_t m0 = CG2 ? (int64_t)(tile / p.n_tiles) * (2 * TC_BM) + (int64_t)rank * TC_BM : (int64_t)(tile / p.n_tiles) * (TC_BM * halves);
+            const int64_t n0 = (int64_t)(tile % p.n_tiles) * BN;
             slice = (EK == 1 && SCDBM_NB_DYN) ? dyn_slice : ((warp >> 2) + it) % NS;
             if constexpr (EK == 1) {
                 // lo count plane: staged in the warp's shared-memory tile (zeroed here, patched by pass B, written
@@ -686,7 +736,7 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
 #pragma unroll
                     for (int i = 0; i < CW; ++i) sum[0][i] = sum[1][i] = 0.0f;
                     for (int c = 0; c < nch; ++c) {
-                        mbar_wait_epi(smem_u32(&bar_tfull[astage]), aphase);
+                        mbar_wait_parked(smem_u32(&bar_tfull[astage]), aphase);
                         tc_fence_after();
                         const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(astage * halves * BN + slice * CW);
 #pragma unroll
@@ -724,11 +774,11 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                         }
                     }
                 } else {
-                    mbar_wait_epi(smem_u32(&bar_tfull[astage]), aphase);
+                    mbar_wait_parked(smem_u32(&bar_tfull[astage]), aphase);
                     tc_fence_after();
                 }
             } else {
-                mbar_wait_epi(smem_u32(&bar_tfull[astage]), aphase);
+                mbar_wait_parked(smem_u32(&bar_tfull[astage]), aphase);
                 tc_fence_after();
             }
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(astage * halves * BN + slice * CW);
@@ -760,7 +810,10 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[astage]));
+                if (lane == 0) {
+                    if constexpr (CG2) mbar_arrive_cluster(smem_u32(&bar_tempty[astage]), 0);
+                    else mbar_arrive(smem_u32(&bar_tempty[astage]));
+                }
                 if (++astage == ASTAGES) { astage = 0; aphase ^= 1u; }
                 drain_all();
                 {   // coalesced write-out of the staged lo plane (undoing the word swizzle of each row)
@@ -822,10 +875,11 @@ __global__ void __launch_bounds__(32 * (4 + EPW), 1) k_gemm_tc(const __grid_cons
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG2) cluster_sync_all(); else __syncthreads();
     if (svc == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if constexpr (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -860,10 +914,11 @@ inline bool tc_supported(const GemmArgs& g, int nsrc) {
     return true;
 }
 
-template <int BN, int EK, int EPW>
+template <int BN, int EK, int EPW, bool CG2 = false>
 inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, int num_sms, cudaStream_t stream) {
-    const int slot = (EK == 1 && BN == TC_NBK_BN) ? 10 : (BN == 64 ? 0 : BN == 128 ? 4 : 8) + EK;   // wide NB kernel: slot 9
-    constexpr int B_TILE = BN * TC_BK * 2;
+    const int slot = CG2 ? 11 : (EK == 1 && BN == TC_NBK_BN) ? 10 : (BN == 64 ? 0 : BN == 128 ? 4 : 8) + EK;   // wide NB kernel: slot 9
+    constexpr int B_TILE = (CG2 ? BN / 2 : BN) * TC_BK * 2;
+    const int units = CG2 ? num_sms / 2 : num_sms;      // CTAs, or clusters of two
     const int qbytes = (EK == 1) ? EPW * tc_epi_smem(BN / (EPW / 4)) : 0;
     p.a_tiles = std::max(p.split_hi[0] ? 1 : p.nA[0], p.nsrc > 1 ? (p.split_hi[1] ? 1 : p.nA[1]) : 1);
     p.stage_bytes = p.a_tiles * (p.pair ? 2 : 1) * TC_A_TILE + 2 * B_TILE;
@@ -873,7 +928,7 @@ inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, i
     p.stages = std::max(1, std::min(p.stages, p.kblocks[0] * (p.split_hi[0] ? 2 : 1) + (p.nsrc > 1 ? p.kblocks[1] * (p.split_hi[1] ? 2 : 1) : 0)));
     const int smem = p.stages * p.stage_bytes + 1024 + qbytes;
     if (!t.attr_set[slot]) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, EK, EPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, EK, EPW, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e != cudaSuccess) return e;
         t.attr_set[slot] = true;
     }
@@ -881,17 +936,28 @@ inline cudaError_t tc_launch_bn(TcContext& t, const TcMaps& maps, TcParams& p, i
     // the sampling epilogue.  Other classes: flat order with the column tile fastest, so the CTAs that share a row tile
     // (A operand) stream it at the same time and the second reader hits L2 (owning it sequentially re-read A from
     // HBM: in pair mode 148 CTAs x 1 MB of A exceed the 126 MB L2).
-#ifdef SCDBM_OLD_SCHED
-    p.sched = (p.m_tiles >= num_sms && p.ksplit <= 1) ? 1 : 0;
-#else
-    p.sched = (EK == 1 && p.m_tiles >= num_sms && p.ksplit <= 1) ? 1 : 0;
-#endif
+    p.sched = (EK == 1 && p.m_tiles >= units && p.ksplit <= 1) ? 1 : 0;
     // Flat order, which operand is re-streamed from L2 / HBM?  Column tile fastest: the ~#SM concurrent tiles span all
     // weight tiles of one or two row tiles, so the weight planes are streamed once per row-tile group (AIS / PCD Gibbs at
     // C4: 16 384 x 20 000 x 1 024 read 3.3 GB of the 82 MB weight planes from HBM, ncu capture prof_r02_aisnb).  Row tile
     // fastest re-streams the state operand instead: chosen when that one is the smaller.
     p.mfast = (!p.sched && p.ksplit <= 1 && p.m_tiles > 1 && p.n_tiles > 1 && p.M * (int64_t)p.a_tiles < p.N * 2) ? 1 : 0;
-    const int grid = p.sched ? std::min(p.m_tiles, num_sms) : std::min(p.m_tiles * p.n_tiles * std::max(p.ksplit, 1), num_sms);
+    const int grid = p.sched ? std::min(p.m_tiles, units) : std::min(p.m_tiles * p.n_tiles * std::max(p.ksplit, 1), units);
+    if constexpr (CG2) {      // clusters of two CTAs (plain stream order: the cluster launch does not take the PDL attribute)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * grid);
+        cfg.blockDim = dim3(32 * (4 + EPW));
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, EK, EPW, CG2>, maps, p);
+    }
     return launch_pdl(k_gemm_tc<BN, EK, EPW>, dim3(grid), dim3(32 * (4 + EPW)), (size_t)smem, stream, maps, p);
 }
 
@@ -933,6 +999,9 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
     // latency-bound launches (a handful of tiles): 64-column tiles halve each epilogue warp's serial work and double the CTAs
     const bool few_tiles = ek != 1 && ((g.M + TC_BM - 1) / TC_BM) * ((g.N + 127) / 128) * std::max(ksplit, 1) * 4 <= num_sms;
     const bool long_k = ek == 1 && g.N >= TC_NBK_BN && (ops[0].K + TC_BK - 1) / TC_BK >= TC_NBK_MIN_KB;
+    // ... and two SMs per 256-row tile when there is at least one wave of such tiles
+    static const bool nb_cg2_on = [] { const char* v = getenv("SCDBM_NB_CG2"); return !(v && v[0] == '0'); }();
+    const bool nb_cg2 = long_k && nb_cg2_on && t.nb_cg2 && ((g.M + 2 * TC_BM - 1) / (2 * TC_BM)) * ((g.N + TC_NBK_BN - 1) / TC_NBK_BN) >= num_sms / 2;
     const int BN = (g.N <= 64 || few_tiles) ? 64 : long_k ? TC_NBK_BN : (ek == 1 && g.N >= TC_NB_BN) ? TC_NB_BN : 128;
     TcMaps maps;
     TcParams p;
@@ -942,12 +1011,10 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
     p.N = g.N;
     // pair mode: 256-row work tiles (two MMA row tiles per weight-tile load) when there is enough work to keep
     // every SM busy with pairs; the NB sampling kernel keeps single tiles (its two 224-column stages fill TMEM)
-    int max_kb = 0;
-    for (int s = 0; s < nsrc; ++s) max_kb += (int)((ops[s].K + TC_BK - 1) / TC_BK) * ((ops[s].a.p1 && ops[s].a.kind == MAT_COUNT) ? 2 : 1);
-    (void)max_kb;
     p.pair = (ek != 1 && g.M >= (int64_t)2 * TC_BM * num_sms) ? 1 : 0;
     const int rows_per_tile = p.pair ? 2 * TC_BM : TC_BM;
     p.m_tiles = (int)((g.M + rows_per_tile - 1) / rows_per_tile);
+    if (nb_cg2) p.m_tiles = (int)((g.M + 2 * TC_BM - 1) / (2 * TC_BM));     // cluster tiles; each CTA's TMA box stays 128 rows
     p.n_tiles = (int)((g.N + BN - 1) / BN);
     p.epi = g.epi;
     p.ksplit = ksplit;
@@ -961,8 +1028,8 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
         p.split_hi[s] = (a.p1 && a.kind == MAT_COUNT) ? 1 : 0;
         bool ok = tc_make_map(t, &maps.a[s][0], a.p0, g.M, ops[s].K, a.ld, rows_per_tile);
         ok = ok && tc_make_map(t, &maps.a[s][1], a.p1 ? a.p1 : a.p0, g.M, ops[s].K, a.ld, rows_per_tile);
-        ok = ok && tc_make_map(t, &maps.b[s][0], ops[s].b0, ops[s].N, ops[s].K, ops[s].ldb, BN);
-        ok = ok && tc_make_map(t, &maps.b[s][1], ops[s].b1, ops[s].N, ops[s].K, ops[s].ldb, BN);
+        ok = ok && tc_make_map(t, &maps.b[s][0], ops[s].b0, ops[s].N, ops[s].K, ops[s].ldb, nb_cg2 ? BN / 2 : BN);
+        ok = ok && tc_make_map(t, &maps.b[s][1], ops[s].b1, ops[s].N, ops[s].K, ops[s].ldb, nb_cg2 ? BN / 2 : BN);
         if (!ok) return cudaErrorInvalidValue;
     }
     if (nsrc == 1) { maps.a[1][0] = maps.a[0][0]; maps.a[1][1] = maps.a[0][1]; maps.b[1][0] = maps.b[0][0]; maps.b[1][1] = maps.b[0][1]; }
@@ -972,6 +1039,7 @@ inline cudaError_t launch_gemm_tc(TcContext& t, const TcOperandPlanes* ops, int 
         if (ek == 3) return tc_launch_bn<64, 3, 16>(t, maps, p, num_sms, stream);
         return tc_launch_bn<64, 0, 16>(t, maps, p, num_sms, stream);
     }
+    if (BN == TC_NBK_BN && ek == 1 && nb_cg2) return tc_launch_bn<TC_NBK_BN, 1, TC_NBK_EPW, true>(t, maps, p, num_sms, stream);
     if (BN == TC_NBK_BN && ek == 1) return tc_launch_bn<TC_NBK_BN, 1, TC_NBK_EPW>(t, maps, p, num_sms, stream);
     if (BN == TC_NB_BN && ek == 1) return tc_launch_bn<TC_NB_BN, 1, TC_NB_EPW>(t, maps, p, num_sms, stream);
     if (ek == 1) return tc_launch_bn<128, 1, 16>(t, maps, p, num_sms, stream);
@@ -1210,7 +1278,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_grad_tc(const __grid_constant
                 const int nch = (n + TC_CHUNK_KB - 1) / TC_CHUNK_KB;
                 const float sc = p.scale[s];
                 for (int c = 0; c < nch; ++c) {
-                    mbar_wait_epi(smem_u32(&bar_tfull[astage]), aphase);
+                    mbar_wait_parked(smem_u32(&bar_tfull[astage]), aphase);
                     tc_fence_after();
                     const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(astage * HALVES) * TG_BN + (uint32_t)(slice * 32);
 #pragma unroll

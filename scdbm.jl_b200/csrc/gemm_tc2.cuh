@@ -21,45 +21,6 @@ namespace scdbm {
 
 constexpr int C2_BN = 256, C2_EPW = 16, C2_CW = 64;
 constexpr int C2_B_TILE = 128 * TC_BK * 2;     // this CTA's half of one weight-plane tile: 128 output columns x 64 K
-constexpr uint32_t C2_PEER_MASK = 0xFEFFFFFFu; // clears the CTA-rank bit of a shared::cluster address -> the leader's copy
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar_leader, int32_t c0, int32_t c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar_leader), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit_cg2(uint32_t bar, uint16_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"(cta_mask)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
-        "r"(cta)
-        : "memory");
-}
-
 template <int EK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 + C2_EPW), 1)
     k_gemm_cg2(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
