@@ -540,8 +540,12 @@ def training_metrics(pkg, ctx, with_cpu=True):
     m = pkg.DeviceModel(ctx, [1000, 128], pkg.VIS_NEGBIN)
     m.init_layer(0, xm, seed=SEED)
     tr = pkg.RBMTrainer(m, 100, pcd=False)
-    for _ in range(3):
+    # warm-up by wall time: the host work above leaves the GPU idle long enough for its clocks to drop, and these
+    # launch-bound loops are over before they have ramped up again (a 3-epoch warm-up gave 840 ... 1490 C2 steps/s from run to run)
+    t_end = time.perf_counter() + 0.4
+    while time.perf_counter() < t_end:
         pkg.trainrbm_(m, xm, tr, 1e-4, 1)
+        ctx.sync()
     best = 1e30
     for _ in range(3):                      # best of 3 repetitions (host launch jitter)
         ctx.sync()
@@ -556,7 +560,10 @@ def training_metrics(pkg, ctx, with_cpu=True):
     dm = pkg.DeviceModel.from_host([pkg.NegativeBinomialBernoulliRBM(**layers[0]), pkg.BernoulliRBM(**layers[1])], ctx)
     x2m = pkg.Mat.from_host(ctx, x2, pkg.MAT_COUNT)
     p = pkg.DeviceParticles(dm, 100).init(False)
-    pkg.traindbm_(dm, x2m, epochs=3, particles=p, learningrate=1e-4, device=True, ctx=ctx)
+    t_end = time.perf_counter() + 0.4
+    while time.perf_counter() < t_end:
+        pkg.traindbm_(dm, x2m, epochs=3, particles=p, learningrate=1e-4, device=True, ctx=ctx)
+        ctx.sync()
     best = 1e30
     for _ in range(3):
         ctx.sync()
@@ -564,7 +571,7 @@ def training_metrics(pkg, ctx, with_cpu=True):
         pkg.traindbm_(dm, x2m, epochs=20, particles=p, learningrate=1e-4, device=True, ctx=ctx)
         best = min(best, ctx.timer_stop())
     out["C2_dbm_pcd_epochs_per_sec"] = 20 / (best * 1e-3)
-    out["note"] = "best of 3 x 20 epochs, CUDA events, data resident"
+    out["note"] = "0.4 s of untimed epochs, then best of 3 x 20 epochs, CUDA events, data resident"
     if with_cpu:
         from oracle import model as om, philox as px
         rng = px.Rng(SEED)
