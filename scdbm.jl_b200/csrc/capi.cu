@@ -9,6 +9,7 @@
 #include "comm.cuh"
 
 #include <algorithm>
+#include <functional>
 #include <atomic>
 #include <cmath>
 #include <cstring>
@@ -1461,8 +1462,11 @@ static void nccl_check(ncclResult_t r, const char* what) {
     if (r != ncclSuccess) throw Err(SCDBM_ECUDA, std::string(what) + ": " + nccl_api().GetErrorString(r));
 }
 
+// after_first_group: work that does not depend on the mean-field result, queued behind the first group of iterations
+// and before the host looks at the stopping rule -- while the host then decides and queues what follows, the GPU
+// still has that work to do (traindbm!: the Gibbs sweeps over the persistent particles)
 static void meanfield_impl(scdbm_model* m, const scdbm_mat* x, double eps, int maxiter, scdbm_particles* mu, int* niter,
-                           double* delta_out) {
+                           double* delta_out, const std::function<void()>& after_first_group = nullptr) {
     scdbm_ctx* c = m->ctx;
     const int nl = m->nlayers();
     const int64_t n = x->v.rows;
@@ -1522,6 +1526,7 @@ static void meanfield_impl(scdbm_model* m, const scdbm_mat* x, double eps, int m
     unsigned long long state = 0ull;
     skip = c->d_mf + 1;
     int launched = 0;
+    bool queued_extra = false;
     bool done = !(1.0 > eps);   // `delta = 1.0; while delta > eps` (dbmtraining.jl:194)
     float last_delta = done ? 1.0f : 0.0f;
     while (!done && launched < cap) {
@@ -1570,6 +1575,7 @@ static void meanfield_impl(scdbm_model* m, const scdbm_mat* x, double eps, int m
             c->launches++;
         }
         launched += group;
+        if (launched == group && after_first_group) { after_first_group(); queued_extra = true; }
         // poll the mapped state word: converged, or every check of this group executed
         for (unsigned int spins = 1;; ++spins) {
             const unsigned long long w = hm[0];
@@ -1584,6 +1590,7 @@ static void meanfield_impl(scdbm_model* m, const scdbm_mat* x, double eps, int m
         done = (hm[0] & 1ull) != 0ull;
         state = hm[1];
     }
+    if (!queued_extra && after_first_group) after_first_group();     // no iteration was launched at all
     const unsigned int delta_bits = (unsigned int)(state & 0xFFFFFFFFull);
     if (launched > 0) memcpy(&last_delta, &delta_bits, sizeof(float));
     if (niter) *niter = (int)(state >> 32);
@@ -2022,9 +2029,11 @@ static void dbm_pcd_step_impl(scdbm_model* m, const scdbm_mat* x, scdbm_particle
     REQUIRE(m && x && p && mu && o, "NULL argument");
     REQUIRE(p->model == m && mu->model == m && o->model == m, "objects belong to different models");
     REQUIRE(m->L.size() >= 2, "traindbm! needs at least two RBM layers");
-    gibbs_dbm_steps(m, p, nsteps, 1.0f);                       // dbmtraining.jl:290
+    // dbmtraining.jl:290-291: gibbssample!(particles), then meanfield(x).  The two are independent (particles vs mu), so
+    // the sweeps are queued behind the first group of mean-field iterations: same results, and the host's look at the
+    // stopping rule no longer leaves the GPU idle
     int it = 0;
-    meanfield_impl(m, x, eps, 0, mu, &it, nullptr);            // :291
+    meanfield_impl(m, x, eps, 0, mu, &it, nullptr, [&] { gibbs_dbm_steps(m, p, nsteps, 1.0f); });
     if (mf_iters) *mf_iters = it;
     const int64_t npos = global_npos > 0 ? global_npos : mu->n, nneg = global_nneg > 0 ? global_nneg : p->n;
     gradient_dbm(o, m, mu, p, 1.0f / (float)std::max<int64_t>(npos, 1), 1.0f / (float)std::max<int64_t>(nneg, 1));   // :293
