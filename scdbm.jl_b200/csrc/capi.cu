@@ -1621,7 +1621,7 @@ int32_t scdbm_opt_create(scdbm_model* m, scdbm_opt** out) {
         o->offB.push_back(off); off += L.H;
     }
     o->n = off;
-    CK(cudaMalloc(&o->buf, off * sizeof(float)));
+    CK(cudaMallocAsync(&o->buf, off * sizeof(float), m->ctx->stream));       // stream-ordered: no device-wide stall per traindbm! call
     CK(cudaMemsetAsync(o->buf, 0, off * sizeof(float), m->ctx->stream));
     *out = o;
     API_END
@@ -1629,8 +1629,8 @@ int32_t scdbm_opt_create(scdbm_model* m, scdbm_opt** out) {
 int32_t scdbm_opt_destroy(scdbm_opt* o) {
     API_BEGIN
     if (o) {
-        cudaStreamSynchronize(o->model->ctx->stream);
-        cudaFree(o->buf);
+        // (every exchange on the communication stream has been joined into the context's stream by the step that queued it)
+        cudaFreeAsync(o->buf, o->model->ctx->stream);
         scdbm_model* om_ = o->model;
         delete o;
         model_release(om_);
