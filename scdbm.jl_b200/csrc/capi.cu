@@ -1299,11 +1299,10 @@ int32_t scdbm_particles_create(scdbm_model* m, int64_t n, uint64_t row_offset, i
 int32_t scdbm_particles_destroy(scdbm_particles* p) {
     API_BEGIN
     if (!p) return SCDBM_OK;
-    cudaStreamSynchronize(p->model->ctx->stream);
-    for (auto* x : p->cur) mat_free(x);
+    for (auto* x : p->cur) mat_free(x);      // stream-ordered frees: work queued on the context's stream still sees the buffers
     for (auto* x : p->nxt) mat_free(x);
     mat_free(p->alias0);
-    cudaFree(p->hoist);
+    if (p->hoist) cudaFreeAsync(p->hoist, p->model->ctx->stream);
     scdbm_model* pm = p->model;
     delete p;
     model_release(pm);
@@ -1484,7 +1483,7 @@ static void meanfield_impl(scdbm_model* m, const scdbm_mat* x, double eps, int m
     if (n == 0 && !global_delta) { if (niter) *niter = 0; if (delta_out) *delta_out = 0; return; }
     // hoist x*W1 (loop invariant; the reference recomputes it, quirk B10)
     Layer& L0 = m->L[0];
-    if (!mu->hoist && n > 0) CK(cudaMalloc(&mu->hoist, (size_t)n * L0.H * sizeof(float)));
+    if (!mu->hoist && n > 0) CK(cudaMallocAsync(&mu->hoist, (size_t)n * L0.H * sizeof(float), c->stream));
     if (n > 0) {
         EpiParams e = epi_base(c);
         e.mode = EPI_RAW_F32;
