@@ -62,6 +62,9 @@ def main():
     xm = pkg.Mat.from_host(ctx, x[rows], pkg.MAT_COUNT)
     p = pkg.DeviceParticles(dm, pshard[rank], row_offset=poff).init(False)
     pkg.init_comm_from_torch(ctx)
+    # one untimed step: NCCL sets up its channels on the first collective, descriptors and workspaces are created
+    pkg.traindbm_(dm, xm, epochs=1, learningrate=1e-3, particles=p, global_nsamples=a.cells,
+                  global_nparticles=a.particles, device=True, ctx=ctx)
     dist.barrier()
     torch.cuda.synchronize()
     ctx.timer_start()
@@ -78,7 +81,7 @@ def main():
         dm1 = pkg.DeviceModel.from_host(host, ctx1)
         x1 = pkg.Mat.from_host(ctx1, x, pkg.MAT_COUNT)
         p1 = pkg.DeviceParticles(dm1, a.particles).init(False)
-        pkg.traindbm_(dm1, x1, epochs=a.steps, learningrate=1e-3, particles=p1, device=True, ctx=ctx1)
+        pkg.traindbm_(dm1, x1, epochs=a.steps + 1, learningrate=1e-3, particles=p1, device=True, ctx=ctx1)
         errs = []
         for l in range(len(host)):
             g, r = dm.get_layer(l), dm1.get_layer(l)
