@@ -1760,7 +1760,10 @@ static void gradient_dbm(scdbm_opt* o, scdbm_model* m, scdbm_particles* mu, scdb
         const MatView& v = l == 0 ? mu->alias0->v : mu->cur[l]->v;
         const MatView &vm = p->cur[l]->v, &h = mu->cur[l + 1]->v, &hm = p->cur[l + 1]->v;
         const int64_t nW = (int64_t)L.V * L.H;
-        const int nblk = (c->comm && nW >= (int64_t)(4 << 20)) ? 4 : 1;
+        // two row blocks: the allreduce of the first runs under the GEMM of the second; more blocks leave too few cluster
+        // tiles per launch (four blocks of the 20 000 x 1 024 layer: 80 tiles on 74 clusters)
+        static const int dp_blocks = [] { const char* v = getenv("SCDBM_DP_BLOCKS"); return v ? std::max(1, atoi(v)) : 2; }();
+        const int nblk = (c->comm && nW >= (int64_t)(4 << 20)) ? dp_blocks : 1;
         const int64_t step = round_up((L.V + nblk - 1) / nblk, 128);
         bool bias_done = false;
         for (int64_t v0 = 0; v0 < L.V; v0 += step) {
