@@ -83,6 +83,12 @@ def static_profile():
     return sp
 
 
+def sampler_max_mhz():
+    out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.max.sm", "--format=csv,noheader,nounits", "-i", "0"],
+                         capture_output=True, text=True, timeout=10).stdout.strip().splitlines()
+    return float(out[0]) if out else 0.0
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -212,7 +218,22 @@ def run_ours(args):
     if sp is not None:
         roofline["static_profile"] = sp
         if not sp.get("stale") and n == sp.get("chains"):
-            roofline["traffic"] = sp.get("nb_downsweep", {}).get("dram_bytes_per_launch")
+            nbp = sp.get("nb_downsweep", {})
+            roofline["traffic"] = nbp.get("dram_bytes_per_launch")
+            # what actually bounds the draw epilogue: warp-instruction issue.  Instruction count from the ncu capture of
+            # these sources, time from THIS run; peak = 4 schedulers x SMs x the SM clock nvidia-smi reports as maximum.
+            wi, num_sms, mhz = nbp.get("warp_instructions"), int(ctx.get("num_sms")), 1965.0
+            try:
+                mhz = float(sampler_max_mhz()) or mhz
+            except Exception:
+                pass
+            if wi:
+                peak_ips = 4.0 * num_sms * mhz * 1e6
+                roofline["issue_slots"] = {"warp_instructions_per_launch": wi, "achieved_gwips": wi / (k_ms * 1e-3) / 1e9,
+                                           "peak_gwips": peak_ips / 1e9, "frac": wi / (k_ms * 1e-3) / peak_ips,
+                                           "thread_instructions_per_draw": nbp.get("warp_instructions_per_draw_x32"),
+                                           "note": "instruction count (polls of waiting warps included) from the static ncu capture, "
+                                                   "launch time live; 7 warps per scheduler, 64 registers per thread"}
     # the deterministic part of the sweep for comparison: the dual-source up-sweep (h1 | v, h2), tensor-bound
     h1out = pkg.Mat(ctx, n, UNITS[1], pkg.MAT_BINARY)
     v0, h2 = p.layer(0), p.layer(2)
